@@ -1,0 +1,151 @@
+/*
+ * fadegpu.h -- C ABI of libfadegpu: the B200 (sm_100a) implementation of the soft-clip
+ * realignment hot path of `fade annotate` (blachlylab/fade).
+ *
+ * The reference has no FFI seam of its own: align_clip() calls dparasail and dhtslib directly
+ * (source/analysis.d:63,67).  This header therefore defines the seam at the narrowest cut that
+ * contains all heavy work, and each entry point names the reference code it replaces:
+ *
+ *   fadegpu_create            <- Parasail("ACTGN",10,2,2,-3) profile construction, source/anno.d:36,
+ *                                and the two numeric flags that reach the path, source/app.d:17-18
+ *   fadegpu_load_reference    <- IndexedFastaFile(args[2]) + every fai.fetchSequence(...).toUpper
+ *                                under the global mutex, source/anno.d:23, source/analysis.d:61-64
+ *   fadegpu_submit/_wait      <- the body of `foreach(rec; parallel(bam.allRecords))`,
+ *                                source/anno.d:44-50, i.e. per record steps a-d of align_clip:
+ *                                length floor (analysis.d:34), reverse complement (analysis.d:40,
+ *                                util.d:18-34), window arithmetic (analysis.d:45-59), window fetch
+ *                                (analysis.d:63), p.sw_striped (analysis.d:67), res.cigar
+ *                                (analysis.d:69) and the accept predicates (analysis.d:69-80,98-104)
+ *
+ * Everything above the seam (BAM/SAM decode, parse_clips on the read's CIGAR, the SA lookup, rs
+ * byte assembly, am/as/ar/ab string formatting, BAM encode, the CLI) stays on the host; see
+ * include/fadehost.h and INTEGRATION.md for the D binding.
+ *
+ * Conventions: plain C; every function returns 0 (FADEGPU_OK) or a negative fadegpu_status and
+ * never throws or aborts.  There is NO CPU fallback: without a CUDA device (or with the kernels
+ * failing to launch) calls fail with FADEGPU_E_CUDA / FADEGPU_E_NODEV.
+ * Threading: a ctx (and its batches) is driven by one host thread at a time; distinct ctxs may be
+ * driven concurrently.  All buffers handed out are owned by the library.
+ */
+#ifndef FADEGPU_H
+#define FADEGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FADEGPU_ABI_VERSION 1
+#define FADEGPU_MAX_OPS 32 /* CIGAR ops materialised per read (fade rejects > 10, analysis.d:69) */
+
+typedef enum {
+    FADEGPU_OK = 0,
+    FADEGPU_E_ARG = -1,   /* bad argument */
+    FADEGPU_E_CUDA = -2,  /* CUDA runtime / kernel failure */
+    FADEGPU_E_OOM = -3,   /* host or device allocation failed */
+    FADEGPU_E_STATE = -4, /* call sequence error (no reference, batch in flight, ...) */
+    FADEGPU_E_NODEV = -5  /* no usable CUDA device */
+} fadegpu_status;
+
+typedef struct fadegpu_ctx fadegpu_ctx;     /* opaque; one per (host thread, GPU) */
+typedef struct fadegpu_batch fadegpu_batch; /* opaque; pinned host + device buffers */
+
+typedef struct fadegpu_params {
+    int32_t window_size;   /* --window-size, source/app.d:18, default 300 */
+    int32_t min_length;    /* --min-length,  source/app.d:17, default 5   */
+    int32_t gap_open;      /* 10  source/anno.d:36 */
+    int32_t gap_extend;    /* 2   */
+    int32_t match;         /* 2   */
+    int32_t mismatch;      /* -3  */
+    uint32_t flags;        /* FADEGPU_F_* */
+    int64_t scratch_bytes; /* cap on the device checkpoint scratch per launch; 0 = default */
+} fadegpu_params;
+
+/* params.flags */
+#define FADEGPU_F_FORCE_GENERIC 1u /* route every alignment through the generic (slow) kernel */
+
+/* per-read result flags */
+#define FADEGPU_R_ALIGNED 1u    /* SW ran for this read (some clip passed the length floor) */
+#define FADEGPU_R_ART_LEFT 2u   /* status.art_left  (analysis.d:82)  */
+#define FADEGPU_R_ART_RIGHT 4u  /* status.art_right (analysis.d:106) */
+#define FADEGPU_R_OPS_TRUNC 8u  /* n_ops > FADEGPU_MAX_OPS, only the first ones are materialised */
+#define FADEGPU_R_GENERIC 16u   /* served by the generic kernel (wildcard letters / odd sizes) */
+
+/* Struct-of-arrays view of a batch.  Inputs are filled by the caller before fadegpu_submit;
+ * outputs are valid after fadegpu_wait until the next submit of the same batch. */
+typedef struct fadegpu_batch_view {
+    int64_t max_reads, max_seq_bytes;
+    /* ---- inputs ---- */
+    uint8_t *seq4;        /* BAM 4-bit packed bases exactly as in bam1_t (util.d:25,31), reads concatenated */
+    int64_t *seq_off;     /* [n+1] byte offset of read k's bases inside seq4 */
+    int32_t *l_qseq;      /* [n] rec.length */
+    int32_t *tid;         /* [n] rec.tid (contig index of fadegpu_load_reference) */
+    int64_t *pos;         /* [n] rec.pos, 0-based */
+    int32_t *aligned_len; /* [n] rec.cigar.alignedLength (reference span), analysis.d:53 */
+    int32_t *clip_left;   /* [n] parse_clips(rec.cigar)[0].length, 0 = none or early-out record */
+    int32_t *clip_right;  /* [n] parse_clips(rec.cigar)[1].length */
+    /* ---- outputs ---- */
+    uint8_t *flags;       /* [n] FADEGPU_R_* */
+    int32_t *score;       /* [n] res.score */
+    int32_t *beg_query;   /* [n] */
+    int32_t *end_query;   /* [n] */
+    int32_t *beg_ref;     /* [n] res.position, window relative */
+    int32_t *end_ref;     /* [n] */
+    int64_t *win_start;   /* [n] `start` of analysis.d:45-51; am POS = win_start + beg_ref */
+    int32_t *n_ops;       /* [n] res.cigar.length including the S padding */
+    uint32_t *ops;        /* [n * FADEGPU_MAX_OPS] BAM-encoded (len<<4|op), forward order */
+} fadegpu_batch_view;
+
+typedef struct fadegpu_stats {
+    int64_t n_reads;          /* reads in the last submit */
+    int64_t n_aligned;        /* reads for which SW ran (once per read) */
+    int64_t n_generic;        /* of those, served by the generic kernel */
+    int64_t cells;            /* sum qlen*tlen over aligned reads (counted once per read) */
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t kernel_launches;  /* kernels launched by the last submit */
+    float kernel_ms;          /* device time of all kernels of the last submit (CUDA events) */
+    float fill_ms, trace_ms, generic_ms; /* per-stage device time (events on the ctx stream) */
+    float total_ms;           /* H2D + kernels + D2H device time */
+    int64_t scratch_bytes;    /* checkpoint scratch used */
+} fadegpu_stats;
+
+int fadegpu_abi_version(void);
+int fadegpu_device_count(int *n);
+int fadegpu_default_params(fadegpu_params *p);
+int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out);
+void fadegpu_destroy(fadegpu_ctx *ctx);
+/* ctx may be NULL: returns the calling thread's last error outside any ctx */
+const char *fadegpu_last_error(const fadegpu_ctx *ctx);
+
+/* Host ASCII contigs (any case, any letters) are packed (2-bit + N plane + wildcard plane) and
+ * uploaded once; the reference then stays resident in HBM.  Replaces anno.d:23 + analysis.d:61-64. */
+int fadegpu_load_reference(fadegpu_ctx *ctx, int32_t n_contigs, const char *const *names,
+                           const int64_t *lengths, const char *const *seqs);
+/* Optional: device-to-device copy (NVLink peer copy when available) of src's packed reference. */
+int fadegpu_share_reference(fadegpu_ctx *dst, const fadegpu_ctx *src);
+int fadegpu_reference_info(const fadegpu_ctx *ctx, int32_t *n_contigs, int64_t *total_bases,
+                           int64_t *device_bytes);
+
+int fadegpu_alloc_batch(fadegpu_ctx *ctx, int64_t max_reads, int64_t max_seq_bytes,
+                        fadegpu_batch **out);
+int fadegpu_get_batch_view(fadegpu_batch *b, fadegpu_batch_view *view);
+void fadegpu_free_batch(fadegpu_batch *b);
+
+/* Asynchronous: host binning, H2D, kernels and D2H are queued on the ctx stream. */
+int fadegpu_submit(fadegpu_ctx *ctx, fadegpu_batch *b, int64_t n_reads);
+/* Blocks until the batch is done and scatters the results into the view's output arrays. */
+int fadegpu_wait(fadegpu_ctx *ctx, fadegpu_batch *b);
+
+/* Measurement helpers (bench.py): stats of the last submit, and a re-run of ONLY the kernels on
+ * the inputs already resident in HBM (no host work, no copies), timed with CUDA events on the ctx
+ * stream.  ms_out receives the device milliseconds of `iters` passes. */
+int fadegpu_get_stats(const fadegpu_batch *b, fadegpu_stats *s);
+int fadegpu_replay_kernels(fadegpu_ctx *ctx, fadegpu_batch *b, int32_t iters, float *ms_out);
+
+/* INT16x2 ALU roofline denominator: measures packed VIMNMX/VIADDMNMX issue rate.
+ * ops_per_sec_out = packed (2-lane) instructions * 32 threads per second over the whole GPU. */
+int fadegpu_measure_alu_peak(fadegpu_ctx *ctx, double *ops_per_sec_out, double *sm_clock_mhz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
