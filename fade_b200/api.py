@@ -1,0 +1,261 @@
+"""Python host layer over the C ABI: Context / Batch wrappers and an `annotate_records` loop that
+mirrors source/anno.d:44-50 + annotateTask (source/anno.d:55-110) in batched form."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from ._lib import BatchView, FadeGpuError, HostRecord, Params, Stats, lib
+
+MAX_OPS = 32
+R_ALIGNED, R_ART_LEFT, R_ART_RIGHT, R_OPS_TRUNC, R_GENERIC = 1, 2, 4, 8, 16
+F_FORCE_GENERIC = 1
+OPCHARS = "MIDNSHP=XB"
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    rc = lib().fadegpu_default_params(C.byref(p))
+    if rc:
+        raise FadeGpuError(rc, "fadegpu_default_params")
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = lib().fadegpu_device_count(C.byref(n))
+    if rc:
+        raise FadeGpuError(rc, lib().fadegpu_last_error(None).decode())
+    return n.value
+
+
+def _np_view(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    addr = C.cast(ptr, C.c_void_p).value
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(addr)
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+class Context:
+    """One per (host thread, GPU): scoring profile + device-resident packed reference.
+    Replaces Parasail("ACTGN",10,2,2,-3) (anno.d:36) and IndexedFastaFile (anno.d:23)."""
+
+    def __init__(self, device: int = 0, params: Params | None = None):
+        self._h = C.c_void_p()
+        self.params = params or default_params()
+        rc = lib().fadegpu_create(device, C.byref(self.params), C.byref(self._h))
+        if rc:
+            raise FadeGpuError(rc, lib().fadegpu_last_error(None).decode())
+        self.device = device
+        self.contig_names: list[str] = []
+
+    def _check(self, rc: int):
+        if rc:
+            raise FadeGpuError(rc, lib().fadegpu_last_error(self._h).decode())
+
+    def load_reference(self, names: list[str], seqs: list[bytes]):
+        n = len(seqs)
+        cn = (C.c_char_p * n)(*[s.encode() for s in names])
+        cs = (C.c_char_p * n)(*seqs)
+        ln = (C.c_int64 * n)(*[len(s) for s in seqs])
+        self._check(lib().fadegpu_load_reference(self._h, n, cn, ln, cs))
+        self.contig_names = list(names)
+
+    def share_reference_from(self, other: "Context"):
+        self._check(lib().fadegpu_share_reference(self._h, other._h))
+        self.contig_names = list(other.contig_names)
+
+    def reference_info(self):
+        a, b, c = C.c_int32(), C.c_int64(), C.c_int64()
+        self._check(lib().fadegpu_reference_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def measure_alu_peak(self):
+        ops, mhz = C.c_double(), C.c_double()
+        self._check(lib().fadegpu_measure_alu_peak(self._h, C.byref(ops), C.byref(mhz)))
+        return ops.value, mhz.value
+
+    def alloc_batch(self, max_reads: int, max_seq_bytes: int) -> "Batch":
+        return Batch(self, max_reads, max_seq_bytes)
+
+    def close(self):
+        if self._h:
+            lib().fadegpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """Pinned struct-of-arrays buffers (numpy views) + device mirrors, owned by the library."""
+
+    def __init__(self, ctx: Context, max_reads: int, max_seq_bytes: int):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        ctx._check(lib().fadegpu_alloc_batch(ctx._h, max_reads, max_seq_bytes, C.byref(self._h)))
+        v = BatchView()
+        ctx._check(lib().fadegpu_get_batch_view(self._h, C.byref(v)))
+        self.max_reads, self.max_seq_bytes = max_reads, max_seq_bytes
+        n = max_reads
+        self.seq4 = _np_view(v.seq4, max_seq_bytes, np.uint8)
+        self.seq_off = _np_view(v.seq_off, n + 1, np.int64)
+        self.l_qseq = _np_view(v.l_qseq, n, np.int32)
+        self.tid = _np_view(v.tid, n, np.int32)
+        self.pos = _np_view(v.pos, n, np.int64)
+        self.aligned_len = _np_view(v.aligned_len, n, np.int32)
+        self.clip_left = _np_view(v.clip_left, n, np.int32)
+        self.clip_right = _np_view(v.clip_right, n, np.int32)
+        self.flags = _np_view(v.flags, n, np.uint8)
+        self.score = _np_view(v.score, n, np.int32)
+        self.beg_query = _np_view(v.beg_query, n, np.int32)
+        self.end_query = _np_view(v.end_query, n, np.int32)
+        self.beg_ref = _np_view(v.beg_ref, n, np.int32)
+        self.end_ref = _np_view(v.end_ref, n, np.int32)
+        self.win_start = _np_view(v.win_start, n, np.int64)
+        self.n_ops = _np_view(v.n_ops, n, np.int32)
+        self.ops = _np_view(v.ops, n * MAX_OPS, np.uint32).reshape(n, MAX_OPS)
+        self.n = 0
+
+    def fill(self, seq4, seq_off, l_qseq, tid, pos, aligned_len, clip_left, clip_right):
+        n = len(l_qseq)
+        if n > self.max_reads or int(seq_off[n]) > self.max_seq_bytes:
+            raise ValueError("batch too small")
+        self.seq4[:int(seq_off[n])] = seq4[:int(seq_off[n])]
+        self.seq_off[:n + 1] = seq_off[:n + 1]
+        self.l_qseq[:n] = l_qseq
+        self.tid[:n] = tid
+        self.pos[:n] = pos
+        self.aligned_len[:n] = aligned_len
+        self.clip_left[:n] = clip_left
+        self.clip_right[:n] = clip_right
+        self.n = n
+        return self
+
+    def submit(self, n: int | None = None):
+        if n is not None:
+            self.n = n
+        self.ctx._check(lib().fadegpu_submit(self.ctx._h, self._h, self.n))
+
+    def wait(self):
+        self.ctx._check(lib().fadegpu_wait(self.ctx._h, self._h))
+
+    def run(self, n: int | None = None):
+        self.submit(n)
+        self.wait()
+        return self
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self.ctx._check(lib().fadegpu_get_stats(self._h, C.byref(s)))
+        return s
+
+    def replay_kernels(self, iters: int = 1) -> float:
+        ms = C.c_float()
+        self.ctx._check(lib().fadegpu_replay_kernels(self.ctx._h, self._h, iters, C.byref(ms)))
+        return ms.value
+
+    def cigar(self, r: int) -> str:
+        k = min(int(self.n_ops[r]), MAX_OPS)
+        return "".join(f"{int(o) >> 4}{OPCHARS[int(o) & 0xf]}" for o in self.ops[r, :k])
+
+    def close(self):
+        if self._h:
+            lib().fadegpu_free_batch(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class Record:
+    """The fields of a SAM/BAM record that annotateTask reads (dhtslib SAMRecord subset)."""
+    qname: str
+    flag: int
+    tid: int
+    pos: int                 # 0-based
+    cigar: np.ndarray        # uint32 BAM-encoded
+    seq4: np.ndarray         # uint8 BAM packed bases
+    qual: np.ndarray         # uint8 raw phred
+    l_qseq: int
+    has_sa: bool = False
+    tags: dict = field(default_factory=dict)   # filled by annotate_records: rs, am, as, ar, ab
+
+
+def _host_record(rec: Record):
+    cg = np.ascontiguousarray(rec.cigar, dtype=np.uint32)
+    s4 = np.ascontiguousarray(rec.seq4, dtype=np.uint8)
+    ql = np.ascontiguousarray(rec.qual, dtype=np.uint8)
+    hr = HostRecord(rec.flag, int(rec.has_sa), cg.ctypes.data_as(C.POINTER(C.c_uint32)), len(cg),
+                    s4.ctypes.data_as(C.POINTER(C.c_uint8)), ql.ctypes.data_as(C.POINTER(C.c_uint8)),
+                    rec.l_qseq, rec.tid, rec.pos)
+    return hr, (cg, s4, ql)
+
+
+def annotate_records(ctx: Context, records: list[Record], batch: Batch | None = None) -> list[Record]:
+    """Batched equivalent of `foreach(rec; parallel(bam.allRecords)) annotateTask(...)`
+    (source/anno.d:44-50): every record gets tags['rs'], artifact records also am/as/ar/ab."""
+    L = lib()
+    n = len(records)
+    total_seq = sum((r.l_qseq + 1) // 2 for r in records)
+    own = batch is None
+    if own:
+        batch = ctx.alloc_batch(max(n, 1), max(total_seq, 16))
+    hrs, keep, prep = [], [], []
+    off = 0
+    for k, rec in enumerate(records):
+        hr, refs = _host_record(rec)
+        hrs.append(hr)
+        keep.append(refs)
+        al, cl, cr, rs = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint8()
+        L.fadehost_prepare(C.byref(hr), C.byref(al), C.byref(cl), C.byref(cr), C.byref(rs))
+        prep.append((al.value, cl.value, cr.value, rs.value))
+        nb = (rec.l_qseq + 1) // 2
+        batch.seq_off[k] = off
+        batch.seq4[off:off + nb] = refs[1][:nb]
+        off += nb
+        batch.l_qseq[k] = rec.l_qseq
+        batch.tid[k] = rec.tid
+        batch.pos[k] = rec.pos
+        batch.aligned_len[k] = al.value
+        batch.clip_left[k] = cl.value
+        batch.clip_right[k] = cr.value
+    batch.seq_off[n] = off
+    batch.run(n)
+    for k, rec in enumerate(records):
+        al, cl, cr, rs = prep[k]
+        cap = 4 * rec.l_qseq + 256 + (len(ctx.contig_names[rec.tid]) if 0 <= rec.tid < len(ctx.contig_names) else 0)
+        am, as_, ar, ab = (C.create_string_buffer(cap) for _ in range(4))
+        rs_out = C.c_uint8()
+        name = ctx.contig_names[rec.tid].encode() if 0 <= rec.tid < len(ctx.contig_names) else b""
+        ops = np.ascontiguousarray(batch.ops[k])
+        rc = L.fadehost_finish(C.byref(hrs[k]), name, rs, cl, cr, al, int(batch.flags[k]), int(batch.win_start[k]),
+                               int(batch.beg_ref[k]), int(batch.n_ops[k]), ops.ctypes.data_as(C.POINTER(C.c_uint32)),
+                               C.byref(rs_out), am, as_, ar, ab, cap)
+        if rc < 0:
+            raise FadeGpuError(rc, "fadehost_finish: buffer too small")
+        rec.tags = {"rs": rs_out.value}
+        if rc == 1:
+            rec.tags.update(am=am.value.decode(), ar=ar.value.decode(), ab=ab.value.decode())
+            rec.tags["as"] = as_.value.decode()
+    if own:
+        batch.close()
+    return records

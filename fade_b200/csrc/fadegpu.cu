@@ -1,0 +1,763 @@
+// fadegpu.cu -- C ABI (include/fadegpu.h) and host runtime of libfadegpu: contexts, packed
+// reference upload, pinned batch buffers, length binning, launch planning, result scatter.
+//
+// Host-side work that mirrors the reference: the length floor of source/analysis.d:34 and the
+// window arithmetic of source/analysis.d:45-59 (both trivially cheap) are evaluated here while
+// building the alignment descriptors; everything else of align_clip runs in kernels.cu.
+// There is no CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../../include/fadegpu.h"
+#include "kernels.cuh"
+
+using namespace fade;
+
+static_assert(FADEGPU_MAX_OPS == OPS_CAP, "ABI ops capacity must match the kernels");
+static_assert(sizeof(AlnOut) == 32 + 4 * OPS_CAP, "AlnOut layout");
+static_assert(sizeof(AlnDesc) == 40, "AlnDesc layout");
+
+static thread_local std::string g_last_error;
+
+struct fadegpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    fadegpu_params p{};
+    SwConsts k{};
+    // reference
+    int32_t n_contigs = 0;
+    std::vector<std::string> names;
+    std::vector<int64_t> clen, coff;
+    int64_t total_bases = 0, padded_bases = 0;
+    uint32_t *d_two = nullptr, *d_n = nullptr, *d_x = nullptr;
+    int64_t *d_xpos = nullptr;
+    uint8_t *d_xchr = nullptr;
+    int64_t n_x = 0;
+    size_t ref_bytes = 0;
+    // scratch shared by all batches of the ctx (one stream -> serialised)
+    uint32_t *d_ck = nullptr;
+    size_t ck_bytes = 0;
+    uint8_t *d_gen = nullptr;
+    size_t gen_bytes = 0;
+    unsigned int *d_cursor = nullptr;
+    uint32_t *d_alu = nullptr;
+    std::string err;
+};
+
+struct Launch {
+    int R;            // 13/19/32 = packed kernels, 0 = generic list
+    int aln_first, n_aln;
+    int item_first, n_items;
+    int tw_stride;
+    int qmax, tmax;   // generic only
+};
+
+struct fadegpu_batch {
+    fadegpu_ctx *ctx = nullptr;
+    fadegpu_batch_view v{};
+    // staging (pinned) and device mirrors
+    AlnDesc *h_aln = nullptr, *d_aln = nullptr;
+    WarpItem *h_items = nullptr, *d_items = nullptr;
+    uint8_t *h_seq = nullptr, *d_seq = nullptr;
+    AlnOut *h_out = nullptr, *d_out = nullptr;
+    uint32_t *d_flags = nullptr;
+    uint2 *d_fillres = nullptr;
+    int64_t cap_items = 0, cap_seq = 0;
+    std::vector<Launch> plan;
+    int64_t n_reads = 0, n_aln = 0, n_items = 0, seq_bytes = 0;
+    int qmax_all = 0, tmax_all = 0;
+    fadegpu_stats st{};
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };  // start, after H2D, after kernels, after D2H
+    bool in_flight = false;
+    // scratch for the host binning
+    std::vector<int32_t> tmp_cls, tmp_tlen;
+    std::vector<int64_t> tmp_start;
+};
+
+namespace {
+
+int fail(fadegpu_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+int cuda_fail(fadegpu_ctx *ctx, cudaError_t e, const char *what)
+{
+    std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+    return fail(ctx, e == cudaErrorMemoryAllocation ? FADEGPU_E_OOM : FADEGPU_E_CUDA, m);
+}
+
+#define CU(ctx, call)                                              \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+template <typename T>
+void free_host(T *&p) { if (p) cudaFreeHost(p); p = nullptr; }
+template <typename T>
+void free_dev(T *&p) { if (p) cudaFree(p); p = nullptr; }
+
+void free_reference(fadegpu_ctx *c)
+{
+    free_dev(c->d_two); free_dev(c->d_n); free_dev(c->d_x); free_dev(c->d_xpos); free_dev(c->d_xchr);
+    c->n_x = 0; c->ref_bytes = 0; c->n_contigs = 0; c->total_bases = c->padded_bases = 0;
+    c->names.clear(); c->clen.clear(); c->coff.clear();
+}
+
+RefDev ref_dev(const fadegpu_ctx *c)
+{
+    RefDev r;
+    r.planes.two = c->d_two; r.planes.nmask = c->d_n; r.planes.xmask = c->d_x;
+    r.xpos = c->d_xpos; r.xchr = c->d_xchr; r.n_x = c->n_x;
+    return r;
+}
+
+int class_of(const fadegpu_ctx *c, int qlen, int tlen)
+{
+    if (c->p.flags & FADEGPU_F_FORCE_GENERIC) return 0;
+    if (qlen > QMAX_FAST || tlen > TMAX_FAST) return 0;
+    if (qlen <= FG * 13) return 13;
+    if (qlen <= FG * 19) return 19;
+    return 32;
+}
+
+size_t ck_words_of(int R) { return (size_t)(2 * R + 2); }
+
+int ensure_ck(fadegpu_ctx *c, size_t bytes)
+{
+    if (bytes <= c->ck_bytes) return 0;
+    free_dev(c->d_ck);
+    c->ck_bytes = 0;
+    CU(c, cudaMalloc(&c->d_ck, bytes));
+    c->ck_bytes = bytes;
+    return 0;
+}
+
+int ensure_gen(fadegpu_ctx *c, size_t bytes)
+{
+    if (bytes <= c->gen_bytes) return 0;
+    free_dev(c->d_gen);
+    c->gen_bytes = 0;
+    CU(c, cudaMalloc(&c->d_gen, bytes));
+    c->gen_bytes = bytes;
+    return 0;
+}
+
+constexpr int GEN_SLOTS_MAX = 8192;
+constexpr size_t GEN_BUDGET = (size_t)4 << 30;
+
+size_t gen_slot_bytes(int qmax, int tmax)
+{
+    size_t b = (size_t)8 * qmax + (((size_t)qmax + 15) & ~(size_t)15) + (size_t)qmax * tmax;
+    return (b + 15) & ~(size_t)15;
+}
+
+// queue every kernel of the batch's plan on the ctx stream; stage times via optional events
+int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, float *gen_ms, int *launches)
+{
+    const bool timed = fill_ms != nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    if (timed) {
+        CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1)); CU(c, cudaEventCreate(&e2));
+        *fill_ms = *trace_ms = *gen_ms = 0.f;
+    }
+    int nl = 0;
+    if (b->n_aln > 0) CU(c, cudaMemsetAsync(b->d_flags, 0, (size_t)b->n_aln * sizeof(uint32_t), c->stream));
+    for (const Launch &L : b->plan) {
+        if (L.R != 0) {
+            KernelArgs a;
+            a.aln = b->d_aln + L.aln_first;
+            a.n_aln = L.n_aln;
+            a.items = b->d_items + L.item_first;
+            a.n_items = L.n_items;
+            a.seq = b->d_seq;
+            a.ref = ref_dev(c);
+            a.ck = c->d_ck;
+            a.fillres = b->d_fillres + (size_t)L.item_first * 32;
+            a.aln_flags = b->d_flags + L.aln_first;
+            a.out = b->d_out + L.aln_first;
+            a.k = c->k;
+            a.min_length = c->p.min_length;
+            a.tw_stride = L.tw_stride;
+            if (timed) CU(c, cudaEventRecord(e0, c->stream));
+            CU(c, launch_fill(L.R, a, c->stream));
+            if (timed) CU(c, cudaEventRecord(e1, c->stream));
+            CU(c, launch_trace(L.R, a, c->stream));
+            nl += 2;
+            // wildcard letters found by the packed kernels -> generic kernel over the flagged ones
+            GenericArgs ga;
+            ga.aln = a.aln; ga.n_aln = L.n_aln; ga.aln_flags = a.aln_flags; ga.seq = b->d_seq; ga.ref = a.ref;
+            ga.out = a.out; ga.cursor = c->d_cursor; ga.scratch = c->d_gen;
+            ga.qmax = L.qmax; ga.tmax = L.tmax;
+            ga.slot_bytes = (int64_t)gen_slot_bytes(L.qmax, L.tmax);
+            ga.n_slots = (int)std::max<size_t>(1, std::min<size_t>(GEN_SLOTS_MAX, c->gen_bytes / (size_t)ga.slot_bytes));
+            ga.chunk = 64;
+            ga.open = c->p.gap_open; ga.extend = c->p.gap_extend; ga.match = c->p.match; ga.mismatch = c->p.mismatch;
+            ga.min_length = c->p.min_length;
+            if (timed) CU(c, cudaEventRecord(e2, c->stream));
+            CU(c, cudaMemsetAsync(c->d_cursor, 0, sizeof(unsigned int), c->stream));
+            CU(c, launch_generic(ga, ga.n_slots, c->stream));
+            nl += 1;
+            if (timed) {
+                cudaEvent_t e3;
+                CU(c, cudaEventCreate(&e3));
+                CU(c, cudaEventRecord(e3, c->stream));
+                CU(c, cudaEventSynchronize(e3));
+                float t;
+                cudaEventElapsedTime(&t, e0, e1); *fill_ms += t;
+                cudaEventElapsedTime(&t, e1, e2); *trace_ms += t;
+                cudaEventElapsedTime(&t, e2, e3); *gen_ms += t;
+                cudaEventDestroy(e3);
+            }
+        } else {
+            GenericArgs ga;
+            ga.aln = b->d_aln + L.aln_first; ga.n_aln = L.n_aln; ga.aln_flags = nullptr; ga.seq = b->d_seq;
+            ga.ref = ref_dev(c); ga.out = b->d_out + L.aln_first; ga.cursor = c->d_cursor; ga.scratch = c->d_gen;
+            ga.qmax = L.qmax; ga.tmax = L.tmax;
+            ga.slot_bytes = (int64_t)gen_slot_bytes(L.qmax, L.tmax);
+            ga.n_slots = (int)std::max<size_t>(1, std::min<size_t>(GEN_SLOTS_MAX, c->gen_bytes / (size_t)ga.slot_bytes));
+            ga.n_slots = std::min(ga.n_slots, std::max(L.n_aln, 1));
+            ga.chunk = 1;
+            ga.open = c->p.gap_open; ga.extend = c->p.gap_extend; ga.match = c->p.match; ga.mismatch = c->p.mismatch;
+            ga.min_length = c->p.min_length;
+            if (timed) CU(c, cudaEventRecord(e0, c->stream));
+            CU(c, cudaMemsetAsync(c->d_cursor, 0, sizeof(unsigned int), c->stream));
+            CU(c, launch_generic(ga, ga.n_slots, c->stream));
+            nl += 1;
+            if (timed) {
+                CU(c, cudaEventRecord(e1, c->stream));
+                CU(c, cudaEventSynchronize(e1));
+                float t;
+                cudaEventElapsedTime(&t, e0, e1); *gen_ms += t;
+            }
+        }
+    }
+    if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
+    if (launches) *launches = nl;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fadegpu_abi_version(void) { return FADEGPU_ABI_VERSION; }
+
+int fadegpu_device_count(int *n)
+{
+    if (!n) return fail(nullptr, FADEGPU_E_ARG, "fadegpu_device_count: null argument");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *n = 0; return cuda_fail(nullptr, e, "cudaGetDeviceCount"); }
+    *n = c;
+    return FADEGPU_OK;
+}
+
+int fadegpu_default_params(fadegpu_params *p)
+{
+    if (!p) return fail(nullptr, FADEGPU_E_ARG, "fadegpu_default_params: null argument");
+    p->window_size = 300;  // source/app.d:18
+    p->min_length = 5;     // source/app.d:17
+    p->gap_open = 10;      // source/anno.d:36
+    p->gap_extend = 2;
+    p->match = 2;
+    p->mismatch = -3;
+    p->flags = 0;
+    p->scratch_bytes = 0;
+    return FADEGPU_OK;
+}
+
+const char *fadegpu_last_error(const fadegpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
+{
+    if (!out) return fail(nullptr, FADEGPU_E_ARG, "fadegpu_create: null out");
+    *out = nullptr;
+    fadegpu_params pp;
+    fadegpu_default_params(&pp);
+    if (p) pp = *p;
+    if (pp.gap_open < pp.gap_extend || pp.gap_extend <= 0 || pp.match <= 0 || pp.mismatch > 0 ||
+        pp.match > 100 || pp.mismatch < -100 || pp.gap_open > 1000 || pp.window_size < 0)
+        return fail(nullptr, FADEGPU_E_ARG, "fadegpu_create: unsupported scoring / window parameters");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(nullptr, FADEGPU_E_NODEV, std::string("fadegpu_create: no CUDA device (") +
+                                                  (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") + "); there is no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, FADEGPU_E_ARG, "fadegpu_create: bad device index");
+    fadegpu_ctx *c = new (std::nothrow) fadegpu_ctx();
+    if (!c) return fail(nullptr, FADEGPU_E_OOM, "fadegpu_create: out of host memory");
+    c->device = device;
+    c->p = pp;
+    if (c->p.scratch_bytes <= 0) c->p.scratch_bytes = (int64_t)8 << 30;
+    c->k = make_consts(pp.gap_open, pp.gap_extend, pp.match, pp.mismatch);
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_cursor, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&c->d_alu, 64)) != cudaSuccess) {
+        int rc = cuda_fail(nullptr, e, "fadegpu_create");
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return FADEGPU_OK;
+}
+
+void fadegpu_destroy(fadegpu_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_reference(c);
+    free_dev(c->d_ck); free_dev(c->d_gen); free_dev(c->d_cursor); free_dev(c->d_alu);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int fadegpu_load_reference(fadegpu_ctx *c, int32_t n_contigs, const char *const *names,
+                           const int64_t *lengths, const char *const *seqs)
+{
+    if (!c) return fail(nullptr, FADEGPU_E_ARG, "fadegpu_load_reference: null ctx");
+    if (n_contigs <= 0 || !lengths || !seqs) return fail(c, FADEGPU_E_ARG, "fadegpu_load_reference: bad arguments");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    free_reference(c);
+    c->n_contigs = n_contigs;
+    int64_t off = 0, total = 0;
+    for (int t = 0; t < n_contigs; ++t) {
+        if (lengths[t] < 0 || !seqs[t]) { free_reference(c); return fail(c, FADEGPU_E_ARG, "fadegpu_load_reference: bad contig"); }
+        c->names.emplace_back(names && names[t] ? names[t] : "");
+        c->clen.push_back(lengths[t]);
+        c->coff.push_back(off);
+        total += lengths[t];
+        off += (lengths[t] + 31) & ~(int64_t)31;  // every contig starts on a 32-base word boundary
+    }
+    c->total_bases = total;
+    c->padded_bases = off + 32;
+    const size_t w2 = (size_t)(c->padded_bases / 16), w1 = (size_t)(c->padded_bases / 32);
+    std::vector<uint32_t> two, nm, xm;
+    try { two.assign(w2, 0u); nm.assign(w1, 0u); xm.assign(w1, 0u); }
+    catch (...) { free_reference(c); return fail(c, FADEGPU_E_OOM, "fadegpu_load_reference: out of host memory"); }
+    // byte -> (2-bit code | 4 = N | 8 = wildcard)
+    uint8_t lut[256];
+    for (int i = 0; i < 256; ++i) lut[i] = 8;
+    lut['A'] = lut['a'] = 0; lut['C'] = lut['c'] = 1; lut['T'] = lut['t'] = 2; lut['G'] = lut['g'] = 3;
+    lut['N'] = lut['n'] = 4;
+    for (int t = 0; t < n_contigs; ++t) {
+        const unsigned char *s = reinterpret_cast<const unsigned char *>(seqs[t]);
+        const int64_t len = lengths[t], base = c->coff[t];
+        const int64_t nwords = (len + 31) / 32;
+#pragma omp parallel for schedule(static)
+        for (int64_t wd = 0; wd < nwords; ++wd) {
+            uint32_t a0 = 0, a1 = 0, n = 0, x = 0;
+            const int64_t p0 = wd * 32;
+            const int lim = (int)std::min<int64_t>(32, len - p0);
+            for (int b = 0; b < lim; ++b) {
+                const uint8_t v = lut[s[p0 + b]];
+                const uint32_t code = v & 3u;
+                if (b < 16) a0 |= code << (2 * b); else a1 |= code << (2 * (b - 16));
+                n |= (uint32_t)((v >> 2) & 1u) << b;
+                x |= (uint32_t)((v >> 3) & 1u) << b;
+            }
+            const size_t gw = (size_t)((base + p0) / 32);
+            two[2 * gw] = a0; two[2 * gw + 1] = a1; nm[gw] = n; xm[gw] = x;
+        }
+    }
+    // sparse list of wildcard letters (upper-cased like source/analysis.d:63)
+    std::vector<int64_t> xpos;
+    std::vector<uint8_t> xchr;
+    for (int t = 0; t < n_contigs; ++t) {
+        const unsigned char *s = reinterpret_cast<const unsigned char *>(seqs[t]);
+        const int64_t len = lengths[t], base = c->coff[t];
+        for (int64_t wd = 0; wd * 32 < len; ++wd) {
+            const uint32_t x = xm[(size_t)((base + wd * 32) / 32)];
+            if (!x) continue;
+            for (int b = 0; b < 32; ++b)
+                if ((x >> b) & 1u) {
+                    unsigned char ch = s[wd * 32 + b];
+                    if (ch >= 'a' && ch <= 'z') ch = (unsigned char)(ch - 32);
+                    xpos.push_back(base + wd * 32 + b);
+                    xchr.push_back(ch);
+                }
+        }
+    }
+    c->n_x = (int64_t)xpos.size();
+    cudaError_t e;
+    if ((e = cudaMalloc(&c->d_two, w2 * 4)) != cudaSuccess || (e = cudaMalloc(&c->d_n, w1 * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_x, w1 * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_xpos, std::max<size_t>(1, xpos.size()) * 8)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_xchr, std::max<size_t>(1, xchr.size()))) != cudaSuccess) {
+        free_reference(c);
+        return cuda_fail(c, e, "fadegpu_load_reference: cudaMalloc");
+    }
+    CU(c, cudaMemcpy(c->d_two, two.data(), w2 * 4, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_n, nm.data(), w1 * 4, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_x, xm.data(), w1 * 4, cudaMemcpyHostToDevice));
+    if (!xpos.empty()) {
+        CU(c, cudaMemcpy(c->d_xpos, xpos.data(), xpos.size() * 8, cudaMemcpyHostToDevice));
+        CU(c, cudaMemcpy(c->d_xchr, xchr.data(), xchr.size(), cudaMemcpyHostToDevice));
+    }
+    c->ref_bytes = w2 * 4 + 2 * w1 * 4 + xpos.size() * 9;
+    return FADEGPU_OK;
+}
+
+int fadegpu_share_reference(fadegpu_ctx *dst, const fadegpu_ctx *src)
+{
+    if (!dst || !src) return fail(dst, FADEGPU_E_ARG, "fadegpu_share_reference: null ctx");
+    if (!src->d_two) return fail(dst, FADEGPU_E_STATE, "fadegpu_share_reference: source has no reference");
+    CU(dst, cudaSetDevice(dst->device));
+    CU(dst, cudaStreamSynchronize(dst->stream));
+    free_reference(dst);
+    dst->n_contigs = src->n_contigs; dst->names = src->names; dst->clen = src->clen; dst->coff = src->coff;
+    dst->total_bases = src->total_bases; dst->padded_bases = src->padded_bases; dst->n_x = src->n_x;
+    const size_t w2 = (size_t)(src->padded_bases / 16), w1 = (size_t)(src->padded_bases / 32);
+    const size_t nx = std::max<size_t>(1, (size_t)src->n_x);
+    CU(dst, cudaMalloc(&dst->d_two, w2 * 4)); CU(dst, cudaMalloc(&dst->d_n, w1 * 4)); CU(dst, cudaMalloc(&dst->d_x, w1 * 4));
+    CU(dst, cudaMalloc(&dst->d_xpos, nx * 8)); CU(dst, cudaMalloc(&dst->d_xchr, nx));
+    CU(dst, cudaMemcpyPeer(dst->d_two, dst->device, src->d_two, src->device, w2 * 4));
+    CU(dst, cudaMemcpyPeer(dst->d_n, dst->device, src->d_n, src->device, w1 * 4));
+    CU(dst, cudaMemcpyPeer(dst->d_x, dst->device, src->d_x, src->device, w1 * 4));
+    if (src->n_x > 0) {
+        CU(dst, cudaMemcpyPeer(dst->d_xpos, dst->device, src->d_xpos, src->device, (size_t)src->n_x * 8));
+        CU(dst, cudaMemcpyPeer(dst->d_xchr, dst->device, src->d_xchr, src->device, (size_t)src->n_x));
+    }
+    dst->ref_bytes = src->ref_bytes;
+    return FADEGPU_OK;
+}
+
+int fadegpu_reference_info(const fadegpu_ctx *c, int32_t *n_contigs, int64_t *total_bases, int64_t *device_bytes)
+{
+    if (!c) return fail(nullptr, FADEGPU_E_ARG, "fadegpu_reference_info: null ctx");
+    if (n_contigs) *n_contigs = c->n_contigs;
+    if (total_bases) *total_bases = c->total_bases;
+    if (device_bytes) *device_bytes = (int64_t)c->ref_bytes;
+    return FADEGPU_OK;
+}
+
+void fadegpu_free_batch(fadegpu_batch *b)
+{
+    if (!b) return;
+    fadegpu_ctx *c = b->ctx;
+    if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); }
+    fadegpu_batch_view &v = b->v;
+    free_host(v.seq4); free_host(v.seq_off); free_host(v.l_qseq); free_host(v.tid); free_host(v.pos);
+    free_host(v.aligned_len); free_host(v.clip_left); free_host(v.clip_right);
+    free_host(v.flags); free_host(v.score); free_host(v.beg_query); free_host(v.end_query);
+    free_host(v.beg_ref); free_host(v.end_ref); free_host(v.win_start); free_host(v.n_ops); free_host(v.ops);
+    free_host(b->h_aln); free_host(b->h_items); free_host(b->h_seq); free_host(b->h_out);
+    free_dev(b->d_aln); free_dev(b->d_items); free_dev(b->d_seq); free_dev(b->d_out); free_dev(b->d_flags);
+    free_dev(b->d_fillres);
+    for (auto &e : b->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    delete b;
+}
+
+int fadegpu_alloc_batch(fadegpu_ctx *c, int64_t max_reads, int64_t max_seq_bytes, fadegpu_batch **out)
+{
+    if (!c || !out) return fail(c, FADEGPU_E_ARG, "fadegpu_alloc_batch: null argument");
+    *out = nullptr;
+    if (max_reads <= 0 || max_seq_bytes <= 0 || max_reads > (int64_t)1 << 30)
+        return fail(c, FADEGPU_E_ARG, "fadegpu_alloc_batch: bad sizes");
+    CU(c, cudaSetDevice(c->device));
+    fadegpu_batch *b = new (std::nothrow) fadegpu_batch();
+    if (!b) return fail(c, FADEGPU_E_OOM, "fadegpu_alloc_batch: out of host memory");
+    b->ctx = c;
+    fadegpu_batch_view &v = b->v;
+    v.max_reads = max_reads; v.max_seq_bytes = max_seq_bytes;
+    const size_t n = (size_t)max_reads;
+    b->cap_items = (max_reads + 7) / 8 + 8;
+    b->cap_seq = max_seq_bytes + 16;
+    cudaError_t e = cudaSuccess;
+    auto H = [&](auto **p, size_t bytes) { if (e == cudaSuccess) e = cudaHostAlloc((void **)p, std::max<size_t>(bytes, 16), cudaHostAllocDefault); };
+    auto D = [&](auto **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc((void **)p, std::max<size_t>(bytes, 16)); };
+    H(&v.seq4, (size_t)max_seq_bytes); H(&v.seq_off, (n + 1) * 8); H(&v.l_qseq, n * 4); H(&v.tid, n * 4);
+    H(&v.pos, n * 8); H(&v.aligned_len, n * 4); H(&v.clip_left, n * 4); H(&v.clip_right, n * 4);
+    H(&v.flags, n); H(&v.score, n * 4); H(&v.beg_query, n * 4); H(&v.end_query, n * 4); H(&v.beg_ref, n * 4);
+    H(&v.end_ref, n * 4); H(&v.win_start, n * 8); H(&v.n_ops, n * 4); H(&v.ops, n * 4 * FADEGPU_MAX_OPS);
+    H(&b->h_aln, n * sizeof(AlnDesc)); H(&b->h_items, (size_t)b->cap_items * sizeof(WarpItem));
+    H(&b->h_seq, (size_t)b->cap_seq); H(&b->h_out, n * sizeof(AlnOut));
+    D(&b->d_aln, n * sizeof(AlnDesc)); D(&b->d_items, (size_t)b->cap_items * sizeof(WarpItem));
+    D(&b->d_seq, (size_t)b->cap_seq); D(&b->d_out, n * sizeof(AlnOut)); D(&b->d_flags, n * 4);
+    D(&b->d_fillres, (size_t)b->cap_items * 32 * sizeof(uint2));
+    for (auto &ev : b->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(c, e, "fadegpu_alloc_batch");
+        fadegpu_free_batch(b);
+        return rc;
+    }
+    *out = b;
+    return FADEGPU_OK;
+}
+
+int fadegpu_get_batch_view(fadegpu_batch *b, fadegpu_batch_view *view)
+{
+    if (!b || !view) return fail(b ? b->ctx : nullptr, FADEGPU_E_ARG, "fadegpu_get_batch_view: null argument");
+    *view = b->v;
+    return FADEGPU_OK;
+}
+
+int fadegpu_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
+{
+    if (!c || !b || b->ctx != c) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: bad ctx/batch");
+    if (!c->d_two) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: no reference loaded");
+    if (b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: batch already in flight (call fadegpu_wait)");
+    if (n_reads < 0 || n_reads > b->v.max_reads) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: n_reads out of range");
+    CU(c, cudaSetDevice(c->device));
+    const fadegpu_batch_view &v = b->v;
+    const int64_t n = n_reads;
+    if (n > 0 && (v.seq_off[n] < 0 || v.seq_off[n] > v.max_seq_bytes))
+        return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off[n] exceeds max_seq_bytes");
+    b->n_reads = n;
+    b->plan.clear();
+    memset(&b->st, 0, sizeof(b->st));
+    b->st.n_reads = n;
+
+    // ---- 1. which reads need SW, their windows (analysis.d:34,45-59) and size class ----
+    b->tmp_cls.assign((size_t)n, -1);
+    b->tmp_tlen.assign((size_t)n, 0);
+    b->tmp_start.assign((size_t)n, 0);
+    const uint32_t floor_u = (uint32_t)c->p.min_length;  // uint <= int compare of analysis.d:34
+    const int64_t W = c->p.window_size;
+    int64_t cells = 0;
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : cells) reduction(| : bad)
+    for (int64_t r = 0; r < n; ++r) {
+        const uint32_t cl = (uint32_t)v.clip_left[r], cr = (uint32_t)v.clip_right[r];
+        const bool need = (cl != 0 && !(cl <= floor_u)) || (cr != 0 && !(cr <= floor_u));
+        if (!need) continue;
+        const int32_t tid = v.tid[r];
+        const int32_t ql = v.l_qseq[r];
+        if (tid < 0 || tid >= c->n_contigs || ql <= 0) continue;
+        const int64_t so = v.seq_off[r];
+        if (so < 0 || so + (ql + 1) / 2 > v.seq_off[n]) { bad = 1; continue; }
+        int64_t start = v.pos[r] - W;
+        if (start < 0) start = 0;
+        int64_t end = v.pos[r] + (int64_t)v.aligned_len[r] + W;
+        if (end > c->clen[tid]) end = c->clen[tid];
+        b->tmp_start[r] = start;
+        if (end <= start || end - start > 0x7fffffff) continue;  // empty window: nothing to align
+        const int tlen = (int)(end - start);
+        b->tmp_tlen[r] = tlen;
+        b->tmp_cls[r] = class_of(c, ql, tlen);
+        cells += (int64_t)ql * tlen;
+    }
+    if (bad) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
+    b->st.cells = cells;
+
+    // ---- 2. bin by class, counting sort by window length (longest first) ----
+    static const int CLS[4] = { 13, 19, 32, 0 };
+    int64_t n_aln = 0, n_items = 0, seq_bytes = 0;
+    std::vector<int64_t> order;
+    std::vector<int32_t> cnt;
+    size_t ck_needed = 0, gen_needed = 0;
+    int qmax_all = 1, tmax_all = 1;
+    for (int64_t r = 0; r < n; ++r)
+        if (b->tmp_cls[r] >= 0) { qmax_all = std::max(qmax_all, v.l_qseq[r]); tmax_all = std::max(tmax_all, b->tmp_tlen[r]); }
+    for (int ci = 0; ci < 4; ++ci) {
+        const int R = CLS[ci];
+        order.clear();
+        if (R != 0) {
+            cnt.assign(TMAX_FAST + 2, 0);
+            for (int64_t r = 0; r < n; ++r) if (b->tmp_cls[r] == R) ++cnt[TMAX_FAST - b->tmp_tlen[r]];
+            int64_t tot = 0;
+            for (auto &x : cnt) { const int32_t t = x; x = (int32_t)tot; tot += t; }
+            if (tot == 0) continue;
+            order.resize((size_t)tot);
+            for (int64_t r = 0; r < n; ++r) if (b->tmp_cls[r] == R) order[(size_t)cnt[TMAX_FAST - b->tmp_tlen[r]]++] = r;
+        } else {
+            for (int64_t r = 0; r < n; ++r) if (b->tmp_cls[r] == 0) order.push_back(r);
+            if (order.empty()) continue;
+        }
+        const int64_t first_aln = n_aln;
+        int qmax = 1, tmax = 1;
+        for (int64_t r : order) {
+            AlnDesc &d = b->h_aln[n_aln++];
+            const int ql = v.l_qseq[r];
+            d.gstart = c->coff[v.tid[r]] + b->tmp_start[r];
+            d.seq_off = seq_bytes;
+            d.tlen = b->tmp_tlen[r];
+            d.qlen = ql;
+            d.clip_left = (uint32_t)v.clip_left[r];
+            d.clip_right = (uint32_t)v.clip_right[r];
+            d.read = (int32_t)r;
+            d.pad = 0;
+            const int nb = (ql + 1) / 2;
+            memcpy(b->h_seq + seq_bytes, v.seq4 + v.seq_off[r], (size_t)nb);
+            seq_bytes += nb;
+            qmax = std::max(qmax, ql); tmax = std::max(tmax, d.tlen);
+        }
+        const int64_t cnt_aln = n_aln - first_aln;
+        if (R == 0) {
+            Launch L{};
+            L.R = 0; L.aln_first = (int)first_aln; L.n_aln = (int)cnt_aln; L.qmax = qmax; L.tmax = tmax;
+            b->plan.push_back(L);
+            gen_needed = std::max(gen_needed, gen_slot_bytes(qmax, tmax));
+            b->st.n_generic += cnt_aln;
+            continue;
+        }
+        // warp items of 8 alignments; split into launches that fit the checkpoint scratch
+        const size_t cw = ck_words_of(R);
+        int64_t a0 = first_aln;
+        while (a0 < n_aln) {
+            Launch L{};
+            L.R = R; L.aln_first = (int)a0; L.item_first = (int)n_items; L.qmax = qmax_all; L.tmax = tmax_all;
+            size_t words = 0;
+            int nblk_max = 1;
+            int64_t a1 = a0;
+            while (a1 < n_aln) {
+                const int nblk = num_blocks(b->h_aln[a1].tlen);  // longest of the 8 (sorted descending)
+                const size_t wds = (size_t)(nblk - 1) * cw * 32;
+                if (a1 > a0 && (words + wds) * 4 > (size_t)c->p.scratch_bytes) break;
+                WarpItem &it = b->h_items[n_items++];
+                it.ck_off = (int64_t)words;
+                it.first = (int32_t)(a1 - a0);
+                it.nblk = nblk;
+                words += wds;
+                nblk_max = std::max(nblk_max, nblk);
+                a1 = std::min<int64_t>(a1 + 8, n_aln);
+            }
+            L.n_aln = (int)(a1 - a0);
+            L.n_items = (int)(n_items - L.item_first);
+            L.tw_stride = tw_stride_for(nblk_max);
+            ck_needed = std::max(ck_needed, words * 4);
+            b->plan.push_back(L);
+            a0 = a1;
+        }
+    }
+    b->n_aln = n_aln; b->n_items = n_items; b->seq_bytes = seq_bytes;
+    b->qmax_all = qmax_all; b->tmax_all = tmax_all;
+    b->st.n_aligned = n_aln;
+    b->st.scratch_bytes = (int64_t)ck_needed;
+    // a slot for wildcard alignments discovered on the device, sized for the largest problem
+    if (n_aln > 0) gen_needed = std::max(gen_needed, gen_slot_bytes(qmax_all, tmax_all));
+    if (ck_needed) { int rc = ensure_ck(c, ck_needed); if (rc) return rc; }
+    if (gen_needed) {
+        const size_t want = std::min<size_t>(GEN_BUDGET, gen_needed * 1024);
+        int rc = ensure_gen(c, std::max(want, gen_needed));
+        if (rc) return rc;
+    }
+
+    // ---- 3. queue copies and kernels ----
+    CU(c, cudaEventRecord(b->ev[0], c->stream));
+    if (n_aln > 0) {
+        CU(c, cudaMemcpyAsync(b->d_aln, b->h_aln, (size_t)n_aln * sizeof(AlnDesc), cudaMemcpyHostToDevice, c->stream));
+        if (n_items > 0)
+            CU(c, cudaMemcpyAsync(b->d_items, b->h_items, (size_t)n_items * sizeof(WarpItem), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(b->d_seq, b->h_seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    b->st.h2d_bytes = n_aln * (int64_t)sizeof(AlnDesc) + n_items * (int64_t)sizeof(WarpItem) + seq_bytes;
+    CU(c, cudaEventRecord(b->ev[1], c->stream));
+    int nl = 0;
+    { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl); if (rc) return rc; }
+    b->st.kernel_launches = nl;
+    CU(c, cudaEventRecord(b->ev[2], c->stream));
+    if (n_aln > 0)
+        CU(c, cudaMemcpyAsync(b->h_out, b->d_out, (size_t)n_aln * sizeof(AlnOut), cudaMemcpyDeviceToHost, c->stream));
+    b->st.d2h_bytes = n_aln * (int64_t)sizeof(AlnOut);
+    CU(c, cudaEventRecord(b->ev[3], c->stream));
+    b->in_flight = true;
+    return FADEGPU_OK;
+}
+
+int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
+{
+    if (!c || !b || b->ctx != c) return fail(c, FADEGPU_E_ARG, "fadegpu_wait: bad ctx/batch");
+    if (!b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_wait: batch not submitted");
+    CU(c, cudaSetDevice(c->device));
+    b->in_flight = false;
+    CU(c, cudaEventSynchronize(b->ev[3]));
+    float t;
+    if (cudaEventElapsedTime(&t, b->ev[1], b->ev[2]) == cudaSuccess) b->st.kernel_ms = t;
+    if (cudaEventElapsedTime(&t, b->ev[0], b->ev[3]) == cudaSuccess) b->st.total_ms = t;
+    fadegpu_batch_view &v = b->v;
+    const int64_t n = b->n_reads;
+    memset(v.flags, 0, (size_t)n);
+    memset(v.score, 0, (size_t)n * 4); memset(v.beg_query, 0, (size_t)n * 4); memset(v.end_query, 0, (size_t)n * 4);
+    memset(v.beg_ref, 0, (size_t)n * 4); memset(v.end_ref, 0, (size_t)n * 4); memset(v.n_ops, 0, (size_t)n * 4);
+    memset(v.win_start, 0, (size_t)n * 8);
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t k = 0; k < b->n_aln; ++k) {
+        const AlnOut &o = b->h_out[k];
+        const int64_t r = b->h_aln[k].read;
+        if (o.read != (int32_t)r || (o.flags & 0x80000000u)) { bad = 1; continue; }
+        v.flags[r] = (uint8_t)(o.flags & 0xff);
+        v.score[r] = o.score; v.beg_query[r] = o.beg_query; v.end_query[r] = o.end_query;
+        v.beg_ref[r] = o.beg_ref; v.end_ref[r] = o.end_ref; v.n_ops[r] = o.n_ops;
+        v.win_start[r] = b->tmp_start[r];
+        memcpy(v.ops + (size_t)r * FADEGPU_MAX_OPS, o.ops, sizeof(o.ops));
+    }
+    if (bad) return fail(c, FADEGPU_E_CUDA, "fadegpu_wait: a kernel did not produce a result record (internal error)");
+    return FADEGPU_OK;
+}
+
+int fadegpu_get_stats(const fadegpu_batch *b, fadegpu_stats *s)
+{
+    if (!b || !s) return fail(nullptr, FADEGPU_E_ARG, "fadegpu_get_stats: null argument");
+    *s = b->st;
+    return FADEGPU_OK;
+}
+
+int fadegpu_replay_kernels(fadegpu_ctx *c, fadegpu_batch *b, int32_t iters, float *ms_out)
+{
+    if (!c || !b || b->ctx != c || iters <= 0) return fail(c, FADEGPU_E_ARG, "fadegpu_replay_kernels: bad arguments");
+    if (b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_replay_kernels: batch in flight");
+    if (b->plan.empty() && b->n_aln > 0) return fail(c, FADEGPU_E_STATE, "fadegpu_replay_kernels: nothing submitted");
+    CU(c, cudaSetDevice(c->device));
+    // one pass with per-stage events (serialising), then `iters` untouched passes for the total
+    float f = 0, t = 0, g = 0;
+    { int rc = run_plan(c, b, &f, &t, &g, nullptr); if (rc) return rc; }
+    b->st.fill_ms = f; b->st.trace_ms = t; b->st.generic_ms = g;
+    cudaEvent_t e0, e1;
+    CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < iters; ++i) { int rc = run_plan(c, b, nullptr, nullptr, nullptr, nullptr); if (rc) return rc; }
+    CU(c, cudaEventRecord(e1, c->stream));
+    CU(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(c, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms;
+    return FADEGPU_OK;
+}
+
+int fadegpu_measure_alu_peak(fadegpu_ctx *c, double *ops_per_sec_out, double *sm_clock_mhz_out)
+{
+    if (!c || !ops_per_sec_out) return fail(c, FADEGPU_E_ARG, "fadegpu_measure_alu_peak: null argument");
+    CU(c, cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CU(c, cudaGetDeviceProperties(&prop, c->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    cudaEvent_t e0, e1;
+    CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(c, cudaEventRecord(e0, c->stream));
+        CU(c, launch_alu_peak(c->d_alu, iters, blocks, threads, c->stream));
+        CU(c, cudaEventRecord(e1, c->stream));
+        CU(c, cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(c, cudaEventElapsedTime(&ms, e0, e1));
+        const double ops = (double)blocks * threads * (double)iters * 64.0;  // thread-instructions
+        if (rep > 0 && ms > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ops_per_sec_out = best;
+    if (sm_clock_mhz_out) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+        *sm_clock_mhz_out = khz / 1000.0;
+    }
+    return FADEGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,478 @@
+// kernels.cu -- hand-written sm_100a kernels for the `fade annotate` realignment path.
+// See kernels.cuh for the inventory and sw_core.cuh for the arithmetic they share with the CPU
+// emulation.  Reference semantics: source/analysis.d:34-80,98-104 + parasail rules P1-P5.
+#include "kernels.cuh"
+
+namespace fade {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// Stage one pair: target selector words (window gather from the packed reference,
+// source/analysis.d:45-64) into shared memory, query selector words (reverse complement of the
+// BAM 4-bit bases, source/util.d:18-34) into registers.  `wild` gets bit0/bit1 when alignment
+// a/b contains a letter outside ACGTN (those go to the generic kernel).
+template <int R>
+__device__ __forceinline__ void stage_pair(const KernelArgs &a, const AlnDesc &da, const AlnDesc &db,
+                                           int g, int nblk, uint16_t *tw, uint32_t (&qs)[R],
+                                           uint8_t *qc, uint32_t &wild)
+{
+    const int TW = FBLK * nblk + FG + 1;
+    uint32_t w = 0;
+    for (int idx = g; idx < TW; idx += FG) {
+        const int j = idx - FG;
+        int ca = C_TPAD, cb = C_TPAD;
+        if (j >= 0 && j < da.tlen) ca = ref_code(a.ref.planes, da.gstart + j);
+        if (j >= 0 && j < db.tlen) cb = ref_code(a.ref.planes, db.gstart + j);
+        w |= (ca == C_WILD ? 1u : 0u) | (cb == C_WILD ? 2u : 0u);
+        tw[idx] = (uint16_t)t_sel(ca, cb);
+    }
+    const uint8_t *sa = a.seq + da.seq_off, *sb = a.seq + db.seq_off;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = g * R + r;
+        int ca = C_QPAD, cb = C_QPAD;
+        if (i < da.qlen) ca = rc_query_code(sa, da.qlen, i);
+        if (i < db.qlen) cb = rc_query_code(sb, db.qlen, i);
+        w |= (ca == C_WILD ? 1u : 0u) | (cb == C_WILD ? 2u : 0u);
+        qs[r] = q_sel(ca, cb);
+        if (qc) qc[i] = (uint8_t)(ca | (cb << 4));
+    }
+    wild = w;
+}
+
+__device__ __forceinline__ AlnDesc load_desc(const KernelArgs &a, int idx)
+{
+    AlnDesc d;
+    if (idx < a.n_aln) d = a.aln[idx];
+    else { d.gstart = 0; d.seq_off = 0; d.tlen = 0; d.qlen = 0; d.clip_left = d.clip_right = 0; d.read = -1; d.pad = 0; }
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// score-only wavefront with checkpoints
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(FILL_THREADS) sw_fill_kernel(const KernelArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = lane & (FG - 1), q = lane >> 3;
+    const int w = blockIdx.x * (FILL_THREADS / 32) + wib;
+    if (w >= a.n_items) return;
+    const WarpItem item = a.items[w];
+    const int ia = item.first + 2 * q, ib = ia + 1;
+    const AlnDesc da = load_desc(a, ia), db = load_desc(a, ib);
+    uint16_t *tw = reinterpret_cast<uint16_t *>(smem_raw) + (size_t)(wib * 4 + q) * a.tw_stride;
+    const int nblk = item.nblk;
+    const SwConsts k = a.k;
+
+    uint32_t H[R], E[R], qs[R];
+    uint32_t wild;
+    stage_pair<R>(a, da, db, g, nblk, tw, qs, nullptr, wild);
+#pragma unroll
+    for (int r = 0; r < R; ++r) { H[r] = 0u; E[r] = k.neg_o; }
+    uint32_t hu_prev = 0u, fout = k.neg_o, M = 0u, Mprev = 0u;
+    int blk_lo = 0, blk_hi = 0;
+    __syncwarp();
+
+    constexpr int CW = ck_words<R>();
+    uint32_t *ckw = a.ck + item.ck_off + lane;
+    const uint16_t *twp = tw + (FG - g);
+    for (int c = 0; c < nblk; ++c) {
+#pragma unroll 2
+        for (int u = 0; u < FBLK; ++u) {
+            const int t = c * FBLK + u;
+            uint32_t hu = __shfl_up_sync(FULL, H[R - 1], 1, FG);
+            uint32_t fin = __shfl_up_sync(FULL, fout, 1, FG);
+            if (g == 0) { hu = 0u; fin = k.neg_o; }
+            const uint32_t ts = twp[t];
+            fill_step<R>(H, E, qs, M, ts, hu_prev, fin, fout, k);
+            hu_prev = hu;
+        }
+        if (c + 1 < nblk) {
+            uint32_t *p = ckw + (size_t)c * CW * 32;
+#pragma unroll
+            for (int r = 0; r < R; ++r) { p[r * 32] = H[r]; p[(R + r) * 32] = E[r]; }
+            p[(2 * R) * 32] = hu_prev;
+            p[(2 * R + 1) * 32] = fout;
+        }
+        if (M != Mprev) {
+            if ((M ^ Mprev) & 0xffffu) blk_lo = c;
+            if ((M ^ Mprev) >> 16) blk_hi = c;
+            Mprev = M;
+        }
+    }
+    a.fillres[(size_t)w * 32 + lane] = make_uint2(M, (uint32_t)blk_lo | ((uint32_t)blk_hi << 16));
+    if ((wild & 1u) && ia < a.n_aln) a.aln_flags[ia] = 1u;
+    if ((wild & 2u) && ib < a.n_aln) a.aln_flags[ib] = 1u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// end cell + traceback by block replay
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(TRACE_THREADS) sw_trace_kernel(const KernelArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int rows = FG * R;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = lane & (FG - 1), q = lane >> 3;
+    const int w = blockIdx.x * (TRACE_THREADS / 32) + wib;
+    if (w >= a.n_items) return;
+    const WarpItem item = a.items[w];
+    const int ia = item.first + 2 * q, ib = ia + 1;
+    const AlnDesc da = load_desc(a, ia), db = load_desc(a, ib);
+    const int nblk = item.nblk;
+    const SwConsts k = a.k;
+
+    const size_t group_bytes = align16((size_t)a.tw_stride * 2) + align16((size_t)FBLK * rows) +
+                               align16(rows) + align16(2 * sizeof(LaneCtl));
+    unsigned char *base = smem_raw + (size_t)(wib * 4 + q) * group_bytes;
+    uint16_t *tw = reinterpret_cast<uint16_t *>(base);
+    uint8_t *tr = base + align16((size_t)a.tw_stride * 2);
+    uint8_t *qc = tr + align16((size_t)FBLK * rows);
+    LaneCtl *ctl = reinterpret_cast<LaneCtl *>(qc + align16(rows));
+    LaneCtl &c0 = ctl[0];
+    LaneCtl &c1 = ctl[1];
+
+    uint32_t H[R], E[R], qs[R];
+    uint32_t wild;
+    stage_pair<R>(a, da, db, g, nblk, tw, qs, qc, wild);
+    {
+        const uint2 fr = a.fillres[(size_t)w * 32 + lane];
+        c0.best[g] = lane_lo(fr.x); c0.blk[g] = (int)(fr.y & 0xffffu);
+        c1.best[g] = lane_hi(fr.x); c1.blk[g] = (int)(fr.y >> 16);
+    }
+    __syncwarp();
+    if (g == 0) ctl_init(c0, da.qlen, da.tlen);
+    else if (g == 1) ctl_init(c1, db.qlen, db.tlen);
+
+    constexpr int CW = ck_words<R>();
+    const uint32_t *ckw = a.ck + item.ck_off + lane;
+    const uint16_t *twp = tw + (FG - g);
+    uint8_t *trg = tr + g * R;
+    bool overrun = false;
+    for (int iter = 0;; ++iter) {
+        __syncwarp();
+        const int ph0 = c0.phase, ph1 = c1.phase;
+        const bool active = (ph0 != 2) || (ph1 != 2);
+        if (!__any_sync(FULL, active)) break;
+        if (iter > 4 * nblk + 16) { overrun = active; break; }  // cannot happen; never hang the GPU
+        const int b0 = (ph0 != 2 && c0.next_blk >= 0) ? c0.next_blk : 0;
+        const int b1 = (ph1 != 2 && c1.next_blk >= 0) ? c1.next_blk : 0;
+        const bool sc0 = ctl_scan_me(c0, g), sc1 = ctl_scan_me(c1, g);
+        const int S0 = c0.S, S1 = c1.S;
+        // lane a state from checkpoint b0-1, lane b state from checkpoint b1-1
+        uint32_t hu_prev, fout;
+        {
+            const uint32_t *p0 = ckw + (size_t)(b0 > 0 ? b0 - 1 : 0) * CW * 32;
+            const uint32_t *p1 = ckw + (size_t)(b1 > 0 ? b1 - 1 : 0) * CW * 32;
+            const bool z0 = (b0 == 0) || nblk < 2, z1 = (b1 == 0) || nblk < 2;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t h0 = z0 ? 0u : p0[r * 32], h1 = z1 ? 0u : p1[r * 32];
+                const uint32_t e0 = z0 ? k.neg_o : p0[(R + r) * 32], e1 = z1 ? k.neg_o : p1[(R + r) * 32];
+                H[r] = (h0 & 0xffffu) | (h1 & 0xffff0000u);
+                E[r] = (e0 & 0xffffu) | (e1 & 0xffff0000u);
+            }
+            const uint32_t u0 = z0 ? 0u : p0[(2 * R) * 32], u1 = z1 ? 0u : p1[(2 * R) * 32];
+            const uint32_t f0 = z0 ? k.neg_o : p0[(2 * R + 1) * 32], f1 = z1 ? k.neg_o : p1[(2 * R + 1) * 32];
+            hu_prev = (u0 & 0xffffu) | (u1 & 0xffff0000u);
+            fout = (f0 & 0xffffu) | (f1 & 0xffff0000u);
+        }
+        bool found0 = false, found1 = false;
+        int fj0 = 0, fr0 = 0, fj1 = 0, fr1 = 0;
+        for (int u = 0; u < FBLK; ++u) {
+            const int t0 = b0 * FBLK + u, t1 = b1 * FBLK + u;
+            uint32_t hu = __shfl_up_sync(FULL, H[R - 1], 1, FG);
+            uint32_t fin = __shfl_up_sync(FULL, fout, 1, FG);
+            if (g == 0) { hu = 0u; fin = k.neg_o; }
+            const uint32_t ts = ((uint32_t)twp[t0] & 0x00ffu) | ((uint32_t)twp[t1] & 0xff00u);
+            int hit0, hit1;
+            const int s0 = (sc0 && !found0) ? S0 : -1;
+            const int s1 = (sc1 && !found1) ? S1 : -1;
+            trace_step<R>(H, E, qs, ts, hu_prev, fin, fout, k, trg + u * rows, s0, s1, hit0, hit1);
+            hu_prev = hu;
+            if (s0 >= 0 && hit0 < R) { found0 = true; fj0 = t0 - g; fr0 = hit0; }
+            if (s1 >= 0 && hit1 < R) { found1 = true; fj1 = t1 - g; fr1 = hit1; }
+        }
+        if (sc0) { c0.fj[g] = found0 ? fj0 : 0; c0.fr[g] = found0 ? fr0 : 0; }
+        if (sc1) { c1.fj[g] = found1 ? fj1 : 0; c1.fr[g] = found1 ? fr1 : 0; }
+        __syncwarp();
+        if (g == 0) ctl_advance<R>(c0, tr, rows, 0, tw, qc);
+        else if (g == 1) ctl_advance<R>(c1, tr, rows, 4, tw, qc);
+    }
+    __syncwarp();
+    // results (alignments that met a wildcard letter are produced by the generic kernel instead)
+    if (g == 0 && ia < a.n_aln && !(a.aln_flags[ia] & 1u)) {
+        AlnOut o;
+        finalize_result(c0, o, da.read, da.clip_left, da.clip_right, a.min_length);
+        if (overrun) o.flags = 0x80000000u;
+        a.out[ia] = o;
+    } else if (g == 1 && ib < a.n_aln && !(a.aln_flags[ib] & 1u)) {
+        AlnOut o;
+        finalize_result(c1, o, db.read, db.clip_left, db.clip_right, a.min_length);
+        if (overrun) o.flags = 0x80000000u;
+        a.out[ib] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic exact kernel: one thread per alignment, int32, arbitrary letters and sizes
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int map_char(int c)
+{
+    switch (c) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'T': return 2;
+    case 'G': return 3;
+    case 'N': return 4;
+    default: return 5;
+    }
+}
+
+// upper-cased reference letter at global position p (source/analysis.d:63 .toUpper)
+__device__ int ref_char(const RefDev &rf, int64_t p)
+{
+    const int c = ref_code(rf.planes, p);
+    if (c < 4) return "ACTG"[c];
+    if (c == C_N) return 'N';
+    int64_t lo = 0, hi = rf.n_x - 1;
+    while (lo <= hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const int64_t v = rf.xpos[mid];
+        if (v == p) return rf.xchr[mid];
+        if (v < p) lo = mid + 1; else hi = mid - 1;
+    }
+    return '?';
+}
+
+__global__ void __launch_bounds__(128) sw_generic_kernel(const GenericArgs a)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.n_slots) return;
+    uint8_t *sc = a.scratch + (size_t)slot * a.slot_bytes;
+    int32_t *Hc = reinterpret_cast<int32_t *>(sc);
+    int32_t *Ec = Hc + a.qmax;
+    uint8_t *qch = reinterpret_cast<uint8_t *>(Ec + a.qmax);
+    uint8_t *trc = qch + ((a.qmax + 15) & ~15);
+    const int o = a.open, e = a.extend;
+    const char nt16[] = "=ACMGRSVTWYHKDBN";
+    const uint8_t comp16[16] = { 0, 8, 4, 12, 2, 10, 6, 14, 1, 9, 5, 13, 3, 11, 7, 15 };
+    unsigned idx = 0, idx_end = 0;
+    for (;;) {
+        if (idx >= idx_end) {
+            idx = atomicAdd(a.cursor, (unsigned)a.chunk);
+            if (idx >= (unsigned)a.n_aln) break;
+            idx_end = min(idx + (unsigned)a.chunk, (unsigned)a.n_aln);
+        }
+        const unsigned cur_idx = idx++;
+        if (a.aln_flags && !(a.aln_flags[cur_idx] & 1u)) continue;
+        const AlnDesc d = a.aln[cur_idx];
+        const int qlen = d.qlen, tlen = d.tlen;
+        AlnOut out;
+        out.read = d.read;
+        for (int kk = 0; kk < OPS_CAP; ++kk) out.ops[kk] = 0;
+        if (qlen <= 0 || tlen <= 0 || qlen > a.qmax || tlen > a.tmax) {
+            out.score = out.end_query = out.end_ref = out.beg_query = out.beg_ref = out.n_ops = 0;
+            out.flags = R_ALIGNED | R_GENERIC;
+            a.out[cur_idx] = out;
+            continue;
+        }
+        const uint8_t *s4 = a.seq + d.seq_off;
+        for (int i = 0; i < qlen; ++i) {   // source/util.d:23-34
+            qch[i] = (uint8_t)nt16[comp16[nt16_at(s4, qlen - 1 - i)]];
+            Hc[i] = 0;
+            Ec[i] = -(1 << 28);
+        }
+        int best = 0, bi = 0, bj = 0;
+        for (int j = 0; j < tlen; ++j) {
+            const int tch = ref_char(a.ref, d.gstart + j);
+            const int tcd = map_char(tch);
+            int hdiag = 0, hup = 0, f = -(1 << 28);
+            for (int i = 0; i < qlen; ++i) {
+                const int hleft = Hc[i];
+                const int e_opn = hleft - o, e_ext = Ec[i] - e;
+                int tb = 0, ev, fv;
+                if (e_opn > e_ext) { ev = e_opn; tb |= T_EOPEN; } else ev = e_ext;
+                const int f_opn = hup - o, f_ext = f - e;
+                if (f_opn > f_ext) { fv = f_opn; tb |= T_FOPEN; } else fv = f_ext;
+                const int qcd = map_char(qch[i]);
+                const int s = (qcd == 5 || tcd == 5) ? 0 : (qcd == tcd ? a.match : a.mismatch);
+                int hd = hdiag + s;
+                if (hd < 0) hd = 0;
+                int h = hd;
+                if (ev > h) h = ev;
+                if (fv > h) h = fv;
+                if (h == hd) tb |= (h == 0) ? T_ZERO : T_DIAG;
+                else tb |= (h == fv) ? T_F : T_E;
+                // here bits 2/3 describe how E[i][j] / F[i][j] THEMSELVES were derived
+                trc[(size_t)i * tlen + j] = (uint8_t)tb;
+                hdiag = hleft; hup = h; f = fv;
+                Ec[i] = ev; Hc[i] = h;
+                if (h > best) { best = h; bi = i; bj = j; }  // P3: first column, then first row
+            }
+        }
+        out.score = best;
+        if (best <= 0) {
+            out.end_query = out.end_ref = out.beg_query = out.beg_ref = out.n_ops = 0;
+            out.flags = R_ALIGNED | R_GENERIC;
+            a.out[cur_idx] = out;
+            continue;
+        }
+        // P4 traceback, reversed RLE ops into a ring (same convention as LaneCtl)
+        uint32_t ring[OPS_CAP];
+        int nrev = 0;
+        uint32_t cur = 0;
+        int i = bi, j = bj, state = 0;
+        while (i >= 0 && j >= 0) {
+            const int tb = trc[(size_t)i * tlen + j];
+            uint32_t op;
+            if (state == 0) {
+                const int src = tb & 3;
+                if (src == T_ZERO) break;
+                if (src == T_DIAG) {
+                    op = (qch[i] == (uint8_t)ref_char(a.ref, d.gstart + j)) ? OP_EQ : OP_X;
+                    --i; --j;
+                } else if (src == T_F) { state = 1; continue; }
+                else { state = 2; continue; }
+            } else if (state == 1) {
+                op = OP_I; --i;
+                if (tb & T_FOPEN) state = 0;
+            } else {
+                op = OP_D; --j;
+                if (tb & T_EOPEN) state = 0;
+            }
+            if (cur != 0 && (cur & 0xf) == op) cur += 16;
+            else {
+                if (cur != 0) { ring[nrev % OPS_CAP] = cur; ++nrev; }
+                cur = (1u << 4) | op;
+            }
+        }
+        if (cur != 0) { ring[nrev % OPS_CAP] = cur; ++nrev; }
+        out.end_query = bi; out.end_ref = bj; out.beg_query = i + 1; out.beg_ref = j + 1;
+        const int lead = i + 1, trail = qlen - 1 - bi;
+        const int n = (lead > 0) + nrev + (trail > 0);
+        out.n_ops = n;
+        int wq = 0;
+        if (lead > 0) out.ops[wq++] = ((uint32_t)lead << 4) | OP_S;
+        for (int kk = nrev - 1; kk >= 0 && wq < OPS_CAP; --kk) {
+            if (nrev - kk > OPS_CAP) break;
+            out.ops[wq++] = ring[kk % OPS_CAP];
+        }
+        if (trail > 0 && wq < OPS_CAP && wq == n - 1) out.ops[wq++] = ((uint32_t)trail << 4) | OP_S;
+        uint32_t flags = R_ALIGNED | R_GENERIC;
+        if (n > OPS_CAP) flags |= R_OPS_TRUNC;
+        const uint32_t first_op = lead > 0 ? (uint32_t)OP_S : (ring[(nrev - 1) % OPS_CAP] & 0xf);
+        const uint32_t last_op = trail > 0 ? (uint32_t)OP_S : (ring[0] & 0xf);
+        if (accept_side(true, best, n, first_op, last_op, lead, trail, d.clip_left, a.min_length)) flags |= R_ART_LEFT;
+        if (accept_side(false, best, n, first_op, last_op, lead, trail, d.clip_right, a.min_length)) flags |= R_ART_RIGHT;
+        out.flags = flags;
+        a.out[cur_idx] = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// INT16x2 ALU issue-rate microbenchmark: 8 independent VIADDMNMX.S16x2 chains per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) alu_peak_kernel(uint32_t *out, int iters)
+{
+    uint32_t x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    const uint32_t c = 0x00010003u + blockIdx.x, d = 0xfffefffdu;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = __viaddmax_s16x2(x0, c, d); x1 = __viaddmax_s16x2(x1, c, d);
+            x2 = __viaddmax_s16x2(x2, c, d); x3 = __viaddmax_s16x2(x3, c, d);
+            x4 = __viaddmax_s16x2(x4, c, d); x5 = __viaddmax_s16x2(x5, c, d);
+            x6 = __viaddmax_s16x2(x6, c, d); x7 = __viaddmax_s16x2(x7, c, d);
+        }
+    }
+    const uint32_t r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+    if (r == 0x12345678u) out[0] = r;  // keep the chains alive
+}
+
+}  // namespace
+
+int tw_stride_for(int nblk_max) { return (FBLK * nblk_max + FG + 1 + 7) & ~7; }
+
+size_t fill_smem_bytes(int tw_stride) { return (size_t)(FILL_THREADS / FG) * tw_stride * 2; }
+
+size_t trace_smem_bytes(int R, int tw_stride)
+{
+    const size_t rows = (size_t)FG * R;
+    const size_t group = align16((size_t)tw_stride * 2) + align16((size_t)FBLK * rows) + align16(rows) +
+                         align16(2 * sizeof(LaneCtl));
+    return (size_t)(TRACE_THREADS / FG) * group;
+}
+
+template <int R>
+static cudaError_t launch_fill_t(const KernelArgs &a, cudaStream_t s)
+{
+    const size_t smem = fill_smem_bytes(a.tw_stride);
+    cudaError_t e = cudaFuncSetAttribute(sw_fill_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int wpb = FILL_THREADS / 32;
+    const int grid = (a.n_items + wpb - 1) / wpb;
+    sw_fill_kernel<R><<<grid, FILL_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t launch_trace_t(const KernelArgs &a, cudaStream_t s)
+{
+    const size_t smem = trace_smem_bytes(R, a.tw_stride);
+    cudaError_t e = cudaFuncSetAttribute(sw_trace_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int wpb = TRACE_THREADS / 32;
+    const int grid = (a.n_items + wpb - 1) / wpb;
+    sw_trace_kernel<R><<<grid, TRACE_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill(int R, const KernelArgs &a, cudaStream_t s)
+{
+    if (a.n_items <= 0) return cudaSuccess;
+    switch (R) {
+    case 13: return launch_fill_t<13>(a, s);
+    case 19: return launch_fill_t<19>(a, s);
+    case 32: return launch_fill_t<32>(a, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_trace(int R, const KernelArgs &a, cudaStream_t s)
+{
+    if (a.n_items <= 0) return cudaSuccess;
+    switch (R) {
+    case 13: return launch_trace_t<13>(a, s);
+    case 19: return launch_trace_t<19>(a, s);
+    case 32: return launch_trace_t<32>(a, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_generic(const GenericArgs &a, int n_slots, cudaStream_t s)
+{
+    if (a.n_aln <= 0 || n_slots <= 0) return cudaSuccess;
+    const int threads = 128;
+    const int grid = (n_slots + threads - 1) / threads;
+    if (a.n_slots != n_slots || a.chunk <= 0) return cudaErrorInvalidValue;
+    sw_generic_kernel<<<grid, threads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_alu_peak(uint32_t *out, int iters, int blocks, int threads, cudaStream_t s)
+{
+    alu_peak_kernel<<<blocks, threads, 0, s>>>(out, iters);
+    return cudaGetLastError();
+}
+
+cudaError_t configure_kernels() { return cudaSuccess; }
+
+}  // namespace fade

@@ -1,0 +1,92 @@
+// kernels.cuh -- sm_100a kernels of the realignment path and their launch descriptors.
+//
+//   sw_fill_kernel<R>    score-only packed-int16x2 wavefront + skewed checkpoints   (P1, P2)
+//   sw_trace_kernel<R>   end cell (P3), block replay with trace, traceback, CIGAR,
+//                        S padding and accept predicates                            (P3-P5, F9)
+//   sw_generic_kernel    exact int32 fallback ON THE DEVICE for wildcard letters and sizes the
+//                        packed kernels do not cover (thread per alignment)
+//   alu_peak_kernel      INT16x2 ALU issue-rate microbenchmark (roofline denominator)
+//
+// Window gather (source/analysis.d:45-64) and reverse complement (source/util.d:18-34) happen
+// inside the kernels from the device-resident packed reference and the BAM 4-bit read bases.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "sw_core.cuh"
+
+namespace fade {
+
+// one alignment = one read with at least one qualifying clip (the left and the right clip of a
+// read are the same SW problem, source/analysis.d:40-67, so it is computed once)
+struct AlnDesc {
+    int64_t gstart;    // global base offset of the window start inside the packed reference
+    int64_t seq_off;   // byte offset of the read's 4-bit bases inside the gathered buffer
+    int32_t tlen;      // window length (end - start)
+    int32_t qlen;      // l_qseq
+    uint32_t clip_left, clip_right;
+    int32_t read;      // index of the read inside the batch
+    int32_t pad;
+};
+
+// one warp = 4 groups = 4 pairs = 8 consecutive alignments of the length-sorted list
+struct WarpItem {
+    int64_t ck_off;    // word offset of this warp's checkpoints inside the scratch
+    int32_t first;     // index of its first alignment
+    int32_t nblk;      // number of 32-step blocks (uniform over the warp)
+};
+
+struct RefDev {
+    RefPlanes planes;
+    const int64_t *xpos;   // sorted global positions of wildcard bases
+    const uint8_t *xchr;   // their upper-cased letters
+    int64_t n_x;
+};
+
+struct KernelArgs {
+    const AlnDesc *aln;
+    int32_t n_aln;
+    const WarpItem *items;
+    int32_t n_items;
+    const uint8_t *seq;        // gathered 4-bit read bases
+    RefDev ref;
+    uint32_t *ck;              // checkpoint scratch
+    uint2 *fillres;            // [n_items*32] per thread: (running max M, first-reached block lo|hi<<16)
+    uint32_t *aln_flags;       // [n_aln] bit0: needs the generic kernel (wildcard letter seen)
+    AlnOut *out;               // [n_aln]
+    SwConsts k;
+    int32_t min_length;
+    int32_t tw_stride;         // uint16 elements per group in shared memory
+};
+
+struct GenericArgs {
+    const AlnDesc *aln;
+    int32_t n_aln;
+    const uint32_t *aln_flags; // nullptr = every alignment of the list
+    const uint8_t *seq;
+    RefDev ref;
+    AlnOut *out;
+    unsigned int *cursor;      // work counter
+    uint8_t *scratch;          // n_slots * slot_bytes
+    int64_t slot_bytes;
+    int32_t qmax, tmax;
+    int32_t n_slots;           // threads that own a scratch slot
+    int32_t chunk;             // work items claimed per atomic
+    int32_t open, extend, match, mismatch, min_length;
+};
+
+constexpr int FILL_THREADS = 128;
+constexpr int TRACE_THREADS = 64;
+constexpr int QMAX_FAST = FG * 32;   // rows covered by the largest packed instantiation
+constexpr int TMAX_FAST = 4000;      // window length covered by the packed kernels
+
+size_t fill_smem_bytes(int tw_stride);
+size_t trace_smem_bytes(int R, int tw_stride);
+int tw_stride_for(int nblk_max);
+
+cudaError_t launch_fill(int R, const KernelArgs &a, cudaStream_t s);
+cudaError_t launch_trace(int R, const KernelArgs &a, cudaStream_t s);
+cudaError_t launch_generic(const GenericArgs &a, int n_slots, cudaStream_t s);
+cudaError_t launch_alu_peak(uint32_t *out, int iters, int blocks, int threads, cudaStream_t s);
+cudaError_t configure_kernels();
+
+}  // namespace fade

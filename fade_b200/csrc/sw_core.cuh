@@ -246,9 +246,9 @@ FD void locate(int i, int j, int &blk, int &u)
 }
 
 // number of 32-step blocks needed for a target of tmax columns
-FD int num_blocks(int tmax) { return (tmax + FG - 1 + FBLK - 1) / FBLK; }
+FD constexpr int num_blocks(int tmax) { return (tmax + FG - 1 + FBLK - 1) / FBLK; }
 // checkpoint words per thread: H[R], E[R], hu_prev, f_out
-template <int R> constexpr int ck_words() { return 2 * R + 2; }
+template <int R> FD constexpr int ck_words() { return 2 * R + 2; }
 
 // ---- per-lane traceback control (lives in shared memory on the device) ---------------------------
 struct LaneCtl {
