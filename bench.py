@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the `fade annotate` realignment hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads M]
+
+One "step" = one pass of the hot path over the whole workload (BASELINE.json configs[1]: 10 M
+simulated 2x150 paired reads against a synthetic 100 Mbp chromosome, default window-size /
+min-length), processed as chunks of --chunk reads through the C ABI (libfadegpu.so).
+
+  value  reads/s with the chunk's inputs already resident in HBM: CUDA-event time of ALL kernel
+         launches of the chunk (fadegpu_replay_kernels), summed over the chunks of a step.
+  e2e    reads/s through the public C ABI with HOST buffers: per chunk the inputs are written
+         into the pinned batch arrays, fadegpu_submit (host binning + H2D + kernels + D2H) and
+         fadegpu_wait (result scatter) run double-buffered, and the rs flags are read back.
+  roofline  the INT16x2 ALU roofline of SURVEY.md 8(d): cells/s against 2*R_alu/9 with R_alu
+         measured live by fadegpu_measure_alu_peak (packed VIADDMNMX.S16x2 issue rate).
+  cpu_baseline  the oracle port (oracle/fade_oracle.c, scalar, OpenMP on all host cores) timed
+         on a bounded sample of the same reads.  `--impl reference` prints that arm on its own.
+
+Multi-GPU: launched under torchrun, one rank per GPU; every rank holds its own reference copy
+and its own shard of reads (weak scaling, no data-path collective); value = all ranks' reads /
+max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+REF_LEN = 100_000_000
+REF_SEED = 1002
+READ_SEED = 2002
+N_READS = 10_000_000
+CHUNK = 1_000_000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="fade_b200", choices=["fade_b200", "reference"])
+    ap.add_argument("--reads", type=int, default=N_READS, help="reads per GPU per step")
+    ap.add_argument("--ref-len", type=int, default=REF_LEN)
+    ap.add_argument("--chunk", type=int, default=CHUNK)
+    ap.add_argument("--cpu-sample", type=int, default=40_000, help="reads in the cpu_baseline sample")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(args, rank: int):
+    from fade_b200 import sim
+    t0 = time.time()
+    ref = sim.make_contig(REF_SEED, 0, args.ref_len, 0, 0, 0.0)
+    cfg = sim.default_cfg(read_seed=READ_SEED)
+    rd = sim.make_reads(cfg, rank * args.reads, args.reads, [ref], with_records=False)
+    return ref, cfg, rd, time.time() - t0
+
+
+def cpu_baseline(ref, rd, n_sample: int, threads: int):
+    """Oracle port on the host cores over the first n_sample reads: reads/s, GCUPS."""
+    from oracle import oracle as orc
+    n = min(n_sample, rd.n)
+    sl = slice(0, n)
+    off = rd.seq_off[: n + 1]
+    contigs = [ref.tobytes()]
+    t0 = time.perf_counter()
+    res, _ = orc.align_batch(rd.seq4[: int(off[n])], off, rd.l_qseq[sl], rd.tid[sl], rd.pos[sl], rd.aligned_len[sl],
+                             rd.clip_left[sl], rd.clip_right[sl], contigs, n_threads=threads)
+    dt = time.perf_counter() - t0
+    al = res["aligned"] == 1
+    cells = int((rd.l_qseq[sl][al].astype(np.int64) * res["tlen"][al]).sum())
+    return n / dt, cells / dt / 1e9, n, dt
+
+
+def run_reference(args, rank: int, world: int):
+    """Reference arm: the reference's CPU implementation of the path.  The real `fade` binary cannot
+    be built here (D + dparasail/parasail + dhtslib/htslib are absent), so this times the oracle
+    port on all host cores (kind "port"), one bounded sample per step."""
+    if rank != 0:
+        return
+    ref, cfg, rd, _ = make_workload(argparse.Namespace(**{**vars(args), "reads": max(args.cpu_sample, 1)}), 0)
+    threads = os.cpu_count() or 1
+    vals, gc = [], []
+    for i in range(args.warmup + args.steps):
+        v, g, n, dt = cpu_baseline(ref, rd, args.cpu_sample, threads)
+        if i >= args.warmup:
+            vals.append(v); gc.append(g)
+    v = statistics.mean(vals)
+    sample = f"first {args.cpu_sample} reads of the workload per step, scalar oracle port, OpenMP {threads} threads"
+    line = {
+        "impl": "reference", "metric": "annotate_reads_per_sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.cpu_sample / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": workload_config(args), "gcups": statistics.mean(gc),
+        "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args) -> dict:
+    return {"workload": f"{args.reads} simulated 2x150 paired reads (seed {READ_SEED}) vs synthetic "
+                        f"{args.ref_len} bp chromosome (seed {REF_SEED}), window-size 300, min-length 5, per GPU",
+            "chunk_reads": args.chunk,
+            "l2": "inputs + checkpoint scratch per chunk (>2 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fade_b200 import Context
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize(local_rank)
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ref, cfg, rd, gen_s = make_workload(args, rank)
+    ctx = Context(local_rank)
+    ctx.load_reference(["chrS"], [ref.tobytes()])
+    alu_ops, max_mhz = ctx.measure_alu_peak()
+
+    n = rd.n
+    chunk = min(args.chunk, n)
+    bounds = [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
+    stride = (cfg.read_len + 1) // 2
+    batches = [ctx.alloc_batch(chunk, chunk * stride) for _ in range(2)]
+
+    def load_chunk(b, a, e):
+        m = e - a
+        b.seq4[: m * stride] = rd.seq4[a * stride: e * stride]
+        b.seq_off[: m + 1] = rd.seq_off[a: e + 1] - rd.seq_off[a]
+        b.l_qseq[:m] = rd.l_qseq[a:e]
+        b.tid[:m] = rd.tid[a:e]
+        b.pos[:m] = rd.pos[a:e]
+        b.aligned_len[:m] = rd.aligned_len[a:e]
+        b.clip_left[:m] = rd.clip_left[a:e]
+        b.clip_right[:m] = rd.clip_right[a:e]
+        b.n = m
+
+    agg = {"aligned": 0, "cells": 0, "h2d": 0, "d2h": 0, "launches": 0, "generic": 0, "art": 0}
+
+    def kernel_step(collect: bool):
+        """inputs resident: per chunk upload untimed, then time only the kernels (CUDA events)."""
+        ms = fill = trace = gen = 0.0
+        for (a, e) in bounds:
+            b = batches[0]
+            load_chunk(b, a, e)
+            b.run()                          # untimed: makes the chunk resident in HBM
+            ms += b.replay_kernels(1)        # timed on the ctx stream with CUDA events
+            st = b.stats()
+            fill += st.fill_ms; trace += st.trace_ms; gen += st.generic_ms
+            if collect:
+                agg["aligned"] += st.n_aligned; agg["cells"] += st.cells; agg["launches"] += st.kernel_launches
+                agg["generic"] += st.n_generic
+                agg["h2d"] += st.h2d_bytes; agg["d2h"] += st.d2h_bytes
+                agg["art"] += int(((b.flags[: b.n] & 6) != 0).sum())
+        return ms, fill, trace, gen
+
+    def e2e_step():
+        """host buffers -> C ABI -> host results, double-buffered; wall clock around the whole step."""
+        t0 = time.perf_counter()
+        pending = None
+        acc = 0
+        for i, (a, e) in enumerate(bounds):
+            b = batches[i & 1]
+            load_chunk(b, a, e)
+            b.submit()
+            if pending is not None:
+                pending.wait()
+                acc += int(pending.flags[: pending.n].sum())     # read the step's result on the host
+            pending = b
+        pending.wait()
+        acc += int(pending.flags[: pending.n].sum())
+        return time.perf_counter() - t0, acc
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        kernel_step(False)
+    e2e_step()
+
+    # ---- timed: kernels with resident inputs ----
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    k_ms = k_fill = k_trace = k_gen = 0.0
+    for s in range(args.steps):
+        ms, f, t, g = kernel_step(s == 0)
+        k_ms += ms; k_fill += f; k_trace += t; k_gen += g
+    barrier()
+    # ---- timed: end to end through the C ABI ----
+    e_s = 0.0
+    for s in range(args.steps):
+        barrier()
+        dt, _ = e2e_step()
+        e_s += dt
+    barrier()
+    clocks = sampler.stop()
+
+    k_ms_max = max_over_ranks(k_ms)
+    e_s_max = max_over_ranks(e_s)
+    total_reads = sum_over_ranks(float(n))
+    total_cells = sum_over_ranks(float(agg["cells"]))
+    total_aligned = sum_over_ranks(float(agg["aligned"]))
+    ms_per_step = k_ms_max / args.steps
+    value = total_reads / (ms_per_step * 1e-3)
+    e2e_value = total_reads / (e_s_max / args.steps)
+
+    if rank == 0:
+        cells_rank = float(agg["cells"])
+        achieved = cells_rank / (k_ms / args.steps * 1e-3) / 1e9            # GCUPS, all kernels of the path
+        fill_gcups = cells_rank / (k_fill / args.steps * 1e-3) / 1e9 if k_fill > 0 else None
+        peak = 2.0 * alu_ops / 9.0 / 1e9                                    # 9 packed instr / 2 cells
+        # algorithmic HBM bytes per alignment: window 2-bit + N mask, query, metadata, result
+        n_al = max(agg["aligned"], 1)
+        hbm_bytes = agg["h2d"] + agg["d2h"] + n_al * 270
+        cb_v, cb_g, cb_n, cb_dt = cpu_baseline(ref, rd, args.cpu_sample, os.cpu_count() or 1)
+        line = {
+            "metric": "annotate_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
+            "data": "synthetic", "config": workload_config(args),
+            "gcups": total_cells / (ms_per_step * 1e-3) / 1e9,
+            "aligned_reads_per_step": total_aligned, "artifact_reads_rank0": agg["art"],
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": agg["h2d"],
+                    "d2h_bytes_per_step": agg["d2h"], "ms_per_step": 1e3 * e_s_max / args.steps},
+            "gpu_launches": agg["launches"] * args.steps,
+            "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "GCUPS",
+                         "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                         "kernel": "sw_fill_kernel<19> + sw_trace_kernel<19> (whole path)",
+                         "fill_only_gcups": fill_gcups,
+                         "fill_ms": k_fill / args.steps, "trace_ms": k_trace / args.steps,
+                         "generic_ms": k_gen / args.steps,
+                         "r_alu_thread_instr_per_s": alu_ops, "peak_source": "measured live (fadegpu_measure_alu_peak)",
+                         "hbm": {"algorithmic_gbs": hbm_bytes / (k_ms / args.steps * 1e-3) / 1e9,
+                                 "peak_gbs": peak_hbm()}},
+            "cpu_baseline": {"value": cb_v, "unit": "reads/s", "cores": os.cpu_count() or 1, "kind": "port",
+                             "gcups": cb_g,
+                             "sample": f"first {cb_n} reads of the workload, scalar oracle port, OpenMP all cores, {cb_dt:.1f} s"},
+            "gen_seconds": gen_s,
+        }
+        print(json.dumps(line), flush=True)
+    for b in batches:
+        b.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f).get("hbm_gbs")
+    except Exception:
+        return 6650.0
+
+
+if __name__ == "__main__":
+    main()
