@@ -24,7 +24,7 @@ struct ThreadState {
 template <int R>
 int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
                const uint8_t *qb, int qlen_b, const uint8_t *tb, int tlen_b,
-               const SwConsts &k, int extra_blocks, int32_t min_length,
+               const SwConsts &k, int extra_blocks, int tagged, int32_t min_length,
                uint32_t clipl_a, uint32_t clipr_a, uint32_t clipl_b, uint32_t clipr_b,
                AlnOut *out_a, AlnOut *out_b)
 {
@@ -95,7 +95,9 @@ int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
     // ---- traceback: replay blocks with trace recording ----
     ctl_init(ctl[0], qlen_a, tlen_a);
     ctl_init(ctl[1], qlen_b, tlen_b);
-    std::vector<uint8_t> tr((size_t)FBLK * rows);
+    constexpr int RW = trace_words<R>();
+    std::vector<uint32_t> tr((size_t)FBLK * FG * RW);
+    const bool tg = tagged && k.tagged_ok;
     int guard = 0;
     while (ctl[0].phase != 2 || ctl[1].phase != 2) {
         if (++guard > 4 * nblk + 16) return -2;
@@ -115,11 +117,16 @@ int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
                 s.hu_prev = p[2 * R]; s.fout = p[2 * R + 1];
             };
             load(s0, blk[0]); load(s1, blk[1]);
-            auto mix = [](uint32_t a, uint32_t b) { return (a & 0xffffu) | (b & 0xffff0000u); };
+            auto mix = [&](uint32_t a, uint32_t b) {
+                const uint32_t w = (a & 0xffffu) | (b & 0xffff0000u);
+                return tg ? to_tagged(w) : w;
+            };
             for (int r = 0; r < R; ++r) { st[g].H[r] = mix(s0.H[r], s1.H[r]); st[g].E[r] = mix(s0.E[r], s1.E[r]); }
             st[g].hu_prev = mix(s0.hu_prev, s1.hu_prev);
             st[g].fout = mix(s0.fout, s1.fout);
         }
+        const uint32_t f_top = tg ? k.neg_o16 : k.neg_o;
+        const int mul = tg ? 16 : 1;
         bool found[2][FG];
         for (int L = 0; L < 2; ++L) for (int g = 0; g < FG; ++g) found[L][g] = false;
         for (int u = 0; u < FBLK; ++u) {
@@ -127,25 +134,36 @@ int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
             uint32_t hu[FG], fin[FG];
             for (int g = 0; g < FG; ++g) {
                 hu[g] = g == 0 ? 0u : st[g - 1].H[R - 1];
-                fin[g] = g == 0 ? k.neg_o : st[g - 1].fout;
+                fin[g] = g == 0 ? f_top : st[g - 1].fout;
             }
             for (int g = 0; g < FG; ++g) {
                 const uint32_t ts = (tw[t0 - g + FG] & 0x00ffu) | (tw[t1 - g + FG] & 0xff00u);
-                int hit0, hit1;
-                const int s0 = (scan[0][g] && !found[0][g]) ? ctl[0].S : -1;
-                const int s1 = (scan[1][g] && !found[1][g]) ? ctl[1].S : -1;
-                trace_step<R>(st[g].H, st[g].E, st[g].qs, ts, st[g].hu_prev, fin[g], st[g].fout, k,
-                              &tr[(size_t)u * rows + g * R], s0, s1, hit0, hit1);
+                uint32_t cmax = 0;
+                uint32_t *trw = &tr[(size_t)(u * FG + g) * RW];
+                if (tg) trace_step_tagged<R>(st[g].H, st[g].E, st[g].qs, ts, st[g].hu_prev, fin[g], st[g].fout, k, trw, cmax);
+                else trace_step_plain<R>(st[g].H, st[g].E, st[g].qs, ts, st[g].hu_prev, fin[g], st[g].fout, k, trw, cmax);
                 st[g].hu_prev = hu[g];
-                if (s0 >= 0 && hit0 < R) { found[0][g] = true; ctl[0].fj[g] = t0 - g; ctl[0].fr[g] = hit0; }
-                if (s1 >= 0 && hit1 < R) { found[1][g] = true; ctl[1].fj[g] = t1 - g; ctl[1].fr[g] = hit1; }
+                for (int L = 0; L < 2; ++L) {
+                    if (!scan[L][g] || found[L][g]) continue;
+                    const int cm = L == 0 ? lane_lo(cmax) : lane_hi(cmax);
+                    if (cm != ctl[L].S * mul) continue;
+                    for (int r = 0; r < R; ++r) {
+                        const int hv = L == 0 ? lane_lo(st[g].H[r]) : lane_hi(st[g].H[r]);
+                        if (hv == ctl[L].S * mul) {
+                            found[L][g] = true;
+                            ctl[L].fj[g] = (L == 0 ? t0 : t1) - g;
+                            ctl[L].fr[g] = r;
+                            break;
+                        }
+                    }
+                }
             }
         }
         for (int L = 0; L < 2; ++L)
             for (int g = 0; g < FG; ++g)
                 if (scan[L][g] && !found[L][g]) return -3;  // a candidate must find its cell
-        ctl_advance<R>(ctl[0], tr.data(), rows, 0, tw.data(), qc.data());
-        ctl_advance<R>(ctl[1], tr.data(), rows, 4, tw.data(), qc.data());
+        ctl_advance<R>(ctl[0], tr.data(), 0, tw.data(), qc.data(), k);
+        ctl_advance<R>(ctl[1], tr.data(), 1, tw.data(), qc.data(), k);
     }
     finalize_result(ctl[0], *out_a, 0, clipl_a, clipr_a, min_length);
     finalize_result(ctl[1], *out_b, 1, clipl_b, clipr_b, min_length);
@@ -157,14 +175,14 @@ int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
 extern "C" int fadeemu_align_pair(int R, const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
                                   const uint8_t *qb, int qlen_b, const uint8_t *tb, int tlen_b,
                                   int open, int extend, int match, int mismatch, int extra_blocks,
-                                  int min_length, const uint32_t *clips /*[4]: la ra lb rb*/,
+                                  int tagged, int min_length, const uint32_t *clips /*[4]: la ra lb rb*/,
                                   AlnOut *out_a, AlnOut *out_b)
 {
     const SwConsts k = make_consts(open, extend, match, mismatch);
 #define CASE(RR)                                                                                   \
     case RR:                                                                                       \
         return align_pair<RR>(qa, qlen_a, ta, tlen_a, qb, qlen_b, tb, tlen_b, k, extra_blocks,    \
-                              min_length, clips[0], clips[1], clips[2], clips[3], out_a, out_b);
+                              tagged, min_length, clips[0], clips[1], clips[2], clips[3], out_a, out_b);
     switch (R) {
         CASE(1) CASE(2) CASE(3) CASE(5) CASE(13) CASE(19) CASE(32)
     default: return -10;

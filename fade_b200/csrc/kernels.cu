@@ -115,10 +115,18 @@ __global__ void __launch_bounds__(FILL_THREADS) sw_fill_kernel(const KernelArgs 
 // end cell + traceback by block replay
 // ------------------------------------------------------------------------------------------------
 template <int R>
+__host__ __device__ inline size_t trace_group_bytes(int tw_stride)
+{
+    return align16((size_t)tw_stride * 2) + align16((size_t)FBLK * FG * trace_words<R>() * 4) +
+           align16((size_t)FG * R) + align16(2 * sizeof(LaneCtl));
+}
+
+template <int R, bool TAGGED>
 __global__ void __launch_bounds__(TRACE_THREADS) sw_trace_kernel(const KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int rows = FG * R;
+    constexpr int RW = trace_words<R>();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = lane & (FG - 1), q = lane >> 3;
     const int w = blockIdx.x * (TRACE_THREADS / 32) + wib;
@@ -129,12 +137,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) sw_trace_kernel(const KernelArg
     const int nblk = item.nblk;
     const SwConsts k = a.k;
 
-    const size_t group_bytes = align16((size_t)a.tw_stride * 2) + align16((size_t)FBLK * rows) +
-                               align16(rows) + align16(2 * sizeof(LaneCtl));
-    unsigned char *base = smem_raw + (size_t)(wib * 4 + q) * group_bytes;
+    unsigned char *base = smem_raw + (size_t)(wib * 4 + q) * trace_group_bytes<R>(a.tw_stride);
     uint16_t *tw = reinterpret_cast<uint16_t *>(base);
-    uint8_t *tr = base + align16((size_t)a.tw_stride * 2);
-    uint8_t *qc = tr + align16((size_t)FBLK * rows);
+    uint32_t *tr = reinterpret_cast<uint32_t *>(base + align16((size_t)a.tw_stride * 2));
+    uint8_t *qc = reinterpret_cast<uint8_t *>(tr) + align16((size_t)FBLK * FG * RW * 4);
     LaneCtl *ctl = reinterpret_cast<LaneCtl *>(qc + align16(rows));
     LaneCtl &c0 = ctl[0];
     LaneCtl &c1 = ctl[1];
@@ -152,9 +158,11 @@ __global__ void __launch_bounds__(TRACE_THREADS) sw_trace_kernel(const KernelArg
     else if (g == 1) ctl_init(c1, db.qlen, db.tlen);
 
     constexpr int CW = ck_words<R>();
+    constexpr int MUL = TAGGED ? 16 : 1;
+    const uint32_t e_init = TAGGED ? k.neg_o16 : k.neg_o;
     const uint32_t *ckw = a.ck + item.ck_off + lane;
     const uint16_t *twp = tw + (FG - g);
-    uint8_t *trg = tr + g * R;
+    uint32_t *trg = tr + g * RW;
     bool overrun = false;
     for (int iter = 0;; ++iter) {
         __syncwarp();
@@ -165,8 +173,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) sw_trace_kernel(const KernelArg
         const int b0 = (ph0 != 2 && c0.next_blk >= 0) ? c0.next_blk : 0;
         const int b1 = (ph1 != 2 && c1.next_blk >= 0) ? c1.next_blk : 0;
         const bool sc0 = ctl_scan_me(c0, g), sc1 = ctl_scan_me(c1, g);
-        const int S0 = c0.S, S1 = c1.S;
-        // lane a state from checkpoint b0-1, lane b state from checkpoint b1-1
+        const int S0 = c0.S * MUL, S1 = c1.S * MUL;
+        // lane a state from checkpoint b0-1, lane b state from checkpoint b1-1 (plain domain)
         uint32_t hu_prev, fout;
         {
             const uint32_t *p0 = ckw + (size_t)(b0 > 0 ? b0 - 1 : 0) * CW * 32;
@@ -176,35 +184,46 @@ __global__ void __launch_bounds__(TRACE_THREADS) sw_trace_kernel(const KernelArg
             for (int r = 0; r < R; ++r) {
                 const uint32_t h0 = z0 ? 0u : p0[r * 32], h1 = z1 ? 0u : p1[r * 32];
                 const uint32_t e0 = z0 ? k.neg_o : p0[(R + r) * 32], e1 = z1 ? k.neg_o : p1[(R + r) * 32];
-                H[r] = (h0 & 0xffffu) | (h1 & 0xffff0000u);
-                E[r] = (e0 & 0xffffu) | (e1 & 0xffff0000u);
+                const uint32_t hw = (h0 & 0xffffu) | (h1 & 0xffff0000u);
+                const uint32_t ew = (e0 & 0xffffu) | (e1 & 0xffff0000u);
+                H[r] = TAGGED ? to_tagged(hw) : hw;
+                E[r] = TAGGED ? to_tagged(ew) : ew;
             }
             const uint32_t u0 = z0 ? 0u : p0[(2 * R) * 32], u1 = z1 ? 0u : p1[(2 * R) * 32];
             const uint32_t f0 = z0 ? k.neg_o : p0[(2 * R + 1) * 32], f1 = z1 ? k.neg_o : p1[(2 * R + 1) * 32];
-            hu_prev = (u0 & 0xffffu) | (u1 & 0xffff0000u);
-            fout = (f0 & 0xffffu) | (f1 & 0xffff0000u);
+            const uint32_t uw = (u0 & 0xffffu) | (u1 & 0xffff0000u);
+            const uint32_t fw = (f0 & 0xffffu) | (f1 & 0xffff0000u);
+            hu_prev = TAGGED ? to_tagged(uw) : uw;
+            fout = TAGGED ? to_tagged(fw) : fw;
         }
-        bool found0 = false, found1 = false;
+        bool need0 = sc0, need1 = sc1;   // still looking for the first H == S cell
         int fj0 = 0, fr0 = 0, fj1 = 0, fr1 = 0;
         for (int u = 0; u < FBLK; ++u) {
             const int t0 = b0 * FBLK + u, t1 = b1 * FBLK + u;
             uint32_t hu = __shfl_up_sync(FULL, H[R - 1], 1, FG);
             uint32_t fin = __shfl_up_sync(FULL, fout, 1, FG);
-            if (g == 0) { hu = 0u; fin = k.neg_o; }
+            if (g == 0) { hu = 0u; fin = e_init; }
             const uint32_t ts = ((uint32_t)twp[t0] & 0x00ffu) | ((uint32_t)twp[t1] & 0xff00u);
-            int hit0, hit1;
-            const int s0 = (sc0 && !found0) ? S0 : -1;
-            const int s1 = (sc1 && !found1) ? S1 : -1;
-            trace_step<R>(H, E, qs, ts, hu_prev, fin, fout, k, trg + u * rows, s0, s1, hit0, hit1);
+            uint32_t cmax = 0u;
+            if (TAGGED) trace_step_tagged<R>(H, E, qs, ts, hu_prev, fin, fout, k, trg + u * (FG * RW), cmax);
+            else trace_step_plain<R>(H, E, qs, ts, hu_prev, fin, fout, k, trg + u * (FG * RW), cmax);
             hu_prev = hu;
-            if (s0 >= 0 && hit0 < R) { found0 = true; fj0 = t0 - g; fr0 = hit0; }
-            if (s1 >= 0 && hit1 < R) { found1 = true; fj1 = t1 - g; fr1 = hit1; }
+            if (need0 && lane_lo(cmax) == S0) {
+                need0 = false; fj0 = t0 - g; fr0 = 0;
+#pragma unroll
+                for (int r = R - 1; r >= 0; --r) if (lane_lo(H[r]) == S0) fr0 = r;
+            }
+            if (need1 && lane_hi(cmax) == S1) {
+                need1 = false; fj1 = t1 - g; fr1 = 0;
+#pragma unroll
+                for (int r = R - 1; r >= 0; --r) if (lane_hi(H[r]) == S1) fr1 = r;
+            }
         }
-        if (sc0) { c0.fj[g] = found0 ? fj0 : 0; c0.fr[g] = found0 ? fr0 : 0; }
-        if (sc1) { c1.fj[g] = found1 ? fj1 : 0; c1.fr[g] = found1 ? fr1 : 0; }
+        if (sc0) { c0.fj[g] = fj0; c0.fr[g] = fr0; }
+        if (sc1) { c1.fj[g] = fj1; c1.fr[g] = fr1; }
         __syncwarp();
-        if (g == 0) ctl_advance<R>(c0, tr, rows, 0, tw, qc);
-        else if (g == 1) ctl_advance<R>(c1, tr, rows, 4, tw, qc);
+        if (g == 0) ctl_advance<R>(c0, tr, 0, tw, qc, k);
+        else if (g == 1) ctl_advance<R>(c1, tr, 1, tw, qc, k);
     }
     __syncwarp();
     // results (alignments that met a wildcard letter are produced by the generic kernel instead)
@@ -405,9 +424,12 @@ size_t fill_smem_bytes(int tw_stride) { return (size_t)(FILL_THREADS / FG) * tw_
 
 size_t trace_smem_bytes(int R, int tw_stride)
 {
-    const size_t rows = (size_t)FG * R;
-    const size_t group = align16((size_t)tw_stride * 2) + align16((size_t)FBLK * rows) + align16(rows) +
-                         align16(2 * sizeof(LaneCtl));
+    size_t group = 0;
+    switch (R) {
+    case 13: group = trace_group_bytes<13>(tw_stride); break;
+    case 19: group = trace_group_bytes<19>(tw_stride); break;
+    default: group = trace_group_bytes<32>(tw_stride); break;
+    }
     return (size_t)(TRACE_THREADS / FG) * group;
 }
 
@@ -423,16 +445,22 @@ static cudaError_t launch_fill_t(const KernelArgs &a, cudaStream_t s)
     return cudaGetLastError();
 }
 
-template <int R>
-static cudaError_t launch_trace_t(const KernelArgs &a, cudaStream_t s)
+template <int R, bool TAGGED>
+static cudaError_t launch_trace_tt(const KernelArgs &a, cudaStream_t s)
 {
     const size_t smem = trace_smem_bytes(R, a.tw_stride);
-    cudaError_t e = cudaFuncSetAttribute(sw_trace_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(sw_trace_kernel<R, TAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int wpb = TRACE_THREADS / 32;
     const int grid = (a.n_items + wpb - 1) / wpb;
-    sw_trace_kernel<R><<<grid, TRACE_THREADS, smem, s>>>(a);
+    sw_trace_kernel<R, TAGGED><<<grid, TRACE_THREADS, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t launch_trace_t(const KernelArgs &a, cudaStream_t s)
+{
+    return a.k.tagged_ok ? launch_trace_tt<R, true>(a, s) : launch_trace_tt<R, false>(a, s);
 }
 
 cudaError_t launch_fill(int R, const KernelArgs &a, cudaStream_t s)

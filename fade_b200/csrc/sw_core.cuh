@@ -39,6 +39,12 @@ struct SwConsts {
     uint32_t lut0, lut1;  // PRMT byte LUT indexed by (qcode ^ tcode): [0] = match, [1..7] = mismatch
     uint32_t neg_o, neg_e;  // packed (-open,-open), (-extend,-extend)
     int32_t open, extend, match, mismatch;
+    // "tagged" x16 domain of the trace replay (value = 16*score + tag, see trace_step)
+    uint32_t tlut0, tlut1;      // byte LUT of 16*s + 8 (the DIAG tag)
+    uint32_t neg_o16;           // packed -16*open
+    uint32_t neg_e16_e;         // packed -16*extend + 1 (E extension tag)
+    uint32_t neg_e16_f;         // packed -16*extend + 2 (F extension tag)
+    int32_t tagged_ok;          // scoring fits the tagged encoding
 };
 
 FD SwConsts make_consts(int open, int extend, int match, int mismatch)
@@ -51,6 +57,16 @@ FD SwConsts make_consts(int open, int extend, int match, int mismatch)
     k.neg_o = no | (no << 16);
     k.neg_e = ne | (ne << 16);
     k.open = open; k.extend = extend; k.match = match; k.mismatch = mismatch;
+    const int tm = 16 * match + 8, tx = 16 * mismatch + 8;
+    k.tagged_ok = (tm <= 127 && tx >= -128 && open <= 1000) ? 1 : 0;
+    const uint32_t bm = (uint32_t)(tm & 0xff), bx = (uint32_t)(tx & 0xff);
+    k.tlut0 = bm | (bx << 8) | (bx << 16) | (bx << 24);
+    k.tlut1 = bx | (bx << 8) | (bx << 16) | (bx << 24);
+    const uint32_t o16 = (uint32_t)((-16 * open) & 0xffff);
+    const uint32_t ee = (uint32_t)((-16 * extend + 1) & 0xffff), ef = (uint32_t)((-16 * extend + 2) & 0xffff);
+    k.neg_o16 = o16 | (o16 << 16);
+    k.neg_e16_e = ee | (ee << 16);
+    k.neg_e16_f = ef | (ef << 16);
     return k;
 }
 
@@ -189,50 +205,89 @@ FD void fill_step(uint32_t (&H)[R], uint32_t (&E)[R], const uint32_t (&qs)[R], u
     f_out = f;
 }
 
-// Trace nibble of a cell: bits 0-1 = source of H (P4 priority DIAG/ZERO > F > E),
-// bit 2 = "E[i][j+1] was opened from H[i][j]" (open iff H-o > E-e, ties extend),
-// bit 3 = "F[i+1][j] was opened from H[i][j]".
-enum : int { T_ZERO = 0, T_DIAG = 1, T_F = 2, T_E = 3, T_EOPEN = 4, T_FOPEN = 8 };
+// Trace nibble of cell (i,j) (one per int16 lane):
+//   bit 0   = E[i][j+1] was obtained by EXTENSION (0: opened from H[i][j]; open iff H-o > E-e)
+//   bit 1   = F[i+1][j] was obtained by EXTENSION
+//   bits 2-3 = source of H[i][j]: 2 = DIAG, 1 = F, 0 = E   (P4 priority DIAG > F > E)
+// A cell with H == 0 always stops the traceback (ZERO); the walker knows H along the path, so
+// ZERO needs no code of its own.
+// Storage: one 32-bit word per (step, thread, row quad): rows 4w..4w+3 of lane a in bits 0-15,
+// of lane b in bits 16-31.
+template <int R> FD constexpr int trace_words() { return (R + 3) / 4; }
 
-FD int trace_nibble(int d0, int ev, int fv, int h, int o, int e)
+FD uint32_t trace_nibble_plain(int d0, int ev, int fv, int h, int o, int e)
 {
-    int nib;
-    if (h == d0) nib = (h == 0) ? T_ZERO : T_DIAG;
-    else nib = (h == fv) ? T_F : T_E;
-    if (h - o > ev - e) nib |= T_EOPEN;
-    if (h - o > fv - e) nib |= T_FOPEN;
+    uint32_t nib = (h == d0) ? 8u : ((h == fv) ? 4u : 0u);
+    if (!(h - o > ev - e)) nib |= 1u;
+    if (!(h - o > fv - e)) nib |= 2u;
     return nib;
 }
 
-// Same step with trace recording.  trow[r] receives (nibble_hi << 4 | nibble_lo) for row r.
-// hit_lo / hit_hi: first row r (or R) whose H equals s_lo / s_hi in this column.
+// Wavefront step with trace recording, plain score domain, any scoring (unpacked compares).
+// trw receives trace_words<R>() words; cmax accumulates the packed maximum of H over the rows.
 template <int R>
-FD void trace_step(uint32_t (&H)[R], uint32_t (&E)[R], const uint32_t (&qs)[R],
-                   uint32_t ts, uint32_t hdiag, uint32_t f_in, uint32_t &f_out, const SwConsts &k,
-                   uint8_t *trow, int s_lo, int s_hi, int &hit_lo, int &hit_hi)
+FD void trace_step_plain(uint32_t (&H)[R], uint32_t (&E)[R], const uint32_t (&qs)[R],
+                         uint32_t ts, uint32_t hdiag, uint32_t f_in, uint32_t &f_out, const SwConsts &k,
+                         uint32_t *trw, uint32_t &cmax)
 {
-    uint32_t f = f_in;
-    hit_lo = R;
-    hit_hi = R;
+    uint32_t f = f_in, acc = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const uint32_t s = score_word(qs[r], ts, k);
         const uint32_t d0 = FADE_VIADDMAX_RELU(hdiag, s, 0u);
         const uint32_t ev = E[r];
         const uint32_t h = FADE_VMAX(FADE_VMAX(d0, ev), f);
-        const int nl = trace_nibble(lane_lo(d0), lane_lo(ev), lane_lo(f), lane_lo(h), k.open, k.extend);
-        const int nh = trace_nibble(lane_hi(d0), lane_hi(ev), lane_hi(f), lane_hi(h), k.open, k.extend);
-        trow[r] = (uint8_t)(nl | (nh << 4));
-        if (hit_lo == R && lane_lo(h) == s_lo) hit_lo = r;
-        if (hit_hi == R && lane_hi(h) == s_hi) hit_hi = r;
+        const uint32_t nl = trace_nibble_plain(lane_lo(d0), lane_lo(ev), lane_lo(f), lane_lo(h), k.open, k.extend);
+        const uint32_t nh = trace_nibble_plain(lane_hi(d0), lane_hi(ev), lane_hi(f), lane_hi(h), k.open, k.extend);
+        acc |= (nl | (nh << 16)) << (4 * (r & 3));
+        if ((r & 3) == 3 || r == R - 1) { trw[r >> 2] = acc; acc = 0; }
         hdiag = H[r];
         H[r] = h;
+        cmax = FADE_VMAX(cmax, h);
         const uint32_t ho = FADE_VADD(h, k.neg_o);
         E[r] = FADE_VIADDMAX(ev, k.neg_e, ho);
         f = FADE_VIADDMAX(f, k.neg_e, ho);
     }
     f_out = f;
 }
+
+// Same step in the TAGGED domain: every value is 16*score + tag, and the tag of the winner of
+// each packed max IS the trace decision, so no compare / select instructions are needed:
+//   DIAG candidate  16*(Hdiag+s) + 8        F candidate  16*F + 4 (+2 if F was extended)
+//   E candidate     16*E (+1 if E was extended)
+//   E' = max(16*(H-o) [tag 0 = opened], 16*(E-e) + 1 [extended wins ties])   likewise F' with +2.
+// H[] holds CLEAN values (tag stripped); E[] and f carry their extension tag.
+template <int R>
+FD void trace_step_tagged(uint32_t (&H)[R], uint32_t (&E)[R], const uint32_t (&qs)[R],
+                          uint32_t ts, uint32_t hdiag, uint32_t f_in, uint32_t &f_out, const SwConsts &k,
+                          uint32_t *trw, uint32_t &cmax)
+{
+    uint32_t f = f_in, acc = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t s16 = prmt_sx(k.tlut0, k.tlut1, qs[r] ^ ts);
+        const uint32_t t1 = FADE_VIADDMAX_RELU(hdiag, s16, E[r]);
+        const uint32_t hv = FADE_VIADDMAX(f, 0x00040004u, t1);
+        const uint32_t hc = hv & 0xfff0fff0u;
+        hdiag = H[r];
+        H[r] = hc;
+        cmax = FADE_VMAX(cmax, hc);
+        const uint32_t ho = FADE_VADD(hc, k.neg_o16);
+        const uint32_t en = FADE_VIADDMAX(E[r] & 0xfff0fff0u, k.neg_e16_e, ho);
+        const uint32_t fn = FADE_VIADDMAX(f & 0xfff0fff0u, k.neg_e16_f, ho);
+        E[r] = en;
+        f = fn;
+        const uint32_t nib = (hv & 0x000c000cu) | ((en | fn) & 0x00030003u);
+        acc += nib << (4 * (r & 3));
+        if ((r & 3) == 3 || r == R - 1) { trw[r >> 2] = acc; acc = 0; }
+    }
+    f_out = f;
+}
+
+// plain -> tagged domain (checkpoints are stored in the plain domain)
+FD uint32_t to_tagged(uint32_t w) { return (w << 4) & 0xfff0fff0u; }
+
+enum : int { T_ZERO = 0, T_DIAG = 1, T_F = 2, T_E = 3, T_EOPEN = 4, T_FOPEN = 8 };  // generic kernel
 
 // ---- geometry -----------------------------------------------------------------------------------
 // cell (i,j) is computed by thread g = i / R at step t = j + g; block = t / FBLK, u = t % FBLK.
@@ -265,6 +320,7 @@ struct LaneCtl {
     int32_t cur_blk;    // block whose trace currently sits in shared memory (-1 none)
     // walker
     int32_t i, j, mode; // mode 0 = H, 1 = arrived in F, 2 = arrived in E
+    int32_t hval, gval; // H of the current cell (mode 0) / value of the gap state we came from
     int32_t end_i, end_j;
     int32_t nrev;       // completed reversed RLE ops pushed so far
     uint32_t cur;       // op being accumulated (len<<4|op), 0 = none
@@ -282,6 +338,7 @@ FD void ctl_init(LaneCtl &c, int qlen, int tlen)
     c.cur_blk = -1;
     c.nrev = 0; c.cur = 0;
     c.i = c.j = c.mode = 0;
+    c.hval = c.gval = 0;
     c.end_i = c.end_j = 0;
     if (S <= 0 || qlen <= 0 || tlen <= 0) { c.phase = 2; c.next_blk = -1; return; }
     c.phase = 0;
@@ -303,14 +360,15 @@ FD void walk_push(LaneCtl &c, uint32_t op)
     c.cur = (1u << 4) | op;
 }
 
-// After a replay of block c.next_blk (trace of that block is in tr[u*rows + row], lane nibble at
-// `shift`): advance the per-lane state machine.  tw = staged target words, qc = staged query codes.
-// P3 (end cell) and P4 (traceback) of SURVEY 8a.
+// After a replay of block c.next_blk (its trace words are in tr, see trace_step): advance the
+// per-lane state machine.  lane = 0/1 (int16 lane of the pair), tw = staged target words,
+// qc = staged query codes.  P3 (end cell) and P4 (traceback) of SURVEY 8a.
 template <int R>
-FD void ctl_advance(LaneCtl &c, const uint8_t *tr, int rows, int shift,
-                    const uint16_t *tw, const uint8_t *qc)
+FD void ctl_advance(LaneCtl &c, const uint32_t *tr, int lane, const uint16_t *tw, const uint8_t *qc,
+                    const SwConsts &k)
 {
     if (c.phase == 2) return;
+    constexpr int RW = trace_words<R>();
     c.cur_blk = c.next_blk;
     if (c.phase == 0) {
         for (int g = 0; g < FG; ++g)
@@ -326,31 +384,35 @@ FD void ctl_advance(LaneCtl &c, const uint8_t *tr, int rows, int shift,
         c.end_j = c.fj[bg];
         c.end_i = bg * R + c.fr[bg];
         c.i = c.end_i; c.j = c.end_j; c.mode = 0;
+        c.hval = c.S;
         c.phase = 1;
     }
     // P4: walk while the current cell lies in the block held in shared memory
     for (;;) {
         if (c.i < 0 || c.j < 0) { c.phase = 2; break; }
-        int blk, u;
-        locate<R>(c.i, c.j, blk, u);
+        if (c.mode == 0 && c.hval <= 0) { c.phase = 2; break; }   // ZERO
+        const int g = c.i / R, r = c.i - g * R;
+        const int t = c.j + g;
+        const int blk = t / FBLK, u = t % FBLK;
         if (blk != c.cur_blk) { c.next_blk = blk; return; }
-        const int nib = (tr[u * rows + c.i] >> shift) & 0xf;
+        const uint32_t nib = (tr[(u * FG + g) * RW + (r >> 2)] >> (16 * lane + 4 * (r & 3))) & 0xfu;
         if (c.mode == 0) {
-            const int src = nib & 3;
-            if (src == T_ZERO) { c.phase = 2; break; }
-            if (src == T_DIAG) {
-                const int qcode = (qc[c.i] >> shift) & 0x7;
-                const int tcode = (tw[c.j + FG] >> (2 * shift)) & 0x7;
-                walk_push(c, qcode == tcode ? OP_EQ : OP_X);
+            const uint32_t src = nib >> 2;
+            if (src == 2u) {
+                const int qcode = (qc[c.i] >> (4 * lane)) & 0x7;
+                const int tcode = (tw[c.j + FG] >> (8 * lane)) & 0x7;
+                const bool eq = qcode == tcode;
+                walk_push(c, eq ? OP_EQ : OP_X);
+                c.hval -= eq ? k.match : k.mismatch;
                 --c.i; --c.j;
-            } else if (src == T_F) { walk_push(c, OP_I); --c.i; c.mode = 1; }
-            else { walk_push(c, OP_D); --c.j; c.mode = 2; }
+            } else if (src == 1u) { walk_push(c, OP_I); --c.i; c.mode = 1; c.gval = c.hval; }
+            else { walk_push(c, OP_D); --c.j; c.mode = 2; c.gval = c.hval; }
         } else if (c.mode == 1) {
-            if (nib & T_FOPEN) c.mode = 0;
-            else { walk_push(c, OP_I); --c.i; }
+            if (!(nib & 2u)) { c.hval = c.gval + k.open; c.mode = 0; }
+            else { walk_push(c, OP_I); --c.i; c.gval += k.extend; }
         } else {
-            if (nib & T_EOPEN) c.mode = 0;
-            else { walk_push(c, OP_D); --c.j; }
+            if (!(nib & 1u)) { c.hval = c.gval + k.open; c.mode = 0; }
+            else { walk_push(c, OP_D); --c.j; c.gval += k.extend; }
         }
     }
     // done: flush the op being accumulated

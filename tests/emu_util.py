@@ -40,7 +40,7 @@ def lib():
         build_emu()
         L = C.CDLL(EMU_SO)
         L.fadeemu_align_pair.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
-                                         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.POINTER(AlnOut), C.POINTER(AlnOut)]
         L.fadeemu_align_pair.restype = C.c_int
         L.fadeemu_prmt.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
@@ -54,12 +54,13 @@ def codes(s: str) -> np.ndarray:
     return np.array([CODE.get(c.upper(), 5) for c in s], dtype=np.uint8)
 
 
-def align_pair(R, qa, ta, qb, tb, clips=(0, 0, 0, 0), scoring=(10, 2, 2, -3), extra_blocks=0, min_length=5):
+def align_pair(R, qa, ta, qb, tb, clips=(0, 0, 0, 0), scoring=(10, 2, 2, -3), extra_blocks=0, min_length=5,
+               tagged=1):
     a, b = AlnOut(), AlnOut()
     ca, cta, cb, ctb = codes(qa), codes(ta), codes(qb), codes(tb)
     cl = np.array(clips, dtype=np.uint32)
     rc = lib().fadeemu_align_pair(R, ca.ctypes.data, len(ca), cta.ctypes.data, len(cta), cb.ctypes.data, len(cb),
-                                  ctb.ctypes.data, len(ctb), *scoring, extra_blocks, min_length, cl.ctypes.data,
+                                  ctb.ctypes.data, len(ctb), *scoring, extra_blocks, tagged, min_length, cl.ctypes.data,
                                   C.byref(a), C.byref(b))
     if rc:
         raise RuntimeError(f"fadeemu_align_pair rc={rc}")

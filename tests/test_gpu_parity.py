@@ -33,3 +33,157 @@ def test_empty_and_no_clip_batches(gpu_ctx):
     b.fill(rd.seq4, rd.seq_off, rd.l_qseq, rd.tid, rd.pos, rd.aligned_len, rd.clip_left, rd.clip_right).run()
     assert not b.flags[:64].any() and b.stats().n_aligned == 0
     b.close()
+
+
+# ---- edge cases -----------------------------------------------------------------------------------
+import random  # noqa: E402
+
+import readsets  # noqa: E402
+from fade_b200 import api  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+def _ctx(**kw):
+    return Context(0, default_params(**kw))
+
+
+def test_ragged_lengths_contig_ends_and_short_clips():
+    """query lengths 20..250 (all three packed instantiations), windows clamped at contig starts
+    and ends, clips at / below the length floor, several contigs."""
+    rng = random.Random(11)
+    contigs = [readsets.random_ref(rng, n) for n in (5000, 1200, 700, 260)]
+    reads = readsets.ragged_reads(rng, contigs, 3000)
+    rd = readsets.build(reads)
+    with _ctx() as ctx:
+        ctx.load_reference([f"c{i}" for i in range(4)], contigs)
+        b = run_gpu(ctx, rd)
+        n_al = compare(b, rd, contigs, oracle_params(ctx.params))
+        assert n_al > 500 and b.stats().n_generic == 0
+        b.close()
+
+
+def test_wildcard_letters_go_through_generic_kernel():
+    """IUPAC letters in reads and reference, lower case, N runs: P1 wildcard row/column (score 0,
+    '=' by byte equality) -- served by the generic kernel on the device."""
+    rng = random.Random(12)
+    base = bytearray(readsets.random_ref(rng, 6000))
+    for _ in range(40):
+        p = rng.randrange(len(base))
+        base[p] = ord(rng.choice("RYKMSWBDHVryn"))
+    base[3000:3100] = b"N" * 100
+    base[1000:1400] = bytes(base[1000:1400]).lower()
+    contigs = [bytes(base)]
+    reads = readsets.ragged_reads(rng, contigs, 1500, wild_read_rate=0.002, alpha="ACGTN")
+    rd = readsets.build(reads)
+    with _ctx() as ctx:
+        ctx.load_reference(["w"], contigs)
+        b = run_gpu(ctx, rd)
+        n_al = compare(b, rd, contigs, oracle_params(ctx.params))
+        st = b.stats()
+        assert n_al > 300
+        assert (b.flags[: rd.n] & api.R_GENERIC).any(), "some alignments must have met a wildcard letter"
+        b.close()
+
+
+def test_force_generic_equals_packed():
+    names, contigs, cfg, n = sim.config_c1()
+    rd = sim.make_reads(cfg, 0, 1500, contigs)
+    with _ctx(flags=api.F_FORCE_GENERIC) as ctx:
+        ctx.load_reference(names, [c.tobytes() for c in contigs])
+        b = run_gpu(ctx, rd)
+        n_al = compare(b, rd, contigs, oracle_params(ctx.params))
+        assert b.stats().n_generic == n_al > 100
+        b.close()
+
+
+def test_stress_config_long_windows_short_clips():
+    """BASELINE.json configs[3]: --window-size 1000, --min-length 5, 2x250 reads, clip law U{1..40}."""
+    ref = sim.make_contig(1002, 0, 400_000, 50_000, 300, 0.02)
+    cfg = sim.default_cfg(read_seed=2004, read_len=250, window=1000, frag_mean=600, frag_sd=80, short_clip_law=1)
+    rd = sim.make_reads(cfg, 0, 3000, [ref])
+    with _ctx(window_size=1000, min_length=5) as ctx:
+        ctx.load_reference(["chrS"], [ref.tobytes()])
+        b = run_gpu(ctx, rd)
+        n_al = compare(b, rd, [ref], oracle_params(ctx.params))
+        assert n_al > 300
+        b.close()
+
+
+@pytest.mark.parametrize("min_length,window", [(0, 300), (20, 50), (59, 10), (-1, 300)])
+def test_flag_variants(min_length, window):
+    """--min-length / --window-size variants, incl. the negative floor that wraps (uint <= int)."""
+    names, contigs, cfg, n = sim.config_c1()
+    rd = sim.make_reads(cfg, 0, 2500, contigs)
+    with _ctx(min_length=min_length, window_size=window) as ctx:
+        ctx.load_reference(names, [c.tobytes() for c in contigs])
+        b = run_gpu(ctx, rd)
+        n_al = compare(b, rd, contigs, oracle_params(ctx.params))
+        if min_length < 0:
+            assert n_al == 0
+        b.close()
+
+
+def test_other_scoring_plain_trace_path():
+    """scoring that does not fit the tagged trace encoding exercises the plain recorder."""
+    names, contigs, cfg, n = sim.config_c1()
+    rd = sim.make_reads(cfg, 0, 2000, contigs)
+    with _ctx(gap_open=12, gap_extend=3, match=9, mismatch=-9) as ctx:
+        ctx.load_reference(names, [c.tobytes() for c in contigs])
+        b = run_gpu(ctx, rd)
+        compare(b, rd, contigs, oracle_params(ctx.params))
+        b.close()
+
+
+def test_small_scratch_forces_many_launches():
+    """a tiny checkpoint scratch splits the batch into many fill/trace launch pairs."""
+    names, contigs, cfg, n = sim.config_c1()
+    rd = sim.make_reads(cfg, 0, 4000, contigs)
+    with _ctx(scratch_bytes=4 << 20) as ctx:
+        ctx.load_reference(names, [c.tobytes() for c in contigs])
+        b = run_gpu(ctx, rd)
+        compare(b, rd, contigs, oracle_params(ctx.params))
+        assert b.stats().kernel_launches > 6
+        b.close()
+
+
+def test_batch_reuse_and_double_buffering(gpu_ctx):
+    names, contigs, cfg, n = sim.config_c1()
+    gpu_ctx.load_reference(names, [c.tobytes() for c in contigs])
+    bs = [gpu_ctx.alloc_batch(3000, 3000 * 75) for _ in range(2)]
+    rds = [sim.make_reads(cfg, k * 3000, 3000 - 7 * k, contigs) for k in range(4)]
+    for k, rd in enumerate(rds):            # submit k while k-1 is in flight
+        b = bs[k & 1]
+        b.fill(rd.seq4, rd.seq_off, rd.l_qseq, rd.tid, rd.pos, rd.aligned_len, rd.clip_left, rd.clip_right)
+        b.submit()
+        if k:
+            bs[(k - 1) & 1].wait()
+            compare(bs[(k - 1) & 1], rds[k - 1], contigs, oracle_params(gpu_ctx.params))
+    bs[1].wait()
+    compare(bs[1], rds[3], contigs, oracle_params(gpu_ctx.params))
+    with pytest.raises(Exception):
+        bs[0].wait()                         # not in flight -> FADEGPU_E_STATE, loudly
+    for b in bs:
+        b.close()
+
+
+def test_record_level_tags_match_oracle(gpu_ctx):
+    """rs / am / as / ar / ab of every record (anno.d:94-107) equal the oracle's."""
+    from fade_b200 import Record, annotate_records
+    names, contigs, cfg, n = sim.config_c1()
+    gpu_ctx.load_reference(names, [c.tobytes() for c in contigs])
+    rd = sim.make_reads(cfg, 0, 3000, contigs)
+    L = rd.read_len
+    stride = (L + 1) // 2
+    recs = [Record(f"r{k}", int(rd.flag[k]), int(rd.tid[k]), int(rd.pos[k]), rd.cigar[k, : rd.n_cigar[k]].copy(),
+                   rd.seq4[k * stride:(k + 1) * stride].copy(), rd.qual[k * L:(k + 1) * L].copy(), L,
+                   bool(rd.has_sa[k])) for k in range(rd.n)]
+    annotate_records(gpu_ctx, recs)
+    n_art = 0
+    refb = contigs[0].tobytes()
+    for rec in recs:
+        exp = orc.annotate_record(is_mapped=not (rec.flag & 4), has_sa=rec.has_sa, cigar=rec.cigar, seq4=rec.seq4,
+                                  qual=rec.qual, l_qseq=rec.l_qseq, pos=rec.pos, contig_name=names[rec.tid],
+                                  ref_seq=refb)
+        assert rec.tags == exp, (rec.qname, rec.tags, exp)
+        n_art += "am" in exp
+    assert n_art > 100
