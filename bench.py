@@ -9,9 +9,9 @@ min-length), processed as chunks of --chunk reads through the C ABI (libfadegpu.
 
   value  reads/s with the chunk's inputs already resident in HBM: CUDA-event time of ALL kernel
          launches of the chunk (fadegpu_replay_kernels), summed over the chunks of a step.
-  e2e    reads/s through the public C ABI with HOST buffers: per chunk the inputs are written
-         into the pinned batch arrays, fadegpu_submit (host binning + H2D + kernels + D2H) and
-         fadegpu_wait (result scatter) run double-buffered, and the rs flags are read back.
+  e2e    reads/s through the public C ABI with HOST buffers: per chunk fadegpu_submit_inputs reads
+         the caller's host arrays (host binning + gather into pinned staging + H2D + kernels +
+         D2H) and fadegpu_wait scatters the results; double-buffered; the flags are read back.
   roofline  the INT16x2 ALU roofline of SURVEY.md 8(d): cells/s against 2*R_alu/9 with R_alu
          measured live by fadegpu_measure_alu_peak (packed VIADDMNMX.S16x2 issue rate).
   cpu_baseline  the oracle port (oracle/fade_oracle.c, scalar, OpenMP on all host cores) timed
@@ -251,8 +251,9 @@ def main():
         acc = 0
         for i, (a, e) in enumerate(bounds):
             b = batches[i & 1]
-            load_chunk(b, a, e)
-            b.submit()
+            # host buffers (pageable numpy arrays) -> C ABI; seq_off holds absolute offsets into seq4
+            b.submit_arrays(e - a, rd.seq4, rd.seq_off[a:], rd.l_qseq[a:], rd.tid[a:], rd.pos[a:],
+                            rd.aligned_len[a:], rd.clip_left[a:], rd.clip_right[a:])
             if pending is not None:
                 pending.wait()
                 acc += int(pending.flags[: pending.n].sum())     # read the step's result on the host

@@ -48,6 +48,12 @@ class BatchView(C.Structure):
                 ("ops", C.POINTER(C.c_uint32))]
 
 
+class Inputs(C.Structure):
+    _fields_ = [("seq4", C.c_void_p), ("seq_off", C.c_void_p), ("l_qseq", C.c_void_p), ("tid", C.c_void_p),
+                ("pos", C.c_void_p), ("aligned_len", C.c_void_p), ("clip_left", C.c_void_p),
+                ("clip_right", C.c_void_p)]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_aligned", C.c_int64), ("n_generic", C.c_int64), ("cells", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int32),
@@ -66,7 +72,7 @@ ABI_SYMBOLS = [
     "fadegpu_abi_version", "fadegpu_device_count", "fadegpu_default_params", "fadegpu_create",
     "fadegpu_destroy", "fadegpu_last_error", "fadegpu_load_reference", "fadegpu_share_reference",
     "fadegpu_reference_info", "fadegpu_alloc_batch", "fadegpu_get_batch_view", "fadegpu_free_batch",
-    "fadegpu_submit", "fadegpu_wait", "fadegpu_get_stats", "fadegpu_replay_kernels",
+    "fadegpu_submit", "fadegpu_submit_inputs", "fadegpu_wait", "fadegpu_get_stats", "fadegpu_replay_kernels",
     "fadegpu_measure_alu_peak",
     "fadehost_parse_clips", "fadehost_aligned_length", "fadehost_prepare", "fadehost_finish",
 ]
@@ -98,6 +104,7 @@ def lib():
     L.fadegpu_free_batch.argtypes = [vp]
     L.fadegpu_free_batch.restype = None
     L.fadegpu_submit.argtypes = [vp, vp, i64]
+    L.fadegpu_submit_inputs.argtypes = [vp, vp, i64, C.POINTER(Inputs)]
     L.fadegpu_wait.argtypes = [vp, vp]
     L.fadegpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.fadegpu_replay_kernels.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]

@@ -7,7 +7,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from ._lib import BatchView, FadeGpuError, HostRecord, Params, Stats, lib
+from ._lib import BatchView, FadeGpuError, HostRecord, Inputs, Params, Stats, lib
 
 MAX_OPS = 32
 R_ALIGNED, R_ART_LEFT, R_ART_RIGHT, R_OPS_TRUNC, R_GENERIC = 1, 2, 4, 8, 16
@@ -150,6 +150,18 @@ class Batch:
         if n is not None:
             self.n = n
         self.ctx._check(lib().fadegpu_submit(self.ctx._h, self._h, self.n))
+
+    def submit_arrays(self, n, seq4, seq_off, l_qseq, tid, pos, aligned_len, clip_left, clip_right):
+        """fadegpu_submit_inputs: read the inputs straight from caller-owned (pageable) numpy arrays.
+        seq_off may hold absolute offsets into seq4; arrays must be C-contiguous with the ABI dtypes."""
+        def ptr(a, dt):
+            assert a.dtype == dt and a.flags["C_CONTIGUOUS"], (a.dtype, dt)
+            return a.ctypes.data
+        inp = Inputs(ptr(seq4, np.uint8), ptr(seq_off, np.int64), ptr(l_qseq, np.int32), ptr(tid, np.int32),
+                     ptr(pos, np.int64), ptr(aligned_len, np.int32), ptr(clip_left, np.int32),
+                     ptr(clip_right, np.int32))
+        self.n = n
+        self.ctx._check(lib().fadegpu_submit_inputs(self.ctx._h, self._h, n, C.byref(inp)))
 
     def wait(self):
         self.ctx._check(lib().fadegpu_wait(self.ctx._h, self._h))

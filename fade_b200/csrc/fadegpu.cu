@@ -52,6 +52,11 @@ struct fadegpu_ctx {
     std::string err;
 };
 
+struct AlnTmp {       // a read that needs SW, before sorting
+    int64_t start;    // window start inside the contig
+    int32_t read, tlen, cls;
+};
+
 struct Launch {
     int R;            // 13/19/32 = packed kernels, 0 = generic list
     int aln_first, n_aln;
@@ -78,8 +83,10 @@ struct fadegpu_batch {
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };  // start, after H2D, after kernels, after D2H
     bool in_flight = false;
     // scratch for the host binning
-    std::vector<int32_t> tmp_cls, tmp_tlen;
-    std::vector<int64_t> tmp_start;
+    std::vector<std::vector<AlnTmp>> tl_aln;   // per host thread
+    std::vector<AlnTmp> all_aln, sorted_aln;
+    std::vector<int32_t> cnt;
+    std::vector<int64_t> soff, aln_start;
 };
 
 namespace {
@@ -504,115 +511,165 @@ int fadegpu_get_batch_view(fadegpu_batch *b, fadegpu_batch_view *view)
     return FADEGPU_OK;
 }
 
-int fadegpu_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
+namespace {
+
+int cls_rank(int cls) { return cls == 13 ? 0 : cls == 19 ? 1 : cls == 32 ? 2 : 3; }
+
+}  // namespace
+
+int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, const fadegpu_inputs *in)
 {
-    if (!c || !b || b->ctx != c) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: bad ctx/batch");
+    if (!c || !b || b->ctx != c || !in) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: bad ctx/batch/inputs");
     if (!c->d_two) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: no reference loaded");
     if (b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: batch already in flight (call fadegpu_wait)");
     if (n_reads < 0 || n_reads > b->v.max_reads) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: n_reads out of range");
+    if (n_reads > 0 && (!in->seq4 || !in->seq_off || !in->l_qseq || !in->tid || !in->pos || !in->aligned_len ||
+                        !in->clip_left || !in->clip_right))
+        return fail(c, FADEGPU_E_ARG, "fadegpu_submit: null input array");
     CU(c, cudaSetDevice(c->device));
-    const fadegpu_batch_view &v = b->v;
     const int64_t n = n_reads;
-    if (n > 0 && (v.seq_off[n] < 0 || v.seq_off[n] > v.max_seq_bytes))
-        return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off[n] exceeds max_seq_bytes");
     b->n_reads = n;
     b->plan.clear();
     memset(&b->st, 0, sizeof(b->st));
     b->st.n_reads = n;
 
     // ---- 1. which reads need SW, their windows (analysis.d:34,45-59) and size class ----
-    b->tmp_cls.assign((size_t)n, -1);
-    b->tmp_tlen.assign((size_t)n, 0);
-    b->tmp_start.assign((size_t)n, 0);
+    int nthr = 1;
+#ifdef _OPENMP
+    nthr = std::max(1, omp_get_max_threads());
+#endif
+    if ((int)b->tl_aln.size() < nthr) b->tl_aln.resize((size_t)nthr);
     const uint32_t floor_u = (uint32_t)c->p.min_length;  // uint <= int compare of analysis.d:34
     const int64_t W = c->p.window_size;
+    const int64_t seq_total = n > 0 ? in->seq_off[n] : 0;
     int64_t cells = 0;
     int bad = 0;
-#pragma omp parallel for schedule(static) reduction(+ : cells) reduction(| : bad)
-    for (int64_t r = 0; r < n; ++r) {
-        const uint32_t cl = (uint32_t)v.clip_left[r], cr = (uint32_t)v.clip_right[r];
-        const bool need = (cl != 0 && !(cl <= floor_u)) || (cr != 0 && !(cr <= floor_u));
-        if (!need) continue;
-        const int32_t tid = v.tid[r];
-        const int32_t ql = v.l_qseq[r];
-        if (tid < 0 || tid >= c->n_contigs || ql <= 0) continue;
-        const int64_t so = v.seq_off[r];
-        if (so < 0 || so + (ql + 1) / 2 > v.seq_off[n]) { bad = 1; continue; }
-        int64_t start = v.pos[r] - W;
-        if (start < 0) start = 0;
-        int64_t end = v.pos[r] + (int64_t)v.aligned_len[r] + W;
-        if (end > c->clen[tid]) end = c->clen[tid];
-        b->tmp_start[r] = start;
-        if (end <= start || end - start > 0x7fffffff) continue;  // empty window: nothing to align
-        const int tlen = (int)(end - start);
-        b->tmp_tlen[r] = tlen;
-        b->tmp_cls[r] = class_of(c, ql, tlen);
-        cells += (int64_t)ql * tlen;
+#pragma omp parallel num_threads(nthr) reduction(+ : cells) reduction(| : bad)
+    {
+        int tix = 0, tn = 1;
+#ifdef _OPENMP
+        tix = omp_get_thread_num(); tn = omp_get_num_threads();
+#endif
+        std::vector<AlnTmp> &loc = b->tl_aln[(size_t)tix];
+        loc.clear();
+        const int64_t lo = n * tix / tn, hi = n * (tix + 1) / tn;
+        for (int64_t r = lo; r < hi; ++r) {
+            const uint32_t cl = (uint32_t)in->clip_left[r], cr = (uint32_t)in->clip_right[r];
+            const bool need = (cl != 0 && !(cl <= floor_u)) || (cr != 0 && !(cr <= floor_u));
+            if (!need) continue;
+            const int32_t tid = in->tid[r];
+            const int32_t ql = in->l_qseq[r];
+            if (tid < 0 || tid >= c->n_contigs || ql <= 0) continue;
+            const int64_t so = in->seq_off[r];
+            if (so < 0 || so + (ql + 1) / 2 > seq_total) { bad = 1; continue; }
+            int64_t start = in->pos[r] - W;
+            if (start < 0) start = 0;
+            int64_t end = in->pos[r] + (int64_t)in->aligned_len[r] + W;
+            if (end > c->clen[tid]) end = c->clen[tid];
+            if (end <= start || end - start > 0x7fffffff) continue;  // empty window: nothing to align
+            const int tlen = (int)(end - start);
+            loc.push_back(AlnTmp{ start, (int32_t)r, tlen, class_of(c, ql, tlen) });
+            cells += (int64_t)ql * tlen;
+        }
     }
     if (bad) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
     b->st.cells = cells;
 
     // ---- 2. bin by class, counting sort by window length (longest first) ----
-    static const int CLS[4] = { 13, 19, 32, 0 };
-    int64_t n_aln = 0, n_items = 0, seq_bytes = 0;
-    std::vector<int64_t> order;
-    std::vector<int32_t> cnt;
-    size_t ck_needed = 0, gen_needed = 0;
+    int64_t n_aln = 0;
+    for (int t = 0; t < nthr; ++t) n_aln += (int64_t)b->tl_aln[(size_t)t].size();
+    std::vector<AlnTmp> &all = b->all_aln, &sorted = b->sorted_aln;
+    all.resize((size_t)n_aln);
+    sorted.resize((size_t)n_aln);
+    {
+        int64_t o = 0;
+        for (int t = 0; t < nthr; ++t) {
+            const auto &loc = b->tl_aln[(size_t)t];
+            if (!loc.empty()) memcpy(all.data() + o, loc.data(), loc.size() * sizeof(AlnTmp));
+            o += (int64_t)loc.size();
+        }
+    }
+    // key = class rank (13, 19, 32, generic) then descending window length (generic: input order)
+    const int KEYS = 4 * (TMAX_FAST + 2);
+    std::vector<int32_t> &cnt = b->cnt;
+    cnt.assign((size_t)KEYS + 1, 0);
+    auto key_of = [](const AlnTmp &a) {
+        const int rk = cls_rank(a.cls);
+        return rk * (TMAX_FAST + 2) + (rk == 3 ? 0 : TMAX_FAST - a.tlen);
+    };
+    for (const AlnTmp &a : all) ++cnt[(size_t)key_of(a) + 1];
+    for (int kx = 0; kx < KEYS; ++kx) cnt[(size_t)kx + 1] += cnt[(size_t)kx];
+    int64_t cls_first[5];
+    for (int rk = 0; rk < 4; ++rk) cls_first[rk] = cnt[(size_t)rk * (TMAX_FAST + 2)];
+    cls_first[4] = n_aln;
+    for (const AlnTmp &a : all) sorted[(size_t)cnt[(size_t)key_of(a)]++] = a;
+
+    // ---- 3. descriptors + gathered read bases ----
+    std::vector<int64_t> &soff = b->soff;
+    soff.resize((size_t)n_aln + 1);
     int qmax_all = 1, tmax_all = 1;
-    for (int64_t r = 0; r < n; ++r)
-        if (b->tmp_cls[r] >= 0) { qmax_all = std::max(qmax_all, v.l_qseq[r]); tmax_all = std::max(tmax_all, b->tmp_tlen[r]); }
-    for (int ci = 0; ci < 4; ++ci) {
-        const int R = CLS[ci];
-        order.clear();
-        if (R != 0) {
-            cnt.assign(TMAX_FAST + 2, 0);
-            for (int64_t r = 0; r < n; ++r) if (b->tmp_cls[r] == R) ++cnt[TMAX_FAST - b->tmp_tlen[r]];
-            int64_t tot = 0;
-            for (auto &x : cnt) { const int32_t t = x; x = (int32_t)tot; tot += t; }
-            if (tot == 0) continue;
-            order.resize((size_t)tot);
-            for (int64_t r = 0; r < n; ++r) if (b->tmp_cls[r] == R) order[(size_t)cnt[TMAX_FAST - b->tmp_tlen[r]]++] = r;
-        } else {
-            for (int64_t r = 0; r < n; ++r) if (b->tmp_cls[r] == 0) order.push_back(r);
-            if (order.empty()) continue;
+    {
+        int64_t o = 0;
+        for (int64_t kx = 0; kx < n_aln; ++kx) {
+            soff[(size_t)kx] = o;
+            const int ql = in->l_qseq[sorted[(size_t)kx].read];
+            o += (ql + 1) / 2;
+            qmax_all = std::max(qmax_all, ql);
+            tmax_all = std::max(tmax_all, sorted[(size_t)kx].tlen);
         }
-        const int64_t first_aln = n_aln;
-        int qmax = 1, tmax = 1;
-        for (int64_t r : order) {
-            AlnDesc &d = b->h_aln[n_aln++];
-            const int ql = v.l_qseq[r];
-            d.gstart = c->coff[v.tid[r]] + b->tmp_start[r];
-            d.seq_off = seq_bytes;
-            d.tlen = b->tmp_tlen[r];
-            d.qlen = ql;
-            d.clip_left = (uint32_t)v.clip_left[r];
-            d.clip_right = (uint32_t)v.clip_right[r];
-            d.read = (int32_t)r;
-            d.pad = 0;
-            const int nb = (ql + 1) / 2;
-            memcpy(b->h_seq + seq_bytes, v.seq4 + v.seq_off[r], (size_t)nb);
-            seq_bytes += nb;
-            qmax = std::max(qmax, ql); tmax = std::max(tmax, d.tlen);
-        }
-        const int64_t cnt_aln = n_aln - first_aln;
+        soff[(size_t)n_aln] = o;
+    }
+    const int64_t seq_bytes = soff[(size_t)n_aln];
+    if (seq_bytes > b->cap_seq) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: read bases exceed max_seq_bytes");
+    b->aln_start.resize((size_t)n_aln);
+#pragma omp parallel for schedule(static) num_threads(nthr)
+    for (int64_t kx = 0; kx < n_aln; ++kx) {
+        const AlnTmp &a = sorted[(size_t)kx];
+        const int64_t r = a.read;
+        AlnDesc &d = b->h_aln[kx];
+        const int ql = in->l_qseq[r];
+        d.gstart = c->coff[in->tid[r]] + a.start;
+        d.seq_off = soff[(size_t)kx];
+        d.tlen = a.tlen;
+        d.qlen = ql;
+        d.clip_left = (uint32_t)in->clip_left[r];
+        d.clip_right = (uint32_t)in->clip_right[r];
+        d.read = (int32_t)r;
+        d.pad = 0;
+        b->aln_start[(size_t)kx] = a.start;
+        memcpy(b->h_seq + d.seq_off, in->seq4 + in->seq_off[r], (size_t)((ql + 1) / 2));
+    }
+
+    // ---- 4. launch plan ----
+    static const int CLS[4] = { 13, 19, 32, 0 };
+    int64_t n_items = 0;
+    size_t ck_needed = 0, gen_needed = 0;
+    for (int rk = 0; rk < 4; ++rk) {
+        const int R = CLS[rk];
+        const int64_t first_aln = cls_first[rk], last_aln = cls_first[rk + 1];
+        if (last_aln <= first_aln) continue;
         if (R == 0) {
+            int qmax = 1, tmax = 1;
+            for (int64_t kx = first_aln; kx < last_aln; ++kx) {
+                qmax = std::max(qmax, b->h_aln[kx].qlen); tmax = std::max(tmax, b->h_aln[kx].tlen);
+            }
             Launch L{};
-            L.R = 0; L.aln_first = (int)first_aln; L.n_aln = (int)cnt_aln; L.qmax = qmax; L.tmax = tmax;
+            L.R = 0; L.aln_first = (int)first_aln; L.n_aln = (int)(last_aln - first_aln); L.qmax = qmax; L.tmax = tmax;
             b->plan.push_back(L);
             gen_needed = std::max(gen_needed, gen_slot_bytes(qmax, tmax));
-            b->st.n_generic += cnt_aln;
+            b->st.n_generic += last_aln - first_aln;
             continue;
         }
         // warp items of 8 alignments; split into launches that fit the checkpoint scratch
         const size_t cw = ck_words_of(R);
         int64_t a0 = first_aln;
-        while (a0 < n_aln) {
+        while (a0 < last_aln) {
             Launch L{};
             L.R = R; L.aln_first = (int)a0; L.item_first = (int)n_items; L.qmax = qmax_all; L.tmax = tmax_all;
             size_t words = 0;
             int nblk_max = 1;
             int64_t a1 = a0;
-            while (a1 < n_aln) {
+            while (a1 < last_aln) {
                 const int nblk = num_blocks(b->h_aln[a1].tlen);  // longest of the 8 (sorted descending)
                 const size_t wds = (size_t)(nblk - 1) * cw * 32;
                 if (a1 > a0 && (words + wds) * 4 > (size_t)c->p.scratch_bytes) break;
@@ -622,7 +679,7 @@ int fadegpu_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
                 it.nblk = nblk;
                 words += wds;
                 nblk_max = std::max(nblk_max, nblk);
-                a1 = std::min<int64_t>(a1 + 8, n_aln);
+                a1 = std::min<int64_t>(a1 + 8, last_aln);
             }
             L.n_aln = (int)(a1 - a0);
             L.n_items = (int)(n_items - L.item_first);
@@ -645,7 +702,7 @@ int fadegpu_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
         if (rc) return rc;
     }
 
-    // ---- 3. queue copies and kernels ----
+    // ---- 5. queue copies and kernels ----
     CU(c, cudaEventRecord(b->ev[0], c->stream));
     if (n_aln > 0) {
         CU(c, cudaMemcpyAsync(b->d_aln, b->h_aln, (size_t)n_aln * sizeof(AlnDesc), cudaMemcpyHostToDevice, c->stream));
@@ -667,6 +724,18 @@ int fadegpu_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
     return FADEGPU_OK;
 }
 
+int fadegpu_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
+{
+    if (!b) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: null batch");
+    const fadegpu_batch_view &v = b->v;
+    if (n_reads > 0 && n_reads <= v.max_reads && (v.seq_off[n_reads] < 0 || v.seq_off[n_reads] > v.max_seq_bytes))
+        return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off[n] exceeds max_seq_bytes");
+    fadegpu_inputs in;
+    in.seq4 = v.seq4; in.seq_off = v.seq_off; in.l_qseq = v.l_qseq; in.tid = v.tid; in.pos = v.pos;
+    in.aligned_len = v.aligned_len; in.clip_left = v.clip_left; in.clip_right = v.clip_right;
+    return fadegpu_submit_inputs(c, b, n_reads, &in);
+}
+
 int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
 {
     if (!c || !b || b->ctx != c) return fail(c, FADEGPU_E_ARG, "fadegpu_wait: bad ctx/batch");
@@ -679,10 +748,7 @@ int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
     if (cudaEventElapsedTime(&t, b->ev[0], b->ev[3]) == cudaSuccess) b->st.total_ms = t;
     fadegpu_batch_view &v = b->v;
     const int64_t n = b->n_reads;
-    memset(v.flags, 0, (size_t)n);
-    memset(v.score, 0, (size_t)n * 4); memset(v.beg_query, 0, (size_t)n * 4); memset(v.end_query, 0, (size_t)n * 4);
-    memset(v.beg_ref, 0, (size_t)n * 4); memset(v.end_ref, 0, (size_t)n * 4); memset(v.n_ops, 0, (size_t)n * 4);
-    memset(v.win_start, 0, (size_t)n * 8);
+    memset(v.flags, 0, (size_t)n);   // the other outputs are defined only where FADEGPU_R_ALIGNED is set
     int bad = 0;
 #pragma omp parallel for schedule(static) reduction(| : bad)
     for (int64_t k = 0; k < b->n_aln; ++k) {
@@ -692,7 +758,7 @@ int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
         v.flags[r] = (uint8_t)(o.flags & 0xff);
         v.score[r] = o.score; v.beg_query[r] = o.beg_query; v.end_query[r] = o.end_query;
         v.beg_ref[r] = o.beg_ref; v.end_ref[r] = o.end_ref; v.n_ops[r] = o.n_ops;
-        v.win_start[r] = b->tmp_start[r];
+        v.win_start[r] = b->aln_start[(size_t)k];
         memcpy(v.ops + (size_t)r * FADEGPU_MAX_OPS, o.ops, sizeof(o.ops));
     }
     if (bad) return fail(c, FADEGPU_E_CUDA, "fadegpu_wait: a kernel did not produce a result record (internal error)");

@@ -83,7 +83,8 @@ typedef struct fadegpu_batch_view {
     int32_t *aligned_len; /* [n] rec.cigar.alignedLength (reference span), analysis.d:53 */
     int32_t *clip_left;   /* [n] parse_clips(rec.cigar)[0].length, 0 = none or early-out record */
     int32_t *clip_right;  /* [n] parse_clips(rec.cigar)[1].length */
-    /* ---- outputs ---- */
+    /* ---- outputs: flags is written for every read; all the others are defined only for reads
+     *      whose flags have FADEGPU_R_ALIGNED set ---- */
     uint8_t *flags;       /* [n] FADEGPU_R_* */
     int32_t *score;       /* [n] res.score */
     int32_t *beg_query;   /* [n] */
@@ -132,6 +133,18 @@ void fadegpu_free_batch(fadegpu_batch *b);
 
 /* Asynchronous: host binning, H2D, kernels and D2H are queued on the ctx stream. */
 int fadegpu_submit(fadegpu_ctx *ctx, fadegpu_batch *b, int64_t n_reads);
+
+/* Same, reading the inputs from caller-owned host arrays (pageable is fine: the library gathers
+ * the reads that need SW into its own pinned staging before the H2D copy).  The arrays are only
+ * read during the call.  n_reads <= max_reads of the batch; the results land in the batch's view. */
+typedef struct fadegpu_inputs {
+    const uint8_t *seq4;
+    const int64_t *seq_off;
+    const int32_t *l_qseq, *tid;
+    const int64_t *pos;
+    const int32_t *aligned_len, *clip_left, *clip_right;
+} fadegpu_inputs;
+int fadegpu_submit_inputs(fadegpu_ctx *ctx, fadegpu_batch *b, int64_t n_reads, const fadegpu_inputs *in);
 /* Blocks until the batch is done and scatters the results into the view's output arrays. */
 int fadegpu_wait(fadegpu_ctx *ctx, fadegpu_batch *b);
 

@@ -187,3 +187,18 @@ def test_record_level_tags_match_oracle(gpu_ctx):
         assert rec.tags == exp, (rec.qname, rec.tags, exp)
         n_art += "am" in exp
     assert n_art > 100
+
+
+def test_submit_inputs_from_caller_arrays(gpu_ctx):
+    """fadegpu_submit_inputs on pageable caller arrays with absolute seq offsets == fadegpu_submit."""
+    names, contigs, cfg, n = sim.config_c1()
+    gpu_ctx.load_reference(names, [c.tobytes() for c in contigs])
+    rd = sim.make_reads(cfg, 0, 6000, contigs)
+    b = gpu_ctx.alloc_batch(2000, 2000 * 75)
+    for a in (0, 2000, 4000):
+        b.submit_arrays(2000, rd.seq4, rd.seq_off[a:], rd.l_qseq[a:], rd.tid[a:], rd.pos[a:], rd.aligned_len[a:],
+                        rd.clip_left[a:], rd.clip_right[a:])
+        b.wait()
+        sub = sim.make_reads(cfg, a, 2000, contigs)
+        compare(b, sub, contigs, oracle_params(gpu_ctx.params))
+    b.close()
