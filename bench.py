@@ -112,7 +112,9 @@ def make_workload(args, rank: int):
     t0 = time.time()
     ref = sim.make_contig(REF_SEED, 0, args.ref_len, 0, 0, 0.0)
     cfg = sim.default_cfg(read_seed=READ_SEED)
-    rd = sim.make_reads(cfg, rank * args.reads, args.reads, [ref], with_records=False)
+    from fade_b200 import shard
+    first, last = shard.weak_range(args.reads, rank)      # every rank owns its slice of the read stream
+    rd = sim.make_reads(cfg, first, last - first, [ref], with_records=False)
     return ref, cfg, rd, time.time() - t0
 
 
@@ -167,9 +169,8 @@ def workload_config(args) -> dict:
 
 def main():
     args = parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from fade_b200 import shard as _shard
+    rank, local_rank, world = _shard.world()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -188,19 +189,9 @@ def main():
         if world > 1:
             dist.barrier()
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    from fade_b200 import shard
+    red = shard.Reducer(world, device=f"cuda:{local_rank}")
+    max_over_ranks, sum_over_ranks = red.max, red.sum
 
     ref, cfg, rd, gen_s = make_workload(args, rank)
     ctx = Context(local_rank)
