@@ -96,7 +96,7 @@ int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
     ctl_init(ctl[0], qlen_a, tlen_a);
     ctl_init(ctl[1], qlen_b, tlen_b);
     constexpr int RW = trace_words<R>();
-    std::vector<uint32_t> tr((size_t)FBLK * FG * RW);
+    std::vector<uint32_t> tr((size_t)tile_words<R>());
     const bool tg = tagged && k.tagged_ok;
     int guard = 0;
     while (ctl[0].phase != 2 || ctl[1].phase != 2) {
@@ -105,7 +105,7 @@ int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
         for (int L = 0; L < 2; ++L) blk[L] = (ctl[L].phase != 2 && ctl[L].next_blk >= 0) ? ctl[L].next_blk : 0;
         bool scan[2][FG];
         for (int L = 0; L < 2; ++L)
-            for (int g = 0; g < FG; ++g) scan[L][g] = ctl_scan_me(ctl[L], g);
+            for (int g = 0; g < FG; ++g) scan[L][g] = (ctl_scanmask(ctl[L]) >> g) & 1u;
         // load per-lane state
         for (int g = 0; g < FG; ++g) {
             ThreadState<R> s0, s1;
@@ -139,10 +139,11 @@ int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
             for (int g = 0; g < FG; ++g) {
                 const uint32_t ts = (tw[t0 - g + FG] & 0x00ffu) | (tw[t1 - g + FG] & 0xff00u);
                 uint32_t cmax = 0;
-                uint32_t *trw = &tr[(size_t)(u * FG + g) * RW];
+                uint32_t trw[RW];
                 if (tg) trace_step_tagged<R>(st[g].H, st[g].E, st[g].qs, ts, st[g].hu_prev, fin[g], st[g].fout, k, trw, cmax);
                 else trace_step_plain<R>(st[g].H, st[g].E, st[g].qs, ts, st[g].hu_prev, fin[g], st[g].fout, k, trw, cmax);
                 st[g].hu_prev = hu[g];
+                for (int w = 0; w < RW; ++w) tr[(size_t)tile_index<R>(u, g, w)] = trw[w];
                 for (int L = 0; L < 2; ++L) {
                     if (!scan[L][g] || found[L][g]) continue;
                     const int cm = L == 0 ? lane_lo(cmax) : lane_hi(cmax);
@@ -162,8 +163,8 @@ int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
         for (int L = 0; L < 2; ++L)
             for (int g = 0; g < FG; ++g)
                 if (scan[L][g] && !found[L][g]) return -3;  // a candidate must find its cell
-        ctl_advance<R>(ctl[0], tr.data(), 0, tw.data(), qc.data(), k);
-        ctl_advance<R>(ctl[1], tr.data(), 1, tw.data(), qc.data(), k);
+        ctl_advance<R>(ctl[0], tr.data(), 0, StagedAcc{ tw.data(), qc.data(), 0 }, k);
+        ctl_advance<R>(ctl[1], tr.data(), 1, StagedAcc{ tw.data(), qc.data(), 1 }, k);
     }
     finalize_result(ctl[0], *out_a, 0, clipl_a, clipr_a, min_length);
     finalize_result(ctl[1], *out_b, 1, clipl_b, clipr_b, min_length);

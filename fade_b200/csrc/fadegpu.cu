@@ -49,6 +49,11 @@ struct fadegpu_ctx {
     size_t gen_bytes = 0;
     unsigned int *d_cursor = nullptr;
     uint32_t *d_alu = nullptr;
+    // traceback rounds: per-alignment state, request queues, trace tiles (sized per launch)
+    uint8_t *d_trace = nullptr;
+    size_t trace_bytes = 0;
+    unsigned int *d_qcount = nullptr;
+    int sm_count = 148;
     std::string err;
 };
 
@@ -62,6 +67,7 @@ struct Launch {
     int aln_first, n_aln;
     int item_first, n_items;
     int tw_stride;
+    int nblk_max;
     int qmax, tmax;   // generic only
 };
 
@@ -151,6 +157,25 @@ int ensure_ck(fadegpu_ctx *c, size_t bytes)
     return 0;
 }
 
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// device bytes of the traceback-round scratch for a launch of n alignments of row class R
+size_t trace_scratch_bytes(int R, int64_t n)
+{
+    return align256((size_t)n * sizeof(LaneCtl)) + 2 * align256((size_t)n * 8) +
+           align256((size_t)((n + 1) / 2) * trace_tile_bytes(R));
+}
+
+int ensure_trace(fadegpu_ctx *c, size_t bytes)
+{
+    if (bytes <= c->trace_bytes) return 0;
+    free_dev(c->d_trace);
+    c->trace_bytes = 0;
+    CU(c, cudaMalloc(&c->d_trace, bytes));
+    c->trace_bytes = bytes;
+    return 0;
+}
+
 int ensure_gen(fadegpu_ctx *c, size_t bytes)
 {
     if (bytes <= c->gen_bytes) return 0;
@@ -197,11 +222,22 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
             a.k = c->k;
             a.min_length = c->p.min_length;
             a.tw_stride = L.tw_stride;
+            {
+                uint8_t *p = c->d_trace;
+                a.state = reinterpret_cast<LaneCtl *>(p); p += align256((size_t)L.n_aln * sizeof(LaneCtl));
+                a.queue[0] = reinterpret_cast<unsigned long long *>(p); p += align256((size_t)L.n_aln * 8);
+                a.queue[1] = reinterpret_cast<unsigned long long *>(p); p += align256((size_t)L.n_aln * 8);
+                a.tiles = reinterpret_cast<uint32_t *>(p);
+                a.qcount = c->d_qcount;
+                a.round = 0;
+                a.max_rounds = L.nblk_max + FG;   // each round scans one candidate block or walks one block
+            }
             if (timed) CU(c, cudaEventRecord(e0, c->stream));
             CU(c, launch_fill(L.R, a, c->stream));
             if (timed) CU(c, cudaEventRecord(e1, c->stream));
-            CU(c, launch_trace(L.R, a, c->stream));
-            nl += 2;
+            CU(c, cudaMemsetAsync(c->d_qcount, 0, 2 * sizeof(unsigned int), c->stream));
+            nl += 1;   // the fill kernel; launch_trace adds its own launches
+            CU(c, launch_trace(L.R, a, c->stream, c->sm_count, &nl));
             // wildcard letters found by the packed kernels -> generic kernel over the flagged ones
             GenericArgs ga;
             ga.aln = a.aln; ga.n_aln = L.n_aln; ga.aln_flags = a.aln_flags; ga.seq = b->d_seq; ga.ref = a.ref;
@@ -310,7 +346,9 @@ int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
     if (c->p.scratch_bytes <= 0) c->p.scratch_bytes = (int64_t)8 << 30;
     c->k = make_consts(pp.gap_open, pp.gap_extend, pp.match, pp.mismatch);
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc(&c->d_cursor, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&c->d_alu, 64)) != cudaSuccess) {
+        (e = cudaMalloc(&c->d_cursor, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&c->d_alu, 64)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "fadegpu_create");
         delete c;
         return rc;
@@ -325,7 +363,7 @@ void fadegpu_destroy(fadegpu_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_reference(c);
-    free_dev(c->d_ck); free_dev(c->d_gen); free_dev(c->d_cursor); free_dev(c->d_alu);
+    free_dev(c->d_ck); free_dev(c->d_gen); free_dev(c->d_cursor); free_dev(c->d_alu); free_dev(c->d_trace); free_dev(c->d_qcount);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -643,7 +681,7 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     // ---- 4. launch plan ----
     static const int CLS[4] = { 13, 19, 32, 0 };
     int64_t n_items = 0;
-    size_t ck_needed = 0, gen_needed = 0;
+    size_t ck_needed = 0, gen_needed = 0, trace_needed = 0;
     for (int rk = 0; rk < 4; ++rk) {
         const int R = CLS[rk];
         const int64_t first_aln = cls_first[rk], last_aln = cls_first[rk + 1];
@@ -684,7 +722,9 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
             L.n_aln = (int)(a1 - a0);
             L.n_items = (int)(n_items - L.item_first);
             L.tw_stride = tw_stride_for(nblk_max);
+            L.nblk_max = nblk_max;
             ck_needed = std::max(ck_needed, words * 4);
+            trace_needed = std::max(trace_needed, trace_scratch_bytes(R, L.n_aln));
             b->plan.push_back(L);
             a0 = a1;
         }
@@ -696,6 +736,7 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     // a slot for wildcard alignments discovered on the device, sized for the largest problem
     if (n_aln > 0) gen_needed = std::max(gen_needed, gen_slot_bytes(qmax_all, tmax_all));
     if (ck_needed) { int rc = ensure_ck(c, ck_needed); if (rc) return rc; }
+    if (trace_needed) { int rc = ensure_trace(c, trace_needed); if (rc) return rc; }
     if (gen_needed) {
         const size_t want = std::min<size_t>(GEN_BUDGET, gen_needed * 1024);
         int rc = ensure_gen(c, std::max(want, gen_needed));

@@ -2,6 +2,7 @@
 // See kernels.cuh for the inventory and sw_core.cuh for the arithmetic they share with the CPU
 // emulation.  Reference semantics: source/analysis.d:34-80,98-104 + parasail rules P1-P5.
 #include "kernels.cuh"
+#include <algorithm>
 
 namespace fade {
 
@@ -112,131 +113,202 @@ __global__ void __launch_bounds__(FILL_THREADS) sw_fill_kernel(const KernelArgs 
 }
 
 // ------------------------------------------------------------------------------------------------
-// end cell + traceback by block replay
+// end cell + traceback by block replay, organised as rounds over a device-side request queue:
+//   trace_init_kernel     per alignment: collect the per-thread maxima of the score-only pass,
+//                         pick the first block to replay, enqueue (alignment, block, scan mask)
+//   trace_replay_kernel   per PAIR OF REQUESTS (any two alignments): reload the wavefront state of
+//                         the requested block from the checkpoints, re-run its 32 steps with
+//                         (tagged) trace recording, write the trace tile, report scan hits
+//   trace_advance_kernel  per request: end-cell selection / traceback walk through the tile;
+//                         either finishes the alignment (CIGAR, predicates, AlnOut) or enqueues
+//                         the next block it needs
+// Requests are paired by queue position, so every replay does useful work for two alignments and
+// no thread waits for a slower neighbour.
 // ------------------------------------------------------------------------------------------------
-template <int R>
-__host__ __device__ inline size_t trace_group_bytes(int tw_stride)
+__device__ __forceinline__ unsigned long long pack_req(int aln, int blk, uint32_t scanmask)
 {
-    return align16((size_t)tw_stride * 2) + align16((size_t)FBLK * FG * trace_words<R>() * 4) +
-           align16((size_t)FG * R) + align16(2 * sizeof(LaneCtl));
+    return (unsigned long long)(uint32_t)aln | ((unsigned long long)(uint32_t)(blk & 0xffff) << 32) |
+           ((unsigned long long)(scanmask & 0xffu) << 48);
+}
+
+struct GlobalAcc {
+    const uint8_t *seq;
+    int qlen;
+    RefPlanes planes;
+    int64_t gstart;
+    __device__ __forceinline__ int qcode(int i) const { return rc_query_code(seq, qlen, i); }
+    __device__ __forceinline__ int tcode(int j) const { return ref_code(planes, gstart + j); }
+};
+
+template <int R>
+__global__ void __launch_bounds__(128) trace_init_kernel(const KernelArgs a)
+{
+    for (int aln = blockIdx.x * blockDim.x + threadIdx.x; aln < a.n_aln; aln += gridDim.x * blockDim.x) {
+        a.out[aln].read = -1;              // "no result yet": fadegpu_wait refuses such a record
+        a.out[aln].flags = 0x80000000u;
+        if (a.aln_flags[aln] & 1u) continue;   // wildcard letter: the generic kernel produces it
+        const AlnDesc d = a.aln[aln];
+        LaneCtl &c = a.state[aln];
+        const int w = aln >> 3, q = (aln & 7) >> 1, half = aln & 1;
+        const uint2 *fr = a.fillres + (size_t)w * 32 + q * FG;
+        for (int g = 0; g < FG; ++g) {
+            const uint2 v = fr[g];
+            c.best[g] = half ? lane_hi(v.x) : lane_lo(v.x);
+            c.blk[g] = half ? (int)(v.y >> 16) : (int)(v.y & 0xffffu);
+        }
+        ctl_init(c, d.qlen, d.tlen);
+        if (c.phase == 2) {
+            AlnOut o;
+            finalize_result(c, o, d.read, d.clip_left, d.clip_right, a.min_length);
+            a.out[aln] = o;
+        } else {
+            const unsigned slot = atomicAdd(&a.qcount[0], 1u);
+            a.queue[0][slot] = pack_req(aln, c.next_blk, ctl_scanmask(c));
+        }
+    }
 }
 
 template <int R, bool TAGGED>
-__global__ void __launch_bounds__(TRACE_THREADS) sw_trace_kernel(const KernelArgs a)
+__global__ void __launch_bounds__(128) trace_replay_kernel(const KernelArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int rows = FG * R;
+    __shared__ uint16_t tws_all[16][40];
     constexpr int RW = trace_words<R>();
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = lane & (FG - 1), q = lane >> 3;
-    const int w = blockIdx.x * (TRACE_THREADS / 32) + wib;
-    if (w >= a.n_items) return;
-    const WarpItem item = a.items[w];
-    const int ia = item.first + 2 * q, ib = ia + 1;
-    const AlnDesc da = load_desc(a, ia), db = load_desc(a, ib);
-    const int nblk = item.nblk;
-    const SwConsts k = a.k;
-
-    unsigned char *base = smem_raw + (size_t)(wib * 4 + q) * trace_group_bytes<R>(a.tw_stride);
-    uint16_t *tw = reinterpret_cast<uint16_t *>(base);
-    uint32_t *tr = reinterpret_cast<uint32_t *>(base + align16((size_t)a.tw_stride * 2));
-    uint8_t *qc = reinterpret_cast<uint8_t *>(tr) + align16((size_t)FBLK * FG * RW * 4);
-    LaneCtl *ctl = reinterpret_cast<LaneCtl *>(qc + align16(rows));
-    LaneCtl &c0 = ctl[0];
-    LaneCtl &c1 = ctl[1];
-
-    uint32_t H[R], E[R], qs[R];
-    uint32_t wild;
-    stage_pair<R>(a, da, db, g, nblk, tw, qs, qc, wild);
-    {
-        const uint2 fr = a.fillres[(size_t)w * 32 + lane];
-        c0.best[g] = lane_lo(fr.x); c0.blk[g] = (int)(fr.y & 0xffffu);
-        c1.best[g] = lane_hi(fr.x); c1.blk[g] = (int)(fr.y >> 16);
-    }
-    __syncwarp();
-    if (g == 0) ctl_init(c0, da.qlen, da.tlen);
-    else if (g == 1) ctl_init(c1, db.qlen, db.tlen);
-
     constexpr int CW = ck_words<R>();
     constexpr int MUL = TAGGED ? 16 : 1;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = lane & (FG - 1), q = lane >> 3;
+    const int rin = a.round & 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.qcount[rin ^ 1] = 0u;   // next round's queue starts empty
+    const unsigned cnt = a.qcount[rin];
+    const unsigned long long *queue = a.queue[rin];
+    const unsigned npairs = (cnt + 1u) >> 1;
+    const unsigned nquads = (npairs + 3u) >> 2;
+    const SwConsts k = a.k;
     const uint32_t e_init = TAGGED ? k.neg_o16 : k.neg_o;
-    const uint32_t *ckw = a.ck + item.ck_off + lane;
-    const uint16_t *twp = tw + (FG - g);
-    uint32_t *trg = tr + g * RW;
-    bool overrun = false;
-    for (int iter = 0;; ++iter) {
-        __syncwarp();
-        const int ph0 = c0.phase, ph1 = c1.phase;
-        const bool active = (ph0 != 2) || (ph1 != 2);
-        if (!__any_sync(FULL, active)) break;
-        if (iter > 4 * nblk + 16) { overrun = active; break; }  // cannot happen; never hang the GPU
-        const int b0 = (ph0 != 2 && c0.next_blk >= 0) ? c0.next_blk : 0;
-        const int b1 = (ph1 != 2 && c1.next_blk >= 0) ? c1.next_blk : 0;
-        const bool sc0 = ctl_scan_me(c0, g), sc1 = ctl_scan_me(c1, g);
-        const int S0 = c0.S * MUL, S1 = c1.S * MUL;
-        // lane a state from checkpoint b0-1, lane b state from checkpoint b1-1 (plain domain)
-        uint32_t hu_prev, fout;
+    uint16_t *tws = tws_all[wib * 4 + q];
+    const unsigned warp0 = blockIdx.x * (blockDim.x >> 5) + wib, nwarps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned quad = warp0; quad < nquads; quad += nwarps) {
+        const unsigned pair = quad * 4u + (unsigned)q;
+        // ---- the two requests of this group ----
+        int aln[2], blk[2], half[2], S[2];
+        uint32_t smask[2];
+        AlnDesc d[2];
+        const uint32_t *ckp[2];
+#pragma unroll
+        for (int L = 0; L < 2; ++L) {
+            const unsigned ri = pair * 2u + (unsigned)L;
+            if (ri < cnt) {
+                const unsigned long long rq = queue[ri];
+                aln[L] = (int)(uint32_t)(rq & 0xffffffffu);
+                blk[L] = (int)((rq >> 32) & 0xffffu);
+                smask[L] = (uint32_t)((rq >> 48) & 0xffu);
+                d[L] = a.aln[aln[L]];
+                const WarpItem it = a.items[aln[L] >> 3];
+                ckp[L] = a.ck + it.ck_off + (((aln[L] & 7) >> 1) * FG + g);
+                half[L] = aln[L] & 1;
+                S[L] = a.state[aln[L]].S * MUL;
+            } else {
+                aln[L] = -1; blk[L] = 0; smask[L] = 0; half[L] = 0; S[L] = -1; ckp[L] = a.ck;
+                d[L].gstart = 0; d[L].seq_off = 0; d[L].tlen = 0; d[L].qlen = 0;
+            }
+        }
+        // ---- wavefront state of the requested blocks (checkpoints are in the plain domain) ----
+        uint32_t H[R], E[R], qs[R], hu_prev, fout;
         {
-            const uint32_t *p0 = ckw + (size_t)(b0 > 0 ? b0 - 1 : 0) * CW * 32;
-            const uint32_t *p1 = ckw + (size_t)(b1 > 0 ? b1 - 1 : 0) * CW * 32;
-            const bool z0 = (b0 == 0) || nblk < 2, z1 = (b1 == 0) || nblk < 2;
+            const uint32_t *p0 = ckp[0] + (size_t)(blk[0] > 0 ? blk[0] - 1 : 0) * CW * 32;
+            const uint32_t *p1 = ckp[1] + (size_t)(blk[1] > 0 ? blk[1] - 1 : 0) * CW * 32;
+            const bool z0 = blk[0] == 0, z1 = blk[1] == 0;
+            const int sh0 = half[0] * 16, sh1 = half[1] * 16;
+            auto mix = [&](uint32_t w0, uint32_t w1) {
+                const uint32_t w = ((w0 >> sh0) & 0xffffu) | ((w1 >> sh1) << 16);
+                return TAGGED ? to_tagged(w) : w;
+            };
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const uint32_t h0 = z0 ? 0u : p0[r * 32], h1 = z1 ? 0u : p1[r * 32];
-                const uint32_t e0 = z0 ? k.neg_o : p0[(R + r) * 32], e1 = z1 ? k.neg_o : p1[(R + r) * 32];
-                const uint32_t hw = (h0 & 0xffffu) | (h1 & 0xffff0000u);
-                const uint32_t ew = (e0 & 0xffffu) | (e1 & 0xffff0000u);
-                H[r] = TAGGED ? to_tagged(hw) : hw;
-                E[r] = TAGGED ? to_tagged(ew) : ew;
+                H[r] = mix(z0 ? 0u : p0[r * 32], z1 ? 0u : p1[r * 32]);
+                E[r] = mix(z0 ? k.neg_o : p0[(R + r) * 32], z1 ? k.neg_o : p1[(R + r) * 32]);
             }
-            const uint32_t u0 = z0 ? 0u : p0[(2 * R) * 32], u1 = z1 ? 0u : p1[(2 * R) * 32];
-            const uint32_t f0 = z0 ? k.neg_o : p0[(2 * R + 1) * 32], f1 = z1 ? k.neg_o : p1[(2 * R + 1) * 32];
-            const uint32_t uw = (u0 & 0xffffu) | (u1 & 0xffff0000u);
-            const uint32_t fw = (f0 & 0xffffu) | (f1 & 0xffff0000u);
-            hu_prev = TAGGED ? to_tagged(uw) : uw;
-            fout = TAGGED ? to_tagged(fw) : fw;
+            hu_prev = mix(z0 ? 0u : p0[(2 * R) * 32], z1 ? 0u : p1[(2 * R) * 32]);
+            fout = mix(z0 ? k.neg_o : p0[(2 * R + 1) * 32], z1 ? k.neg_o : p1[(2 * R + 1) * 32]);
         }
-        bool need0 = sc0, need1 = sc1;   // still looking for the first H == S cell
-        int fj0 = 0, fr0 = 0, fj1 = 0, fr1 = 0;
+        // ---- query rows (reverse complement of the BAM nibbles) and the 39 target columns ----
+        {
+            const uint8_t *s0 = a.seq + d[0].seq_off, *s1 = a.seq + d[1].seq_off;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = g * R + r;
+                const int ca = i < d[0].qlen ? rc_query_code(s0, d[0].qlen, i) : C_QPAD;
+                const int cb = i < d[1].qlen ? rc_query_code(s1, d[1].qlen, i) : C_QPAD;
+                qs[r] = q_sel(ca, cb);
+            }
+            __syncwarp();   // previous iteration's readers of tws are done
+            for (int x = g; x < FBLK + FG - 1; x += FG) {
+                const int j0 = blk[0] * FBLK - (FG - 1) + x, j1 = blk[1] * FBLK - (FG - 1) + x;
+                const int ca = (j0 >= 0 && j0 < d[0].tlen) ? ref_code(a.ref.planes, d[0].gstart + j0) : C_TPAD;
+                const int cb = (j1 >= 0 && j1 < d[1].tlen) ? ref_code(a.ref.planes, d[1].gstart + j1) : C_TPAD;
+                tws[x] = (uint16_t)t_sel(ca, cb);
+            }
+            __syncwarp();
+        }
+        // ---- replay ----
+        uint32_t *tile = a.tiles + (size_t)pair * tile_words<R>();
+        const bool store = aln[0] >= 0;      // a pair without requests computes padding only
+        bool need0 = (smask[0] >> g) & 1u, need1 = (smask[1] >> g) & 1u;
+        const uint16_t *twp = tws + (FG - 1 - g);
         for (int u = 0; u < FBLK; ++u) {
-            const int t0 = b0 * FBLK + u, t1 = b1 * FBLK + u;
             uint32_t hu = __shfl_up_sync(FULL, H[R - 1], 1, FG);
             uint32_t fin = __shfl_up_sync(FULL, fout, 1, FG);
             if (g == 0) { hu = 0u; fin = e_init; }
-            const uint32_t ts = ((uint32_t)twp[t0] & 0x00ffu) | ((uint32_t)twp[t1] & 0xff00u);
-            uint32_t cmax = 0u;
-            if (TAGGED) trace_step_tagged<R>(H, E, qs, ts, hu_prev, fin, fout, k, trg + u * (FG * RW), cmax);
-            else trace_step_plain<R>(H, E, qs, ts, hu_prev, fin, fout, k, trg + u * (FG * RW), cmax);
+            const uint32_t ts = twp[u];
+            uint32_t cmax = 0u, trw[RW];
+            if (TAGGED) trace_step_tagged<R>(H, E, qs, ts, hu_prev, fin, fout, k, trw, cmax);
+            else trace_step_plain<R>(H, E, qs, ts, hu_prev, fin, fout, k, trw, cmax);
             hu_prev = hu;
-            if (need0 && lane_lo(cmax) == S0) {
-                need0 = false; fj0 = t0 - g; fr0 = 0;
+            if (store) {
 #pragma unroll
-                for (int r = R - 1; r >= 0; --r) if (lane_lo(H[r]) == S0) fr0 = r;
+                for (int w = 0; w < RW; ++w) tile[tile_index<R>(u, g, w)] = trw[w];
             }
-            if (need1 && lane_hi(cmax) == S1) {
-                need1 = false; fj1 = t1 - g; fr1 = 0;
+            if (need0 && lane_lo(cmax) == S[0]) {
+                need0 = false;
+                int fr = 0;
 #pragma unroll
-                for (int r = R - 1; r >= 0; --r) if (lane_hi(H[r]) == S1) fr1 = r;
+                for (int r = R - 1; r >= 0; --r) if (lane_lo(H[r]) == S[0]) fr = r;
+                a.state[aln[0]].fj[g] = blk[0] * FBLK + u - g;
+                a.state[aln[0]].fr[g] = fr;
+            }
+            if (need1 && lane_hi(cmax) == S[1]) {
+                need1 = false;
+                int fr = 0;
+#pragma unroll
+                for (int r = R - 1; r >= 0; --r) if (lane_hi(H[r]) == S[1]) fr = r;
+                a.state[aln[1]].fj[g] = blk[1] * FBLK + u - g;
+                a.state[aln[1]].fr[g] = fr;
             }
         }
-        if (sc0) { c0.fj[g] = fj0; c0.fr[g] = fr0; }
-        if (sc1) { c1.fj[g] = fj1; c1.fr[g] = fr1; }
-        __syncwarp();
-        if (g == 0) ctl_advance<R>(c0, tr, 0, tw, qc, k);
-        else if (g == 1) ctl_advance<R>(c1, tr, 1, tw, qc, k);
     }
-    __syncwarp();
-    // results (alignments that met a wildcard letter are produced by the generic kernel instead)
-    if (g == 0 && ia < a.n_aln && !(a.aln_flags[ia] & 1u)) {
-        AlnOut o;
-        finalize_result(c0, o, da.read, da.clip_left, da.clip_right, a.min_length);
-        if (overrun) o.flags = 0x80000000u;
-        a.out[ia] = o;
-    } else if (g == 1 && ib < a.n_aln && !(a.aln_flags[ib] & 1u)) {
-        AlnOut o;
-        finalize_result(c1, o, db.read, db.clip_left, db.clip_right, a.min_length);
-        if (overrun) o.flags = 0x80000000u;
-        a.out[ib] = o;
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) trace_advance_kernel(const KernelArgs a)
+{
+    const int rin = a.round & 1;
+    const unsigned cnt = a.qcount[rin];
+    const unsigned long long *queue = a.queue[rin];
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x) {
+        const int aln = (int)(uint32_t)(queue[idx] & 0xffffffffu);
+        const AlnDesc d = a.aln[aln];
+        LaneCtl &c = a.state[aln];
+        GlobalAcc acc;
+        acc.seq = a.seq + d.seq_off; acc.qlen = d.qlen; acc.planes = a.ref.planes; acc.gstart = d.gstart;
+        ctl_advance<R>(c, a.tiles + (size_t)(idx >> 1) * tile_words<R>(), (int)(idx & 1u), acc, a.k);
+        if (c.phase == 2) {
+            AlnOut o;
+            finalize_result(c, o, d.read, d.clip_left, d.clip_right, a.min_length);
+            a.out[aln] = o;
+        } else if (a.round + 1 < a.max_rounds) {
+            const unsigned slot = atomicAdd(&a.qcount[rin ^ 1], 1u);
+            a.queue[rin ^ 1][slot] = pack_req(aln, c.next_blk, ctl_scanmask(c));
+        }   // else: out[aln] keeps its "no result" marker and fadegpu_wait reports the error
     }
 }
 
@@ -422,17 +494,6 @@ int tw_stride_for(int nblk_max) { return (FBLK * nblk_max + FG + 1 + 7) & ~7; }
 
 size_t fill_smem_bytes(int tw_stride) { return (size_t)(FILL_THREADS / FG) * tw_stride * 2; }
 
-size_t trace_smem_bytes(int R, int tw_stride)
-{
-    size_t group = 0;
-    switch (R) {
-    case 13: group = trace_group_bytes<13>(tw_stride); break;
-    case 19: group = trace_group_bytes<19>(tw_stride); break;
-    default: group = trace_group_bytes<32>(tw_stride); break;
-    }
-    return (size_t)(TRACE_THREADS / FG) * group;
-}
-
 template <int R>
 static cudaError_t launch_fill_t(const KernelArgs &a, cudaStream_t s)
 {
@@ -446,21 +507,32 @@ static cudaError_t launch_fill_t(const KernelArgs &a, cudaStream_t s)
 }
 
 template <int R, bool TAGGED>
-static cudaError_t launch_trace_tt(const KernelArgs &a, cudaStream_t s)
+static cudaError_t launch_trace_tt(KernelArgs a, cudaStream_t s, int sm_count, int *launches)
 {
-    const size_t smem = trace_smem_bytes(R, a.tw_stride);
-    cudaError_t e = cudaFuncSetAttribute(sw_trace_kernel<R, TAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int wpb = TRACE_THREADS / 32;
-    const int grid = (a.n_items + wpb - 1) / wpb;
-    sw_trace_kernel<R, TAGGED><<<grid, TRACE_THREADS, smem, s>>>(a);
+    // init: one thread per alignment
+    const int n = a.n_aln;
+    int grid = std::min((n + 127) / 128, sm_count * 8);
+    trace_init_kernel<R><<<grid, 128, 0, s>>>(a);
+    int nl = 1;
+    for (int r = 0; r < a.max_rounds; ++r) {
+        a.round = r;
+        // the queue shrinks quickly: full grids for the first rounds, small grid-stride grids later
+        const int quads = (n + 7) / 8;
+        const int g1 = r < 6 ? std::min((quads + 3) / 4, sm_count * 4) : std::min((quads + 3) / 4, 32);
+        const int g2 = r < 6 ? std::min((n + 127) / 128, sm_count * 8) : std::min((n + 127) / 128, 32);
+        trace_replay_kernel<R, TAGGED><<<std::max(g1, 1), 128, 0, s>>>(a);
+        trace_advance_kernel<R><<<std::max(g2, 1), 128, 0, s>>>(a);
+        nl += 2;
+    }
+    if (launches) *launches += nl;
     return cudaGetLastError();
 }
 
 template <int R>
-static cudaError_t launch_trace_t(const KernelArgs &a, cudaStream_t s)
+static cudaError_t launch_trace_t(const KernelArgs &a, cudaStream_t s, int sm_count, int *launches)
 {
-    return a.k.tagged_ok ? launch_trace_tt<R, true>(a, s) : launch_trace_tt<R, false>(a, s);
+    return a.k.tagged_ok ? launch_trace_tt<R, true>(a, s, sm_count, launches)
+                         : launch_trace_tt<R, false>(a, s, sm_count, launches);
 }
 
 cudaError_t launch_fill(int R, const KernelArgs &a, cudaStream_t s)
@@ -474,14 +546,23 @@ cudaError_t launch_fill(int R, const KernelArgs &a, cudaStream_t s)
     }
 }
 
-cudaError_t launch_trace(int R, const KernelArgs &a, cudaStream_t s)
+cudaError_t launch_trace(int R, const KernelArgs &a, cudaStream_t s, int sm_count, int *launches)
 {
     if (a.n_items <= 0) return cudaSuccess;
     switch (R) {
-    case 13: return launch_trace_t<13>(a, s);
-    case 19: return launch_trace_t<19>(a, s);
-    case 32: return launch_trace_t<32>(a, s);
+    case 13: return launch_trace_t<13>(a, s, sm_count, launches);
+    case 19: return launch_trace_t<19>(a, s, sm_count, launches);
+    case 32: return launch_trace_t<32>(a, s, sm_count, launches);
     default: return cudaErrorInvalidValue;
+    }
+}
+
+size_t trace_tile_bytes(int R)
+{
+    switch (R) {
+    case 13: return (size_t)tile_words<13>() * 4;
+    case 19: return (size_t)tile_words<19>() * 4;
+    default: return (size_t)tile_words<32>() * 4;
     }
 }
 

@@ -56,6 +56,12 @@ struct KernelArgs {
     SwConsts k;
     int32_t min_length;
     int32_t tw_stride;         // uint16 elements per group in shared memory
+    // traceback rounds
+    LaneCtl *state;            // [n_aln] per-alignment traceback state
+    unsigned long long *queue[2];  // request queues (ping-pong): aln | blk << 32 | scanmask << 48
+    unsigned int *qcount;      // [2]
+    uint32_t *tiles;           // [ceil(n_aln/2)] trace tiles of the current round
+    int32_t round, max_rounds;
 };
 
 struct GenericArgs {
@@ -75,16 +81,15 @@ struct GenericArgs {
 };
 
 constexpr int FILL_THREADS = 128;
-constexpr int TRACE_THREADS = 64;
 constexpr int QMAX_FAST = FG * 32;   // rows covered by the largest packed instantiation
 constexpr int TMAX_FAST = 4000;      // window length covered by the packed kernels
 
 size_t fill_smem_bytes(int tw_stride);
-size_t trace_smem_bytes(int R, int tw_stride);
+size_t trace_tile_bytes(int R);
 int tw_stride_for(int nblk_max);
 
 cudaError_t launch_fill(int R, const KernelArgs &a, cudaStream_t s);
-cudaError_t launch_trace(int R, const KernelArgs &a, cudaStream_t s);
+cudaError_t launch_trace(int R, const KernelArgs &a, cudaStream_t s, int sm_count, int *launches);
 cudaError_t launch_generic(const GenericArgs &a, int n_slots, cudaStream_t s);
 cudaError_t launch_alu_peak(uint32_t *out, int iters, int blocks, int threads, cudaStream_t s);
 cudaError_t configure_kernels();

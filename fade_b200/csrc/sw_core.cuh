@@ -360,15 +360,28 @@ FD void walk_push(LaneCtl &c, uint32_t op)
     c.cur = (1u << 4) | op;
 }
 
-// After a replay of block c.next_blk (its trace words are in tr, see trace_step): advance the
-// per-lane state machine.  lane = 0/1 (int16 lane of the pair), tw = staged target words,
-// qc = staged query codes.  P3 (end cell) and P4 (traceback) of SURVEY 8a.
-template <int R>
-FD void ctl_advance(LaneCtl &c, const uint32_t *tr, int lane, const uint16_t *tw, const uint8_t *qc,
-                    const SwConsts &k)
+// Trace tile of one replayed block: word (u, w, g) = step u, row quad w, thread g.  The layout
+// [u][w][g] makes the 8 threads of a group write 8 consecutive words (one 32 B sector) per store.
+template <int R> FD constexpr int tile_words() { return FBLK * trace_words<R>() * FG; }
+template <int R> FD int tile_index(int u, int g, int w) { return (u * trace_words<R>() + w) * FG + g; }
+
+// bit g set: thread g must look for its first H == S cell during the replay of c.next_blk
+FD uint32_t ctl_scanmask(const LaneCtl &c)
+{
+    uint32_t m = 0;
+    if (c.phase != 0) return 0;
+    for (int g = 0; g < FG; ++g)
+        if (c.best[g] == c.S && c.blk[g] == c.next_blk && !((c.scanned >> g) & 1u)) m |= 1u << g;
+    return m;
+}
+
+// After a replay of block c.next_blk (its trace tile is `tile`): advance the per-lane state
+// machine.  lane = 0/1 (int16 half of the tile words); acc.qcode(i) / acc.tcode(j) give the symbol
+// codes of query row i / target column j.  P3 (end cell) and P4 (traceback) of SURVEY 8a.
+template <int R, class Acc>
+FD void ctl_advance(LaneCtl &c, const uint32_t *tile, int lane, const Acc &acc, const SwConsts &k)
 {
     if (c.phase == 2) return;
-    constexpr int RW = trace_words<R>();
     c.cur_blk = c.next_blk;
     if (c.phase == 0) {
         for (int g = 0; g < FG; ++g)
@@ -387,38 +400,52 @@ FD void ctl_advance(LaneCtl &c, const uint32_t *tr, int lane, const uint16_t *tw
         c.hval = c.S;
         c.phase = 1;
     }
-    // P4: walk while the current cell lies in the block held in shared memory
+    // P4: walk while the current cell lies in the replayed block (hot fields in registers)
+    int i = c.i, j = c.j, mode = c.mode, hval = c.hval, gval = c.gval;
+    const int cur_blk = c.cur_blk;
+    bool done = false;
+    int need = -1;
     for (;;) {
-        if (c.i < 0 || c.j < 0) { c.phase = 2; break; }
-        if (c.mode == 0 && c.hval <= 0) { c.phase = 2; break; }   // ZERO
-        const int g = c.i / R, r = c.i - g * R;
-        const int t = c.j + g;
+        if (i < 0 || j < 0) { done = true; break; }
+        if (mode == 0 && hval <= 0) { done = true; break; }   // ZERO
+        const int g = i / R, r = i - g * R;
+        const int t = j + g;
         const int blk = t / FBLK, u = t % FBLK;
-        if (blk != c.cur_blk) { c.next_blk = blk; return; }
-        const uint32_t nib = (tr[(u * FG + g) * RW + (r >> 2)] >> (16 * lane + 4 * (r & 3))) & 0xfu;
-        if (c.mode == 0) {
+        if (blk != cur_blk) { need = blk; break; }
+        const uint32_t nib = (tile[tile_index<R>(u, g, r >> 2)] >> (16 * lane + 4 * (r & 3))) & 0xfu;
+        if (mode == 0) {
             const uint32_t src = nib >> 2;
             if (src == 2u) {
-                const int qcode = (qc[c.i] >> (4 * lane)) & 0x7;
-                const int tcode = (tw[c.j + FG] >> (8 * lane)) & 0x7;
-                const bool eq = qcode == tcode;
+                const bool eq = acc.qcode(i) == acc.tcode(j);
                 walk_push(c, eq ? OP_EQ : OP_X);
-                c.hval -= eq ? k.match : k.mismatch;
-                --c.i; --c.j;
-            } else if (src == 1u) { walk_push(c, OP_I); --c.i; c.mode = 1; c.gval = c.hval; }
-            else { walk_push(c, OP_D); --c.j; c.mode = 2; c.gval = c.hval; }
-        } else if (c.mode == 1) {
-            if (!(nib & 2u)) { c.hval = c.gval + k.open; c.mode = 0; }
-            else { walk_push(c, OP_I); --c.i; c.gval += k.extend; }
+                hval -= eq ? k.match : k.mismatch;
+                --i; --j;
+            } else if (src == 1u) { walk_push(c, OP_I); --i; mode = 1; gval = hval; }
+            else { walk_push(c, OP_D); --j; mode = 2; gval = hval; }
+        } else if (mode == 1) {
+            if (!(nib & 2u)) { hval = gval + k.open; mode = 0; }
+            else { walk_push(c, OP_I); --i; gval += k.extend; }
         } else {
-            if (!(nib & 1u)) { c.hval = c.gval + k.open; c.mode = 0; }
-            else { walk_push(c, OP_D); --c.j; c.gval += k.extend; }
+            if (!(nib & 1u)) { hval = gval + k.open; mode = 0; }
+            else { walk_push(c, OP_D); --j; gval += k.extend; }
         }
     }
+    c.i = i; c.j = j; c.mode = mode; c.hval = hval; c.gval = gval;
+    if (!done) { c.next_blk = need; return; }
     // done: flush the op being accumulated
+    c.phase = 2;
     if (c.cur != 0) { c.ring[c.nrev % OPS_CAP] = c.cur; ++c.nrev; c.cur = 0; }
     c.next_blk = -1;
 }
+
+// accessor over staged arrays (emulation and unit tests)
+struct StagedAcc {
+    const uint16_t *tw;   // target selector words, column j at index j + FG
+    const uint8_t *qc;    // query codes, lane a low nibble, lane b high nibble
+    int lane;
+    FD int qcode(int i) const { return (qc[i] >> (4 * lane)) & 0x7; }
+    FD int tcode(int j) const { return (tw[j + FG] >> (8 * lane)) & 0x7; }
+};
 
 // ---- result record (device -> host, one per alignment) ---------------------------------------
 struct AlnOut {
