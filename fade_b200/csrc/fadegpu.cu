@@ -714,7 +714,9 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
                 WarpItem &it = b->h_items[n_items++];
                 it.ck_off = (int64_t)words;
                 it.first = (int32_t)(a1 - a0);
-                it.nblk = nblk;
+                it.nblk = (int16_t)nblk;
+                it.pad = 0;
+                it.nsteps = b->h_aln[a1].tlen + FG - 1;
                 words += wds;
                 nblk_max = std::max(nblk_max, nblk);
                 a1 = std::min<int64_t>(a1 + 8, last_aln);

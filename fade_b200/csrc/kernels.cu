@@ -83,9 +83,11 @@ __global__ void __launch_bounds__(FILL_THREADS) sw_fill_kernel(const KernelArgs 
     constexpr int CW = ck_words<R>();
     uint32_t *ckw = a.ck + item.ck_off + lane;
     const uint16_t *twp = tw + (FG - g);
+    const int nsteps = item.nsteps;   // tmax + FG - 1: the last block may be partial
     for (int c = 0; c < nblk; ++c) {
+        const int ulim = min(FBLK, nsteps - c * FBLK);
 #pragma unroll 2
-        for (int u = 0; u < FBLK; ++u) {
+        for (int u = 0; u < ulim; ++u) {
             const int t = c * FBLK + u;
             uint32_t hu = __shfl_up_sync(FULL, H[R - 1], 1, FG);
             uint32_t fin = __shfl_up_sync(FULL, fout, 1, FG);
@@ -169,16 +171,15 @@ __global__ void __launch_bounds__(128) trace_init_kernel(const KernelArgs a)
 }
 
 template <int R, bool TAGGED>
-__global__ void __launch_bounds__(128) trace_replay_kernel(const KernelArgs a)
+__device__ __forceinline__ void replay_round(const KernelArgs &a, int round, unsigned warp0, unsigned nwarps,
+                                             uint16_t (*tws_all)[40])
 {
-    __shared__ uint16_t tws_all[16][40];
     constexpr int RW = trace_words<R>();
     constexpr int CW = ck_words<R>();
     constexpr int MUL = TAGGED ? 16 : 1;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = lane & (FG - 1), q = lane >> 3;
-    const int rin = a.round & 1;
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.qcount[rin ^ 1] = 0u;   // next round's queue starts empty
+    const int rin = round & 1;
     const unsigned cnt = a.qcount[rin];
     const unsigned long long *queue = a.queue[rin];
     const unsigned npairs = (cnt + 1u) >> 1;
@@ -186,7 +187,6 @@ __global__ void __launch_bounds__(128) trace_replay_kernel(const KernelArgs a)
     const SwConsts k = a.k;
     const uint32_t e_init = TAGGED ? k.neg_o16 : k.neg_o;
     uint16_t *tws = tws_all[wib * 4 + q];
-    const unsigned warp0 = blockIdx.x * (blockDim.x >> 5) + wib, nwarps = gridDim.x * (blockDim.x >> 5);
     for (unsigned quad = warp0; quad < nquads; quad += nwarps) {
         const unsigned pair = quad * 4u + (unsigned)q;
         // ---- the two requests of this group ----
@@ -288,13 +288,22 @@ __global__ void __launch_bounds__(128) trace_replay_kernel(const KernelArgs a)
     }
 }
 
-template <int R>
-__global__ void __launch_bounds__(128) trace_advance_kernel(const KernelArgs a)
+template <int R, bool TAGGED>
+__global__ void __launch_bounds__(128) trace_replay_kernel(const KernelArgs a)
 {
-    const int rin = a.round & 1;
+    __shared__ uint16_t tws_all[16][40];
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.qcount[(a.round & 1) ^ 1] = 0u;   // next round's queue starts empty
+    replay_round<R, TAGGED>(a, a.round, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5),
+                            gridDim.x * (blockDim.x >> 5), tws_all);
+}
+
+template <int R>
+__device__ __forceinline__ void advance_round(const KernelArgs &a, int round, unsigned tid0, unsigned nthreads)
+{
+    const int rin = round & 1;
     const unsigned cnt = a.qcount[rin];
     const unsigned long long *queue = a.queue[rin];
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < cnt; idx += gridDim.x * blockDim.x) {
+    for (unsigned idx = tid0; idx < cnt; idx += nthreads) {
         const int aln = (int)(uint32_t)(queue[idx] & 0xffffffffu);
         const AlnDesc d = a.aln[aln];
         LaneCtl &c = a.state[aln];
@@ -305,10 +314,36 @@ __global__ void __launch_bounds__(128) trace_advance_kernel(const KernelArgs a)
             AlnOut o;
             finalize_result(c, o, d.read, d.clip_left, d.clip_right, a.min_length);
             a.out[aln] = o;
-        } else if (a.round + 1 < a.max_rounds) {
+        } else if (round + 1 < a.max_rounds) {
             const unsigned slot = atomicAdd(&a.qcount[rin ^ 1], 1u);
             a.queue[rin ^ 1][slot] = pack_req(aln, c.next_blk, ctl_scanmask(c));
         }   // else: out[aln] keeps its "no result" marker and fadegpu_wait reports the error
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) trace_advance_kernel(const KernelArgs a)
+{
+    advance_round<R>(a, a.round, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// The few alignments still unfinished after the full-grid rounds (very long paths): one block
+// runs the remaining rounds back to back, separated by block barriers instead of launches.
+template <int R, bool TAGGED>
+__global__ void __launch_bounds__(128) trace_tail_kernel(const KernelArgs a)
+{
+    __shared__ uint16_t tws_all[16][40];
+    for (int r = a.round; r < a.max_rounds; ++r) {
+        if (a.qcount[r & 1] == 0u) break;          // uniform: every thread reads the same counter
+        __syncthreads();
+        if (threadIdx.x == 0) a.qcount[(r & 1) ^ 1] = 0u;
+        __syncthreads();
+        replay_round<R, TAGGED>(a, r, threadIdx.x >> 5, blockDim.x >> 5, tws_all);
+        __threadfence_block();
+        __syncthreads();
+        advance_round<R>(a, r, threadIdx.x, blockDim.x);
+        __threadfence_block();
+        __syncthreads();
     }
 }
 
@@ -514,15 +549,22 @@ static cudaError_t launch_trace_tt(KernelArgs a, cudaStream_t s, int sm_count, i
     int grid = std::min((n + 127) / 128, sm_count * 8);
     trace_init_kernel<R><<<grid, 128, 0, s>>>(a);
     int nl = 1;
-    for (int r = 0; r < a.max_rounds; ++r) {
+    constexpr int FULL_ROUNDS = 7;   // covers paths up to ~6 blocks; the rest goes to the tail kernel
+    const int quads = (n + 7) / 8;
+    int r = 0;
+    for (; r < a.max_rounds && r < FULL_ROUNDS; ++r) {
         a.round = r;
-        // the queue shrinks quickly: full grids for the first rounds, small grid-stride grids later
-        const int quads = (n + 7) / 8;
-        const int g1 = r < 6 ? std::min((quads + 3) / 4, sm_count * 4) : std::min((quads + 3) / 4, 32);
-        const int g2 = r < 6 ? std::min((n + 127) / 128, sm_count * 8) : std::min((n + 127) / 128, 32);
+        // the queue shrinks quickly: smaller grid-stride grids for the later rounds
+        const int g1 = std::min((quads + 3) / 4, r < 3 ? sm_count * 4 : sm_count);
+        const int g2 = std::min((n + 127) / 128, r < 3 ? sm_count * 8 : sm_count);
         trace_replay_kernel<R, TAGGED><<<std::max(g1, 1), 128, 0, s>>>(a);
         trace_advance_kernel<R><<<std::max(g2, 1), 128, 0, s>>>(a);
         nl += 2;
+    }
+    if (r < a.max_rounds) {
+        a.round = r;
+        trace_tail_kernel<R, TAGGED><<<1, 128, 0, s>>>(a);
+        nl += 1;
     }
     if (launches) *launches += nl;
     return cudaGetLastError();

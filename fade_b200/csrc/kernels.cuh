@@ -32,7 +32,9 @@ struct AlnDesc {
 struct WarpItem {
     int64_t ck_off;    // word offset of this warp's checkpoints inside the scratch
     int32_t first;     // index of its first alignment
-    int32_t nblk;      // number of 32-step blocks (uniform over the warp)
+    int16_t nblk;      // number of 32-step blocks (uniform over the warp)
+    int16_t pad;
+    int32_t nsteps;    // wavefront steps of the score-only pass: tmax + FG - 1
 };
 
 struct RefDev {

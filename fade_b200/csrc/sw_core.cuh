@@ -181,10 +181,13 @@ FD uint32_t FADE_VIADDMAX_RELU(uint32_t a, uint32_t b, uint32_t c)
 }
 
 // One wavefront step of the score-only pass for one thread: column j of rows [0,R) of this thread.
-//   hdiag = H[first_row-1][j-1], hup = H[first_row-1][j] (not needed: only through f_in),
-//   f_in  = F[first_row][j]; returns f_out = F[first_row+R][j].
+//   hdiag = H[first_row-1][j-1], f_in = F[first_row][j]; returns f_out = F[first_row+R][j].
 // P2: E[i][j+1] = max(H[i][j]-o, E[i][j]-e); F[i+1][j] = max(H[i][j]-o, F[i][j]-e);
 //     H = max(0, Hdiag + s, E, F).
+// Per packed cell pair: LOP3 + PRMT (score), VIADDMNMX.RELU, VIMNMX, VIADD (H-open), 2x VIADDMNMX,
+// VIMNMX (running maximum) = 8 ALU-pipe issue units.  (Measured on B200: VIMNMX3 costs two units,
+// and moving H-open to the FMA pipe as IMAD in a biased domain needs one more max for the zero
+// floor, so neither reduces the ALU-pipe time)
 template <int R>
 FD void fill_step(uint32_t (&H)[R], uint32_t (&E)[R], const uint32_t (&qs)[R], uint32_t &M,
                   uint32_t ts, uint32_t hdiag, uint32_t f_in, uint32_t &f_out, const SwConsts &k)
@@ -284,8 +287,9 @@ FD void trace_step_tagged(uint32_t (&H)[R], uint32_t (&E)[R], const uint32_t (&q
     f_out = f;
 }
 
-// plain -> tagged domain (checkpoints are stored in the plain domain)
+// plain -> tagged domain
 FD uint32_t to_tagged(uint32_t w) { return (w << 4) & 0xfff0fff0u; }
+
 
 enum : int { T_ZERO = 0, T_DIAG = 1, T_F = 2, T_E = 3, T_EOPEN = 4, T_FOPEN = 8 };  // generic kernel
 
@@ -401,10 +405,16 @@ FD void ctl_advance(LaneCtl &c, const uint32_t *tile, int lane, const Acc &acc, 
         c.phase = 1;
     }
     // P4: walk while the current cell lies in the replayed block (hot fields in registers)
-    int i = c.i, j = c.j, mode = c.mode, hval = c.hval, gval = c.gval;
+    int i = c.i, j = c.j, mode = c.mode, hval = c.hval, gval = c.gval, nrev = c.nrev;
+    uint32_t cur = c.cur;
     const int cur_blk = c.cur_blk;
     bool done = false;
     int need = -1;
+    auto push = [&](uint32_t op) {
+        if (cur != 0 && (cur & 0xf) == op) { cur += 16; return; }
+        if (cur != 0) { c.ring[nrev % OPS_CAP] = cur; ++nrev; }
+        cur = (1u << 4) | op;
+    };
     for (;;) {
         if (i < 0 || j < 0) { done = true; break; }
         if (mode == 0 && hval <= 0) { done = true; break; }   // ZERO
@@ -417,24 +427,24 @@ FD void ctl_advance(LaneCtl &c, const uint32_t *tile, int lane, const Acc &acc, 
             const uint32_t src = nib >> 2;
             if (src == 2u) {
                 const bool eq = acc.qcode(i) == acc.tcode(j);
-                walk_push(c, eq ? OP_EQ : OP_X);
+                push(eq ? OP_EQ : OP_X);
                 hval -= eq ? k.match : k.mismatch;
                 --i; --j;
-            } else if (src == 1u) { walk_push(c, OP_I); --i; mode = 1; gval = hval; }
-            else { walk_push(c, OP_D); --j; mode = 2; gval = hval; }
+            } else if (src == 1u) { push(OP_I); --i; mode = 1; gval = hval; }
+            else { push(OP_D); --j; mode = 2; gval = hval; }
         } else if (mode == 1) {
             if (!(nib & 2u)) { hval = gval + k.open; mode = 0; }
-            else { walk_push(c, OP_I); --i; gval += k.extend; }
+            else { push(OP_I); --i; gval += k.extend; }
         } else {
             if (!(nib & 1u)) { hval = gval + k.open; mode = 0; }
-            else { walk_push(c, OP_D); --j; gval += k.extend; }
+            else { push(OP_D); --j; gval += k.extend; }
         }
     }
     c.i = i; c.j = j; c.mode = mode; c.hval = hval; c.gval = gval;
+    if (done && cur != 0) { c.ring[nrev % OPS_CAP] = cur; ++nrev; cur = 0; }   // flush the last op
+    c.cur = cur; c.nrev = nrev;
     if (!done) { c.next_blk = need; return; }
-    // done: flush the op being accumulated
     c.phase = 2;
-    if (c.cur != 0) { c.ring[c.nrev % OPS_CAP] = c.cur; ++c.nrev; c.cur = 0; }
     c.next_blk = -1;
 }
 
