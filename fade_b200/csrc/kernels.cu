@@ -297,34 +297,175 @@ __global__ void __launch_bounds__(128) trace_replay_kernel(const KernelArgs a)
                             gridDim.x * (blockDim.x >> 5), tws_all);
 }
 
+// One WARP per request.  The traceback is a pointer chase; to avoid one L2 round trip per step the
+// 32 lanes fetch the trace nibbles (and symbol codes) of the next 32 cells of the DIAGONAL through
+// the current cell at once, speculating that the path keeps going diagonally (gaps cost >= 10, so
+// it almost always does); a prefix sum of the step scores gives every lane the H value its cell
+// would have, the first lane whose step is not "DIAG with H > 0" ends the batch.  Gap steps are
+// taken one at a time.  Semantics are exactly those of ctl_advance (sw_core.cuh).
+struct AdvanceSmem {
+    LaneCtl ctl;     // staged copy of the alignment's traceback state
+    AlnOut out;      // result record, written out coalesced
+};
+static_assert(sizeof(LaneCtl) % 4 == 0 && sizeof(AlnOut) % 4 == 0, "word-copyable");
+
 template <int R>
-__device__ __forceinline__ void advance_round(const KernelArgs &a, int round, unsigned tid0, unsigned nthreads)
+__device__ __forceinline__ void advance_round(const KernelArgs &a, int round, unsigned warp0, unsigned nwarps,
+                                              AdvanceSmem *smem_all)
 {
+    constexpr int RW = trace_words<R>();
+    constexpr int CTLW = (int)(sizeof(LaneCtl) / 4), OUTW = (int)(sizeof(AlnOut) / 4);
+    AdvanceSmem &sm = smem_all[threadIdx.x >> 5];
     const int rin = round & 1;
     const unsigned cnt = a.qcount[rin];
     const unsigned long long *queue = a.queue[rin];
-    for (unsigned idx = tid0; idx < cnt; idx += nthreads) {
+    const int l = threadIdx.x & 31;
+    const SwConsts &k = a.k;
+    for (unsigned idx = warp0; idx < cnt; idx += nwarps) {
         const int aln = (int)(uint32_t)(queue[idx] & 0xffffffffu);
         const AlnDesc d = a.aln[aln];
-        LaneCtl &c = a.state[aln];
+        // stage the state in shared memory: one coalesced round trip instead of dozens of dependent ones
+        LaneCtl &c = sm.ctl;
+        {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&a.state[aln]);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&c);
+            for (int w = l; w < CTLW; w += 32) dst[w] = src[w];
+        }
+        __syncwarp();
+        const uint32_t *tile = a.tiles + (size_t)(idx >> 1) * tile_words<R>();
+        const int sh = 16 * (int)(idx & 1u);
         GlobalAcc acc;
         acc.seq = a.seq + d.seq_off; acc.qlen = d.qlen; acc.planes = a.ref.planes; acc.gstart = d.gstart;
-        ctl_advance<R>(c, a.tiles + (size_t)(idx >> 1) * tile_words<R>(), (int)(idx & 1u), acc, a.k);
-        if (c.phase == 2) {
-            AlnOut o;
-            finalize_result(c, o, d.read, d.clip_left, d.clip_right, a.min_length);
-            a.out[aln] = o;
-        } else if (round + 1 < a.max_rounds) {
-            const unsigned slot = atomicAdd(&a.qcount[rin ^ 1], 1u);
-            a.queue[rin ^ 1][slot] = pack_req(aln, c.next_blk, ctl_scanmask(c));
-        }   // else: out[aln] keeps its "no result" marker and fadegpu_wait reports the error
+        // ---- phase 0 bookkeeping by lane 0, then every lane reads the (uniform) state ----
+        int go = 1;
+        if (l == 0) {
+            c.cur_blk = c.next_blk;
+            if (c.phase == 0 && !ctl_select_end<R>(c)) go = 0;
+        }
+        go = __shfl_sync(FULL, go, 0);
+        __syncwarp();
+        bool done = false;
+        int need = -1;
+        if (go) {
+            int i = 0, j = 0, mode = 0, hval = 0, gval = 0, nrev = 0, cur_blk_ = 0;
+            uint32_t cur = 0;
+            if (l == 0) {
+                i = c.i; j = c.j; mode = c.mode; hval = c.hval; gval = c.gval; nrev = c.nrev; cur = c.cur;
+                cur_blk_ = c.cur_blk;
+            }
+            i = __shfl_sync(FULL, i, 0); j = __shfl_sync(FULL, j, 0); mode = __shfl_sync(FULL, mode, 0);
+            hval = __shfl_sync(FULL, hval, 0); gval = __shfl_sync(FULL, gval, 0); nrev = __shfl_sync(FULL, nrev, 0);
+            cur = __shfl_sync(FULL, cur, 0);
+            const int cur_blk = __shfl_sync(FULL, cur_blk_, 0);
+            auto push_n = [&](uint32_t op, int n) {
+                if (cur != 0 && (cur & 0xf) == op) { cur += 16u * (uint32_t)n; return; }
+                if (cur != 0) { if (l == 0) c.ring[nrev % OPS_CAP] = cur; ++nrev; }
+                cur = ((uint32_t)n << 4) | op;
+            };
+            for (;;) {
+                if (i < 0 || j < 0) { done = true; break; }
+                if (mode == 0 && hval <= 0) { done = true; break; }   // ZERO
+                if (mode == 0) {
+                    // speculative diagonal batch: lane l looks at cell (i-l, j-l)
+                    const int ii = i - l, jj = j - l;
+                    const bool valid = ii >= 0 && jj >= 0;
+                    const int g = valid ? ii / R : 0, r = valid ? ii - g * R : 0;
+                    const int t = jj + g;
+                    const bool inblk = valid && (t / FBLK) == cur_blk;
+                    uint32_t nib = 0;
+                    int sc = 0;
+                    bool eq = false;
+                    if (inblk) {
+                        nib = (tile[tile_index<R>(t % FBLK, g, r >> 2)] >> (sh + 4 * (r & 3))) & 0xfu;
+                        eq = acc.qcode(ii) == acc.tcode(jj);
+                        sc = eq ? k.match : k.mismatch;
+                    }
+                    const bool diag = inblk && (nib >> 2) == 2u;
+                    if (!diag) sc = 0;
+                    int pre = sc;                       // inclusive prefix sum over lanes
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(FULL, pre, o);
+                        if (l >= o) pre += v;
+                    }
+                    const int hv = hval - (pre - sc);   // H of this lane's cell if all earlier steps were DIAG
+                    const bool ok = diag && hv > 0;
+                    const unsigned bad = __ballot_sync(FULL, !ok);
+                    const int L = bad ? __ffs(bad) - 1 : 32;
+                    if (L > 0) {
+                        const unsigned lim = L == 32 ? 0xffffffffu : ((1u << L) - 1u);
+                        const unsigned eqm = __ballot_sync(FULL, eq) & lim;
+                        int kx = 0;
+                        while (kx < L) {
+                            const unsigned bit = (eqm >> kx) & 1u;
+                            const unsigned diff = ((bit ? ~eqm : eqm) & lim) >> kx;   // first position that differs
+                            int run = diff ? __ffs(diff) - 1 : L - kx;
+                            push_n(bit ? OP_EQ : OP_X, run);
+                            kx += run;
+                        }
+                        // H after L diagonal steps = H of lane L's cell (lane L-1's value minus its step)
+                        const int hlast = __shfl_sync(FULL, hv - sc, L - 1);
+                        hval = hlast;
+                        i -= L; j -= L;
+                        continue;
+                    }
+                    // lane 0's own cell is not a diagonal step
+                    if (!__shfl_sync(FULL, (int)inblk, 0)) {
+                        const int g0 = i / R;
+                        need = (j + g0) / FBLK;
+                        break;
+                    }
+                    const uint32_t n0 = __shfl_sync(FULL, nib, 0);
+                    if ((n0 >> 2) == 1u) { push_n(OP_I, 1); --i; mode = 1; gval = hval; }
+                    else { push_n(OP_D, 1); --j; mode = 2; gval = hval; }
+                } else {
+                    const int g = i / R, r = i - g * R;
+                    const int t = j + g;
+                    if (t / FBLK != cur_blk) { need = t / FBLK; break; }
+                    const uint32_t nib = (tile[tile_index<R>(t % FBLK, g, r >> 2)] >> (sh + 4 * (r & 3))) & 0xfu;
+                    if (mode == 1) {
+                        if (!(nib & 2u)) { hval = gval + k.open; mode = 0; }
+                        else { push_n(OP_I, 1); --i; gval += k.extend; }
+                    } else {
+                        if (!(nib & 1u)) { hval = gval + k.open; mode = 0; }
+                        else { push_n(OP_D, 1); --j; gval += k.extend; }
+                    }
+                }
+            }
+            if (done && cur != 0) { if (l == 0) c.ring[nrev % OPS_CAP] = cur; ++nrev; cur = 0; }
+            if (l == 0) {
+                c.i = i; c.j = j; c.mode = mode; c.hval = hval; c.gval = gval; c.cur = cur; c.nrev = nrev;
+                if (done) { c.phase = 2; c.next_blk = -1; } else c.next_blk = need;
+            }
+        }
+        __syncwarp();
+        const bool fin = c.phase == 2;
+        if (l == 0) {
+            if (fin) finalize_result(c, sm.out, d.read, d.clip_left, d.clip_right, a.min_length);
+            else if (round + 1 < a.max_rounds) {
+                const unsigned slot = atomicAdd(&a.qcount[rin ^ 1], 1u);
+                a.queue[rin ^ 1][slot] = pack_req(aln, c.next_blk, ctl_scanmask(c));
+            }   // else: out[aln] keeps its "no result" marker and fadegpu_wait reports the error
+        }
+        __syncwarp();
+        if (fin) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&sm.out);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&a.out[aln]);
+            for (int w = l; w < OUTW; w += 32) dst[w] = src[w];
+        } else {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&c);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&a.state[aln]);
+            for (int w = l; w < CTLW; w += 32) dst[w] = src[w];
+        }
+        __syncwarp();
     }
 }
 
 template <int R>
 __global__ void __launch_bounds__(128) trace_advance_kernel(const KernelArgs a)
 {
-    advance_round<R>(a, a.round, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    __shared__ AdvanceSmem adv[4];
+    advance_round<R>(a, a.round, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5), adv);
 }
 
 // The few alignments still unfinished after the full-grid rounds (very long paths): one block
@@ -333,6 +474,7 @@ template <int R, bool TAGGED>
 __global__ void __launch_bounds__(128) trace_tail_kernel(const KernelArgs a)
 {
     __shared__ uint16_t tws_all[16][40];
+    __shared__ AdvanceSmem adv[4];
     for (int r = a.round; r < a.max_rounds; ++r) {
         if (a.qcount[r & 1] == 0u) break;          // uniform: every thread reads the same counter
         __syncthreads();
@@ -341,7 +483,7 @@ __global__ void __launch_bounds__(128) trace_tail_kernel(const KernelArgs a)
         replay_round<R, TAGGED>(a, r, threadIdx.x >> 5, blockDim.x >> 5, tws_all);
         __threadfence_block();
         __syncthreads();
-        advance_round<R>(a, r, threadIdx.x, blockDim.x);
+        advance_round<R>(a, r, threadIdx.x >> 5, blockDim.x >> 5, adv);
         __threadfence_block();
         __syncthreads();
     }
@@ -556,7 +698,7 @@ static cudaError_t launch_trace_tt(KernelArgs a, cudaStream_t s, int sm_count, i
         a.round = r;
         // the queue shrinks quickly: smaller grid-stride grids for the later rounds
         const int g1 = std::min((quads + 3) / 4, r < 3 ? sm_count * 4 : sm_count);
-        const int g2 = std::min((n + 127) / 128, r < 3 ? sm_count * 8 : sm_count);
+        const int g2 = std::min((n + 3) / 4, r < 3 ? sm_count * 16 : sm_count * 2);   // a warp per request
         trace_replay_kernel<R, TAGGED><<<std::max(g1, 1), 128, 0, s>>>(a);
         trace_advance_kernel<R><<<std::max(g2, 1), 128, 0, s>>>(a);
         nl += 2;

@@ -382,28 +382,35 @@ FD uint32_t ctl_scanmask(const LaneCtl &c)
 // After a replay of block c.next_blk (its trace tile is `tile`): advance the per-lane state
 // machine.  lane = 0/1 (int16 half of the tile words); acc.qcode(i) / acc.tcode(j) give the symbol
 // codes of query row i / target column j.  P3 (end cell) and P4 (traceback) of SURVEY 8a.
+// Phase 0 bookkeeping after a scan replay (P3): mark the scanned candidates; either request the
+// next candidate block (returns false) or select the end cell and switch to the walk (true).
+template <int R>
+FD bool ctl_select_end(LaneCtl &c)
+{
+    for (int g = 0; g < FG; ++g)
+        if (c.best[g] == c.S && c.blk[g] == c.cur_blk) c.scanned |= 1u << g;
+    int nb = 0x7fffffff;
+    for (int g = 0; g < FG; ++g)
+        if (c.best[g] == c.S && !((c.scanned >> g) & 1u) && c.blk[g] < nb) nb = c.blk[g];
+    if (nb != 0x7fffffff) { c.next_blk = nb; return false; }
+    // P3: smallest column holding S, then smallest row
+    int bg = -1;
+    for (int g = 0; g < FG; ++g)
+        if (c.best[g] == c.S && (bg < 0 || c.fj[g] < c.fj[bg])) bg = g;
+    c.end_j = c.fj[bg];
+    c.end_i = bg * R + c.fr[bg];
+    c.i = c.end_i; c.j = c.end_j; c.mode = 0;
+    c.hval = c.S;
+    c.phase = 1;
+    return true;
+}
+
 template <int R, class Acc>
 FD void ctl_advance(LaneCtl &c, const uint32_t *tile, int lane, const Acc &acc, const SwConsts &k)
 {
     if (c.phase == 2) return;
     c.cur_blk = c.next_blk;
-    if (c.phase == 0) {
-        for (int g = 0; g < FG; ++g)
-            if (c.best[g] == c.S && c.blk[g] == c.cur_blk) c.scanned |= 1u << g;
-        int nb = 0x7fffffff;
-        for (int g = 0; g < FG; ++g)
-            if (c.best[g] == c.S && !((c.scanned >> g) & 1u) && c.blk[g] < nb) nb = c.blk[g];
-        if (nb != 0x7fffffff) { c.next_blk = nb; return; }
-        // P3: smallest column holding S, then smallest row
-        int bg = -1;
-        for (int g = 0; g < FG; ++g)
-            if (c.best[g] == c.S && (bg < 0 || c.fj[g] < c.fj[bg])) bg = g;
-        c.end_j = c.fj[bg];
-        c.end_i = bg * R + c.fr[bg];
-        c.i = c.end_i; c.j = c.end_j; c.mode = 0;
-        c.hval = c.S;
-        c.phase = 1;
-    }
+    if (c.phase == 0 && !ctl_select_end<R>(c)) return;
     // P4: walk while the current cell lies in the replayed block (hot fields in registers)
     int i = c.i, j = c.j, mode = c.mode, hval = c.hval, gval = c.gval, nrev = c.nrev;
     uint32_t cur = c.cur;
