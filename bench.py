@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--ref-len", type=int, default=REF_LEN)
     ap.add_argument("--chunk", type=int, default=CHUNK)
     ap.add_argument("--cpu-sample", type=int, default=40_000, help="reads in the cpu_baseline sample")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
     return ap.parse_args()
 
 
@@ -141,7 +142,9 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     ref, cfg, rd, _ = make_workload(argparse.Namespace(**{**vars(args), "reads": max(args.cpu_sample, 1)}), 0)
-    threads = os.cpu_count() or 1
+    threads = os.cpu_count() or 1          # rank 0 alone runs this arm: it may use every host core
+    from fade_b200 import sim as _sim
+    _sim.set_threads(threads)
     vals, gc = [], []
     for i in range(args.warmup + args.steps):
         v, g, n, dt = cpu_baseline(ref, rd, args.cpu_sample, threads)
@@ -157,7 +160,7 @@ def run_reference(args, rank: int, world: int):
         "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=args.out, flush=True)
 
 
 def workload_config(args) -> dict:
@@ -167,13 +170,31 @@ def workload_config(args) -> dict:
             "l2": "inputs + checkpoint scratch per chunk (>2 GB) exceed the 126 MB L2; no explicit flush"}
 
 
+def claim_stdout():
+    """Keep stdout clean for the ONE JSON line: everything else that writes to fd 1 (NCCL's version
+    banner, library chatter) goes to stderr; returns a writer bound to the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     args = parse_args()
+    out = claim_stdout()
     from fade_b200 import shard as _shard
     rank, local_rank, world = _shard.world()
+    # torchrun exports OMP_NUM_THREADS=1; the host side of the path (binning / gather / scatter) and
+    # the generators are told their thread count explicitly instead: the node's cores split by ranks
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_threads = args.host_threads or max(1, (os.cpu_count() or 1) // max(1, local_world))
+    args.host_threads = host_threads
+    args.out = out
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    from fade_b200 import sim as _sim
+    _sim.set_threads(host_threads)
 
     import torch
     import torch.distributed as dist
@@ -194,7 +215,8 @@ def main():
     max_over_ranks, sum_over_ranks = red.max, red.sum
 
     ref, cfg, rd, gen_s = make_workload(args, rank)
-    ctx = Context(local_rank)
+    from fade_b200 import default_params
+    ctx = Context(local_rank, default_params(host_threads=host_threads))
     ctx.load_reference(["chrS"], [ref.tobytes()])
     alu_ops, max_mhz = ctx.measure_alu_peak()
 
@@ -253,6 +275,13 @@ def main():
         acc += int(pending.flags[: pending.n].sum())
         return time.perf_counter() - t0, acc
 
+    host_ms = {}
+
+    def note_host(b):
+        st = b.stats()
+        for kx in ("host_submit_ms", "host_wait_ms", "host_classify_ms", "host_sort_ms", "host_gather_ms"):
+            host_ms[kx] = host_ms.get(kx, 0.0) + getattr(st, kx)
+
     # ---- warm-up ----
     for _ in range(args.warmup):
         kernel_step(False)
@@ -274,6 +303,8 @@ def main():
         dt, _ = e2e_step()
         e_s += dt
     barrier()
+    for b in batches:
+        note_host(b)
     clocks = sampler.stop()
 
     k_ms_max = max_over_ranks(k_ms)
@@ -293,7 +324,7 @@ def main():
         # algorithmic HBM bytes per alignment: window 2-bit + N mask, query, metadata, result
         n_al = max(agg["aligned"], 1)
         hbm_bytes = agg["h2d"] + agg["d2h"] + n_al * 270
-        cb_v, cb_g, cb_n, cb_dt = cpu_baseline(ref, rd, args.cpu_sample, os.cpu_count() or 1)
+        cb_v, cb_g, cb_n, cb_dt = cpu_baseline(ref, rd, args.cpu_sample, host_threads)
         line = {
             "metric": "annotate_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -303,7 +334,9 @@ def main():
             "aligned_reads_per_step": total_aligned, "artifact_reads_rank0": agg["art"],
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": agg["h2d"],
-                    "d2h_bytes_per_step": agg["d2h"], "ms_per_step": 1e3 * e_s_max / args.steps},
+                    "d2h_bytes_per_step": agg["d2h"], "ms_per_step": 1e3 * e_s_max / args.steps,
+                    "host_threads_per_rank": host_threads,
+                    "host_ms_last_chunks": {kx: round(v, 3) for kx, v in host_ms.items()}},
             "gpu_launches": agg["launches"] * args.steps,
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "GCUPS",
                          "frac": achieved / peak if peak > 0 else None, "traffic": None,
@@ -314,12 +347,12 @@ def main():
                          "r_alu_thread_instr_per_s": alu_ops, "peak_source": "measured live (fadegpu_measure_alu_peak)",
                          "hbm": {"algorithmic_gbs": hbm_bytes / (k_ms / args.steps * 1e-3) / 1e9,
                                  "peak_gbs": peak_hbm()}},
-            "cpu_baseline": {"value": cb_v, "unit": "reads/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "cpu_baseline": {"value": cb_v, "unit": "reads/s", "cores": host_threads, "kind": "port",
                              "gcups": cb_g,
-                             "sample": f"first {cb_n} reads of the workload, scalar oracle port, OpenMP all cores, {cb_dt:.1f} s"},
+                             "sample": f"first {cb_n} reads of the workload, scalar oracle port, OpenMP {host_threads} threads, {cb_dt:.1f} s"},
             "gen_seconds": gen_s,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     for b in batches:
         b.close()
     ctx.close()

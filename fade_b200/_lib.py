@@ -32,7 +32,8 @@ def build(force: bool = False) -> str:
 class Params(C.Structure):
     _fields_ = [("window_size", C.c_int32), ("min_length", C.c_int32), ("gap_open", C.c_int32),
                 ("gap_extend", C.c_int32), ("match", C.c_int32), ("mismatch", C.c_int32),
-                ("flags", C.c_uint32), ("scratch_bytes", C.c_int64)]
+                ("flags", C.c_uint32), ("scratch_bytes", C.c_int64), ("host_threads", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class BatchView(C.Structure):
@@ -58,7 +59,9 @@ class Stats(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_aligned", C.c_int64), ("n_generic", C.c_int64), ("cells", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int32),
                 ("kernel_ms", C.c_float), ("fill_ms", C.c_float), ("trace_ms", C.c_float),
-                ("generic_ms", C.c_float), ("total_ms", C.c_float), ("scratch_bytes", C.c_int64)]
+                ("generic_ms", C.c_float), ("total_ms", C.c_float), ("scratch_bytes", C.c_int64),
+                ("host_submit_ms", C.c_float), ("host_wait_ms", C.c_float), ("host_classify_ms", C.c_float),
+                ("host_sort_ms", C.c_float), ("host_gather_ms", C.c_float), ("host_threads", C.c_int32)]
 
 
 class HostRecord(C.Structure):

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <chrono>
 #include <string>
 #include <vector>
 #ifdef _OPENMP
@@ -54,6 +55,7 @@ struct fadegpu_ctx {
     size_t trace_bytes = 0;
     unsigned int *d_qcount = nullptr;
     int sm_count = 148;
+    int host_threads = 1;
     std::string err;
 };
 
@@ -318,6 +320,8 @@ int fadegpu_default_params(fadegpu_params *p)
     p->mismatch = -3;
     p->flags = 0;
     p->scratch_bytes = 0;
+    p->host_threads = 0;
+    p->reserved = 0;
     return FADEGPU_OK;
 }
 
@@ -344,6 +348,13 @@ int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
     c->device = device;
     c->p = pp;
     if (c->p.scratch_bytes <= 0) c->p.scratch_bytes = (int64_t)8 << 30;
+    {
+        int hw = 1;
+#ifdef _OPENMP
+        hw = std::max(1, omp_get_num_procs());
+#endif
+        c->host_threads = c->p.host_threads > 0 ? std::min(c->p.host_threads, 4 * hw) : hw;
+    }
     c->k = make_consts(pp.gap_open, pp.gap_extend, pp.match, pp.mismatch);
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_cursor, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&c->d_alu, 64)) != cudaSuccess ||
@@ -401,7 +412,7 @@ int fadegpu_load_reference(fadegpu_ctx *c, int32_t n_contigs, const char *const 
         const unsigned char *s = reinterpret_cast<const unsigned char *>(seqs[t]);
         const int64_t len = lengths[t], base = c->coff[t];
         const int64_t nwords = (len + 31) / 32;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(std::max(1, c->host_threads))
         for (int64_t wd = 0; wd < nwords; ++wd) {
             uint32_t a0 = 0, a1 = 0, n = 0, x = 0;
             const int64_t p0 = wd * 32;
@@ -572,10 +583,12 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     b->st.n_reads = n;
 
     // ---- 1. which reads need SW, their windows (analysis.d:34,45-59) and size class ----
-    int nthr = 1;
-#ifdef _OPENMP
-    nthr = std::max(1, omp_get_max_threads());
-#endif
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    const int nthr = std::max(1, c->host_threads);   // explicit: OMP_NUM_THREADS (torchrun sets it to 1) is ignored
+    b->st.host_threads = nthr;
     if ((int)b->tl_aln.size() < nthr) b->tl_aln.resize((size_t)nthr);
     const uint32_t floor_u = (uint32_t)c->p.min_length;  // uint <= int compare of analysis.d:34
     const int64_t W = c->p.window_size;
@@ -612,6 +625,8 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     }
     if (bad) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
     b->st.cells = cells;
+    b->st.host_classify_ms = ms_since(t_begin);
+    const auto t_sort = std::chrono::steady_clock::now();
 
     // ---- 2. bin by class, counting sort by window length (longest first) ----
     int64_t n_aln = 0;
@@ -642,6 +657,8 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     cls_first[4] = n_aln;
     for (const AlnTmp &a : all) sorted[(size_t)cnt[(size_t)key_of(a)]++] = a;
 
+    b->st.host_sort_ms = ms_since(t_sort);
+    const auto t_gather = std::chrono::steady_clock::now();
     // ---- 3. descriptors + gathered read bases ----
     std::vector<int64_t> &soff = b->soff;
     soff.resize((size_t)n_aln + 1);
@@ -678,6 +695,7 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
         memcpy(b->h_seq + d.seq_off, in->seq4 + in->seq_off[r], (size_t)((ql + 1) / 2));
     }
 
+    b->st.host_gather_ms = ms_since(t_gather);
     // ---- 4. launch plan ----
     static const int CLS[4] = { 13, 19, 32, 0 };
     int64_t n_items = 0;
@@ -764,6 +782,7 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     b->st.d2h_bytes = n_aln * (int64_t)sizeof(AlnOut);
     CU(c, cudaEventRecord(b->ev[3], c->stream));
     b->in_flight = true;
+    b->st.host_submit_ms = ms_since(t_begin);
     return FADEGPU_OK;
 }
 
@@ -789,11 +808,13 @@ int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
     float t;
     if (cudaEventElapsedTime(&t, b->ev[1], b->ev[2]) == cudaSuccess) b->st.kernel_ms = t;
     if (cudaEventElapsedTime(&t, b->ev[0], b->ev[3]) == cudaSuccess) b->st.total_ms = t;
+    const auto t_scatter = std::chrono::steady_clock::now();
     fadegpu_batch_view &v = b->v;
     const int64_t n = b->n_reads;
     memset(v.flags, 0, (size_t)n);   // the other outputs are defined only where FADEGPU_R_ALIGNED is set
     int bad = 0;
-#pragma omp parallel for schedule(static) reduction(| : bad)
+    const int nthr = std::max(1, c->host_threads);
+#pragma omp parallel for schedule(static) reduction(| : bad) num_threads(nthr)
     for (int64_t k = 0; k < b->n_aln; ++k) {
         const AlnOut &o = b->h_out[k];
         const int64_t r = b->h_aln[k].read;
@@ -804,6 +825,7 @@ int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
         v.win_start[r] = b->aln_start[(size_t)k];
         memcpy(v.ops + (size_t)r * FADEGPU_MAX_OPS, o.ops, sizeof(o.ops));
     }
+    b->st.host_wait_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_scatter).count();
     if (bad) return fail(c, FADEGPU_E_CUDA, "fadegpu_wait: a kernel did not produce a result record (internal error)");
     return FADEGPU_OK;
 }

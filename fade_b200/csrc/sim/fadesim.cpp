@@ -69,6 +69,16 @@ inline char up(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
 
 extern "C" {
 
+// host threads used by the generators (0 = leave the OpenMP default; torchrun sets OMP_NUM_THREADS=1)
+void fadesim_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 // Fill `out` (len bytes, no NUL) with a random contig.  n_run_every > 0 plants one N run of
 // n_run_len bases in every n_run_every bases (at a random offset); lower_frac of the 1-kb
 // tiles are lower-cased (soft-masking must be a no-op after upper-casing, analysis.d:63).

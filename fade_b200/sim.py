@@ -36,8 +36,14 @@ def _l():
         L.fadesim_reads.argtypes = [C.POINTER(SimCfg), C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_void_p),
                                     C.c_void_p] + [C.c_void_p] * 14
         L.fadesim_reads.restype = None
+        L.fadesim_set_threads.argtypes = [C.c_int]
+        L.fadesim_set_threads.restype = None
         _lib = L
     return _lib
+
+
+def set_threads(n: int):
+    _l().fadesim_set_threads(n)
 
 
 def default_cfg(**kw) -> SimCfg:

@@ -58,6 +58,8 @@ typedef struct fadegpu_params {
     int32_t mismatch;      /* -3  */
     uint32_t flags;        /* FADEGPU_F_* */
     int64_t scratch_bytes; /* cap on the device checkpoint scratch per launch; 0 = default */
+    int32_t host_threads;  /* host threads used by submit/wait (binning, gather, scatter); 0 = all cores */
+    int32_t reserved;
 } fadegpu_params;
 
 /* params.flags */
@@ -107,6 +109,10 @@ typedef struct fadegpu_stats {
     float fill_ms, trace_ms, generic_ms; /* per-stage device time (events on the ctx stream) */
     float total_ms;           /* H2D + kernels + D2H device time */
     int64_t scratch_bytes;    /* checkpoint scratch used */
+    float host_submit_ms;     /* wall clock of the host part of fadegpu_submit (binning, gather, queueing) */
+    float host_wait_ms;       /* wall clock of the host part of fadegpu_wait after the stream finished (scatter) */
+    float host_classify_ms, host_sort_ms, host_gather_ms;   /* parts of host_submit_ms */
+    int32_t host_threads;     /* threads actually used */
 } fadegpu_stats;
 
 int fadegpu_abi_version(void);

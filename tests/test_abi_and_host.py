@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.Params) == 40
+    assert C.sizeof(_lib.Params) == 48
     assert C.sizeof(_lib.Inputs) == 8 * 8
     assert C.sizeof(_lib.BatchView) == 8 * 19
     p = api.default_params()
