@@ -55,6 +55,17 @@ class Inputs(C.Structure):
                 ("clip_right", C.c_void_p)]
 
 
+class Result(C.Structure):
+    _fields_ = [("score", C.c_int32), ("end_query", C.c_int32), ("end_ref", C.c_int32), ("beg_query", C.c_int32),
+                ("beg_ref", C.c_int32), ("n_ops", C.c_int32), ("flags", C.c_uint32), ("read", C.c_int32),
+                ("ops", C.c_uint32 * 32)]
+
+
+class ResultsView(C.Structure):
+    _fields_ = [("n_results", C.c_int64), ("results", C.POINTER(Result)), ("win_start", C.POINTER(C.c_int64)),
+                ("result_index", C.POINTER(C.c_int32))]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_aligned", C.c_int64), ("n_generic", C.c_int64), ("cells", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int32),
@@ -75,7 +86,7 @@ ABI_SYMBOLS = [
     "fadegpu_abi_version", "fadegpu_device_count", "fadegpu_default_params", "fadegpu_create",
     "fadegpu_destroy", "fadegpu_last_error", "fadegpu_load_reference", "fadegpu_share_reference",
     "fadegpu_reference_info", "fadegpu_alloc_batch", "fadegpu_get_batch_view", "fadegpu_free_batch",
-    "fadegpu_submit", "fadegpu_submit_inputs", "fadegpu_wait", "fadegpu_get_stats", "fadegpu_replay_kernels",
+    "fadegpu_submit", "fadegpu_submit_inputs", "fadegpu_wait", "fadegpu_get_results", "fadegpu_get_stats", "fadegpu_replay_kernels",
     "fadegpu_measure_alu_peak",
     "fadehost_parse_clips", "fadehost_aligned_length", "fadehost_prepare", "fadehost_finish",
 ]
@@ -109,6 +120,7 @@ def lib():
     L.fadegpu_submit.argtypes = [vp, vp, i64]
     L.fadegpu_submit_inputs.argtypes = [vp, vp, i64, C.POINTER(Inputs)]
     L.fadegpu_wait.argtypes = [vp, vp]
+    L.fadegpu_get_results.argtypes = [vp, C.POINTER(ResultsView)]
     L.fadegpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.fadegpu_replay_kernels.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]
     L.fadegpu_measure_alu_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]

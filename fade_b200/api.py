@@ -7,11 +7,15 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from ._lib import BatchView, FadeGpuError, HostRecord, Inputs, Params, Stats, lib
+from ._lib import BatchView, FadeGpuError, HostRecord, Inputs, Params, Result, ResultsView, Stats, lib
 
 MAX_OPS = 32
 R_ALIGNED, R_ART_LEFT, R_ART_RIGHT, R_OPS_TRUNC, R_GENERIC = 1, 2, 4, 8, 16
 F_FORCE_GENERIC = 1
+F_NO_SCATTER = 2
+RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_query", "<i4"), ("end_ref", "<i4"), ("beg_query", "<i4"),
+                         ("beg_ref", "<i4"), ("n_ops", "<i4"), ("flags", "<u4"), ("read", "<i4"),
+                         ("ops", "<u4", (32,))])
 OPCHARS = "MIDNSHP=XB"
 
 
@@ -170,6 +174,22 @@ class Batch:
         self.submit(n)
         self.wait()
         return self
+
+    def results(self):
+        """fadegpu_get_results: (records[n_results] structured array, win_start[n_results], result_index[n])
+        as zero-copy numpy views valid until the next submit."""
+        rv = ResultsView()
+        self.ctx._check(lib().fadegpu_get_results(self._h, C.byref(rv)))
+        k = int(rv.n_results)
+        assert RESULT_DTYPE.itemsize == C.sizeof(Result)
+        if k == 0:
+            rec = np.zeros(0, dtype=RESULT_DTYPE)
+            ws = np.zeros(0, dtype=np.int64)
+        else:
+            addr = C.cast(rv.results, C.c_void_p).value
+            rec = np.frombuffer((C.c_char * (k * RESULT_DTYPE.itemsize)).from_address(addr), dtype=RESULT_DTYPE, count=k)
+            ws = _np_view(rv.win_start, k, np.int64)
+        return rec, ws, _np_view(rv.result_index, self.n, np.int32)
 
     def stats(self) -> Stats:
         s = Stats()

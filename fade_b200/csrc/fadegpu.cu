@@ -59,9 +59,11 @@ struct fadegpu_ctx {
     std::string err;
 };
 
-struct AlnTmp {       // a read that needs SW, before sorting
+struct AlnTmp {       // a read that needs SW, captured in read order (sequential pass), before sorting
     int64_t start;    // window start inside the contig
-    int32_t read, tlen, cls;
+    int64_t so;       // byte offset of its bases inside the caller's seq4
+    int32_t read, tlen, cls, qlen, tid, key;
+    uint32_t clip_left, clip_right;
 };
 
 struct Launch {
@@ -92,7 +94,9 @@ struct fadegpu_batch {
     bool in_flight = false;
     // scratch for the host binning
     std::vector<std::vector<AlnTmp>> tl_aln;   // per host thread
-    std::vector<AlnTmp> all_aln, sorted_aln;
+    std::vector<uint32_t> order;               // alignment indices sorted by (class, window length desc)
+    int32_t *h_ridx = nullptr;                 // [max_reads] per read: index into the results, -1 = none
+    std::vector<AlnTmp> all_aln;
     std::vector<int32_t> cnt;
     std::vector<int64_t> soff, aln_start;
 };
@@ -137,6 +141,8 @@ RefDev ref_dev(const fadegpu_ctx *c)
     r.xpos = c->d_xpos; r.xchr = c->d_xchr; r.n_x = c->n_x;
     return r;
 }
+
+int cls_rank(int cls) { return cls == 13 ? 0 : cls == 19 ? 1 : cls == 32 ? 2 : 3; }
 
 int class_of(const fadegpu_ctx *c, int qlen, int tlen)
 {
@@ -509,7 +515,7 @@ void fadegpu_free_batch(fadegpu_batch *b)
     free_host(v.aligned_len); free_host(v.clip_left); free_host(v.clip_right);
     free_host(v.flags); free_host(v.score); free_host(v.beg_query); free_host(v.end_query);
     free_host(v.beg_ref); free_host(v.end_ref); free_host(v.win_start); free_host(v.n_ops); free_host(v.ops);
-    free_host(b->h_aln); free_host(b->h_items); free_host(b->h_seq); free_host(b->h_out);
+    free_host(b->h_aln); free_host(b->h_items); free_host(b->h_seq); free_host(b->h_out); free_host(b->h_ridx);
     free_dev(b->d_aln); free_dev(b->d_items); free_dev(b->d_seq); free_dev(b->d_out); free_dev(b->d_flags);
     free_dev(b->d_fillres);
     for (auto &e : b->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -539,7 +545,7 @@ int fadegpu_alloc_batch(fadegpu_ctx *c, int64_t max_reads, int64_t max_seq_bytes
     H(&v.flags, n); H(&v.score, n * 4); H(&v.beg_query, n * 4); H(&v.end_query, n * 4); H(&v.beg_ref, n * 4);
     H(&v.end_ref, n * 4); H(&v.win_start, n * 8); H(&v.n_ops, n * 4); H(&v.ops, n * 4 * FADEGPU_MAX_OPS);
     H(&b->h_aln, n * sizeof(AlnDesc)); H(&b->h_items, (size_t)b->cap_items * sizeof(WarpItem));
-    H(&b->h_seq, (size_t)b->cap_seq); H(&b->h_out, n * sizeof(AlnOut));
+    H(&b->h_seq, (size_t)b->cap_seq); H(&b->h_out, n * sizeof(AlnOut)); H(&b->h_ridx, n * 4);
     D(&b->d_aln, n * sizeof(AlnDesc)); D(&b->d_items, (size_t)b->cap_items * sizeof(WarpItem));
     D(&b->d_seq, (size_t)b->cap_seq); D(&b->d_out, n * sizeof(AlnOut)); D(&b->d_flags, n * 4);
     D(&b->d_fillres, (size_t)b->cap_items * 32 * sizeof(uint2));
@@ -559,12 +565,6 @@ int fadegpu_get_batch_view(fadegpu_batch *b, fadegpu_batch_view *view)
     *view = b->v;
     return FADEGPU_OK;
 }
-
-namespace {
-
-int cls_rank(int cls) { return cls == 13 ? 0 : cls == 19 ? 1 : cls == 32 ? 2 : 3; }
-
-}  // namespace
 
 int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, const fadegpu_inputs *in)
 {
@@ -619,7 +619,11 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
             if (end > c->clen[tid]) end = c->clen[tid];
             if (end <= start || end - start > 0x7fffffff) continue;  // empty window: nothing to align
             const int tlen = (int)(end - start);
-            loc.push_back(AlnTmp{ start, (int32_t)r, tlen, class_of(c, ql, tlen) });
+            const int cls = class_of(c, ql, tlen);
+            const int rk = cls_rank(cls);
+            // key = class rank (13, 19, 32, generic) then descending window length (generic: input order)
+            const int key = rk * (TMAX_FAST + 2) + (rk == 3 ? 0 : TMAX_FAST - tlen);
+            loc.push_back(AlnTmp{ start, so, (int32_t)r, tlen, cls, ql, tid, key, cl, cr });
             cells += (int64_t)ql * tlen;
         }
     }
@@ -631,9 +635,10 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     // ---- 2. bin by class, counting sort by window length (longest first) ----
     int64_t n_aln = 0;
     for (int t = 0; t < nthr; ++t) n_aln += (int64_t)b->tl_aln[(size_t)t].size();
-    std::vector<AlnTmp> &all = b->all_aln, &sorted = b->sorted_aln;
+    std::vector<AlnTmp> &all = b->all_aln;
+    std::vector<uint32_t> &order = b->order;
     all.resize((size_t)n_aln);
-    sorted.resize((size_t)n_aln);
+    order.resize((size_t)n_aln);
     {
         int64_t o = 0;
         for (int t = 0; t < nthr; ++t) {
@@ -642,20 +647,16 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
             o += (int64_t)loc.size();
         }
     }
-    // key = class rank (13, 19, 32, generic) then descending window length (generic: input order)
+    // counting sort of the INDICES (stable: equal keys keep read order)
     const int KEYS = 4 * (TMAX_FAST + 2);
     std::vector<int32_t> &cnt = b->cnt;
     cnt.assign((size_t)KEYS + 1, 0);
-    auto key_of = [](const AlnTmp &a) {
-        const int rk = cls_rank(a.cls);
-        return rk * (TMAX_FAST + 2) + (rk == 3 ? 0 : TMAX_FAST - a.tlen);
-    };
-    for (const AlnTmp &a : all) ++cnt[(size_t)key_of(a) + 1];
+    for (const AlnTmp &a : all) ++cnt[(size_t)a.key + 1];
     for (int kx = 0; kx < KEYS; ++kx) cnt[(size_t)kx + 1] += cnt[(size_t)kx];
     int64_t cls_first[5];
     for (int rk = 0; rk < 4; ++rk) cls_first[rk] = cnt[(size_t)rk * (TMAX_FAST + 2)];
     cls_first[4] = n_aln;
-    for (const AlnTmp &a : all) sorted[(size_t)cnt[(size_t)key_of(a)]++] = a;
+    for (int64_t kx = 0; kx < n_aln; ++kx) order[(size_t)cnt[(size_t)all[(size_t)kx].key]++] = (uint32_t)kx;
 
     b->st.host_sort_ms = ms_since(t_sort);
     const auto t_gather = std::chrono::steady_clock::now();
@@ -667,10 +668,10 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
         int64_t o = 0;
         for (int64_t kx = 0; kx < n_aln; ++kx) {
             soff[(size_t)kx] = o;
-            const int ql = in->l_qseq[sorted[(size_t)kx].read];
-            o += (ql + 1) / 2;
-            qmax_all = std::max(qmax_all, ql);
-            tmax_all = std::max(tmax_all, sorted[(size_t)kx].tlen);
+            const AlnTmp &a = all[order[(size_t)kx]];
+            o += (a.qlen + 1) / 2;
+            qmax_all = std::max(qmax_all, a.qlen);
+            tmax_all = std::max(tmax_all, a.tlen);
         }
         soff[(size_t)n_aln] = o;
     }
@@ -679,20 +680,23 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     b->aln_start.resize((size_t)n_aln);
 #pragma omp parallel for schedule(static) num_threads(nthr)
     for (int64_t kx = 0; kx < n_aln; ++kx) {
-        const AlnTmp &a = sorted[(size_t)kx];
-        const int64_t r = a.read;
+        const AlnTmp &a = all[order[(size_t)kx]];
+        if (kx + 8 < n_aln) {   // the bases sit at random places of the caller's array: prefetch ahead
+            const uint8_t *pf = in->seq4 + all[order[(size_t)kx + 8]].so;
+            __builtin_prefetch(pf); __builtin_prefetch(pf + 64);
+        }
         AlnDesc &d = b->h_aln[kx];
-        const int ql = in->l_qseq[r];
-        d.gstart = c->coff[in->tid[r]] + a.start;
+        const int ql = a.qlen;
+        d.gstart = c->coff[a.tid] + a.start;
         d.seq_off = soff[(size_t)kx];
         d.tlen = a.tlen;
         d.qlen = ql;
-        d.clip_left = (uint32_t)in->clip_left[r];
-        d.clip_right = (uint32_t)in->clip_right[r];
-        d.read = (int32_t)r;
+        d.clip_left = a.clip_left;
+        d.clip_right = a.clip_right;
+        d.read = a.read;
         d.pad = 0;
         b->aln_start[(size_t)kx] = a.start;
-        memcpy(b->h_seq + d.seq_off, in->seq4 + in->seq_off[r], (size_t)((ql + 1) / 2));
+        memcpy(b->h_seq + d.seq_off, in->seq4 + a.so, (size_t)((ql + 1) / 2));
     }
 
     b->st.host_gather_ms = ms_since(t_gather);
@@ -811,15 +815,19 @@ int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
     const auto t_scatter = std::chrono::steady_clock::now();
     fadegpu_batch_view &v = b->v;
     const int64_t n = b->n_reads;
-    memset(v.flags, 0, (size_t)n);   // the other outputs are defined only where FADEGPU_R_ALIGNED is set
+    memset(v.flags, 0, (size_t)n);   // the other per-read outputs are defined only where FADEGPU_R_ALIGNED is set
+    memset(b->h_ridx, 0xff, (size_t)n * sizeof(int32_t));
     int bad = 0;
     const int nthr = std::max(1, c->host_threads);
+    const bool scatter = !(c->p.flags & FADEGPU_F_NO_SCATTER);
 #pragma omp parallel for schedule(static) reduction(| : bad) num_threads(nthr)
     for (int64_t k = 0; k < b->n_aln; ++k) {
         const AlnOut &o = b->h_out[k];
         const int64_t r = b->h_aln[k].read;
         if (o.read != (int32_t)r || (o.flags & 0x80000000u)) { bad = 1; continue; }
         v.flags[r] = (uint8_t)(o.flags & 0xff);
+        b->h_ridx[r] = (int32_t)k;
+        if (!scatter) continue;
         v.score[r] = o.score; v.beg_query[r] = o.beg_query; v.end_query[r] = o.end_query;
         v.beg_ref[r] = o.beg_ref; v.end_ref[r] = o.end_ref; v.n_ops[r] = o.n_ops;
         v.win_start[r] = b->aln_start[(size_t)k];
@@ -827,6 +835,18 @@ int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
     }
     b->st.host_wait_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_scatter).count();
     if (bad) return fail(c, FADEGPU_E_CUDA, "fadegpu_wait: a kernel did not produce a result record (internal error)");
+    return FADEGPU_OK;
+}
+
+int fadegpu_get_results(const fadegpu_batch *b, fadegpu_results_view *r)
+{
+    if (!b || !r) return fail(nullptr, FADEGPU_E_ARG, "fadegpu_get_results: null argument");
+    if (b->in_flight) return fail(b->ctx, FADEGPU_E_STATE, "fadegpu_get_results: batch in flight (call fadegpu_wait)");
+    static_assert(sizeof(fadegpu_result) == sizeof(AlnOut), "fadegpu_result must mirror AlnOut");
+    r->n_results = b->n_aln;
+    r->results = reinterpret_cast<const fadegpu_result *>(b->h_out);
+    r->win_start = b->aln_start.data();
+    r->result_index = b->h_ridx;
     return FADEGPU_OK;
 }
 

@@ -64,6 +64,8 @@ typedef struct fadegpu_params {
 
 /* params.flags */
 #define FADEGPU_F_FORCE_GENERIC 1u /* route every alignment through the generic (slow) kernel */
+#define FADEGPU_F_NO_SCATTER 2u    /* fadegpu_wait fills only flags[] and the compact results
+                                      (fadegpu_get_results), not the other per-read output arrays */
 
 /* per-read result flags */
 #define FADEGPU_R_ALIGNED 1u    /* SW ran for this read (some clip passed the length floor) */
@@ -153,6 +155,26 @@ typedef struct fadegpu_inputs {
 int fadegpu_submit_inputs(fadegpu_ctx *ctx, fadegpu_batch *b, int64_t n_reads, const fadegpu_inputs *in);
 /* Blocks until the batch is done and scatters the results into the view's output arrays. */
 int fadegpu_wait(fadegpu_ctx *ctx, fadegpu_batch *b);
+
+/* Compact results of the last fadegpu_wait: one record per read for which SW ran, in the
+ * library's processing order, plus a per-read index into them.  Always filled (cheaper for the
+ * host than the per-read arrays of the view: nothing is scattered but flags[] and the index). */
+typedef struct fadegpu_result {
+    int32_t score;                 /* res.score */
+    int32_t end_query, end_ref;    /* end cell, window relative */
+    int32_t beg_query, beg_ref;    /* beg_ref == res.position */
+    int32_t n_ops;                 /* res.cigar.length including the S padding */
+    uint32_t flags;                /* FADEGPU_R_* */
+    int32_t read;                  /* index of the read inside the batch */
+    uint32_t ops[FADEGPU_MAX_OPS]; /* BAM-encoded, forward order */
+} fadegpu_result;
+typedef struct fadegpu_results_view {
+    int64_t n_results;
+    const fadegpu_result *results;   /* [n_results] */
+    const int64_t *win_start;        /* [n_results] `start` of analysis.d:45-51 */
+    const int32_t *result_index;     /* [n_reads]  index into results, -1 = no SW for this read */
+} fadegpu_results_view;
+int fadegpu_get_results(const fadegpu_batch *b, fadegpu_results_view *r);
 
 /* Measurement helpers (bench.py): stats of the last submit, and a re-run of ONLY the kernels on
  * the inputs already resident in HBM (no host work, no copies), timed with CUDA events on the ctx

@@ -202,3 +202,37 @@ def test_submit_inputs_from_caller_arrays(gpu_ctx):
         sub = sim.make_reads(cfg, a, 2000, contigs)
         compare(b, sub, contigs, oracle_params(gpu_ctx.params))
     b.close()
+
+
+def test_compact_results_and_no_scatter():
+    """fadegpu_get_results (compact records + per-read index) carries the same data as the per-read
+    arrays; with FADEGPU_F_NO_SCATTER only flags[] and the compact results are filled."""
+    names, contigs, cfg, n = sim.config_c1()
+    rd = sim.make_reads(cfg, 0, 4000, contigs)
+    with _ctx() as ctx:
+        ctx.load_reference(names, [c.tobytes() for c in contigs])
+        b = run_gpu(ctx, rd)
+        compare(b, rd, contigs, oracle_params(ctx.params))
+        rec, ws, ridx = b.results()
+        al = np.where(b.flags[: rd.n] & 1)[0]
+        assert len(rec) == len(al) == b.stats().n_aligned
+        assert np.array_equal(np.sort(rec["read"]), al) and np.array_equal(np.where(ridx >= 0)[0], al)
+        k = ridx[al]
+        assert np.array_equal(rec["read"][k], al)
+        for f in ("score", "beg_query", "end_query", "beg_ref", "end_ref", "n_ops"):
+            assert np.array_equal(rec[f][k], getattr(b, f)[al]), f
+        assert np.array_equal(ws[k], b.win_start[al]) and np.array_equal(rec["ops"][k], b.ops[al])
+        assert np.array_equal(rec["flags"][k] & 0xff, b.flags[al])
+        ref_flags = b.flags[: rd.n].copy()
+        ref_rec = rec.copy()
+        b.close()
+    with _ctx(flags=api.F_NO_SCATTER) as ctx:
+        ctx.load_reference(names, [c.tobytes() for c in contigs])
+        b = ctx.alloc_batch(rd.n, int(rd.seq_off[rd.n]))
+        b.score[:] = -7
+        b.fill(rd.seq4, rd.seq_off, rd.l_qseq, rd.tid, rd.pos, rd.aligned_len, rd.clip_left, rd.clip_right).run()
+        rec2, ws2, ridx2 = b.results()
+        assert np.array_equal(b.flags[: rd.n], ref_flags) and (b.score[: rd.n] == -7).all()
+        o1, o2 = np.argsort(ref_rec["read"]), np.argsort(rec2["read"])
+        assert np.array_equal(ref_rec[o1], rec2[o2])
+        b.close()
