@@ -1,0 +1,93 @@
+// ubench.cu -- instruction-throughput microbenchmarks for the INT16x2 DP instruction mix on B200.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench ubench.cu ; run on the GPU box.
+// Prints thread-instructions / clk / SM for each kernel (8 independent chains per thread unless noted).
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CHK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k(uint32_t *out, int iters, uint32_t c1, uint32_t c2, uint32_t one)
+{
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 3 + i;
+    uint32_t y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = threadIdx.x * 5 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (KIND == 0) x[i] = __viaddmax_s16x2(x[i], c1, c2);
+                if (KIND == 1) x[i] = __vimax3_s16x2(x[i], c1, c2);
+                if (KIND == 2) x[i] = __vmaxs2(x[i], c1);
+                if (KIND == 3) x[i] = __vadd2(x[i], c1);
+                if (KIND == 4) x[i] = __byte_perm(x[i], c1, c2);
+                if (KIND == 5) x[i] = (x[i] ^ c1) & c2;
+                if (KIND == 6) x[i] = x[i] * one + c1;                       // IMAD
+                if (KIND == 7) { x[i] = __viaddmax_s16x2(x[i], c1, c2); y[i] = y[i] * one + c1; }   // ALU + FMA pipes
+                if (KIND == 8) { x[i] = __viaddmax_s16x2(x[i], c1, c2); y[i] = __vmaxs2(y[i], c1); } // 2 ALU
+                if (KIND == 9) x[i] = __viaddmax_s16x2_relu(x[i], c1, c2);
+                if (KIND == 10) { x[i] = __viaddmax_s16x2(x[i], c1, c2); y[i] = (y[i] ^ c1) & c2; }
+                if (KIND == 11) { x[i] = __viaddmax_s16x2(x[i], c1, y[i]); y[i] = __viaddmax_s16x2(y[i], c2, x[i]); } // 3 register operands
+                if (KIND == 12) { x[i] = __vmaxs2(x[i], c1); y[i] = y[i] * one + c1; }
+                if (KIND == 13) x[i] = __vimax3_s16x2_relu(x[i], c1, c2);
+            }
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= x[i] ^ y[i];
+    if (r == 0x12345678u) out[0] = r;
+}
+
+template <int KIND>
+int run(const char *name, int per_iter, int sms, double mhz)
+{
+    uint32_t *d;
+    CHK(cudaMalloc(&d, 64));
+    const int blocks = sms * 8, threads = 256, iters = 2048;
+    cudaEvent_t e0, e1;
+    CHK(cudaEventCreate(&e0)); CHK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CHK(cudaEventRecord(e0));
+        k<KIND><<<blocks, threads>>>(d, iters, 0x00010003u, 0xfffefffdu, 1u);
+        CHK(cudaEventRecord(e1));
+        CHK(cudaEventSynchronize(e1));
+        float ms; CHK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep && ms < best) best = ms;
+    }
+    const double ops = (double)blocks * threads * iters * 64.0 * per_iter;
+    const double per_clk_sm = ops / (best * 1e-3) / (mhz * 1e6) / sms;
+    printf("%-34s %8.3f ms  %7.1f thread-instr/clk/SM  (%.2e /s)\n", name, best, per_clk_sm, ops / (best * 1e-3));
+    cudaFree(d);
+    return 0;
+}
+
+int main()
+{
+    cudaDeviceProp p; CHK(cudaGetDeviceProperties(&p, 0));
+    int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    const double mhz = khz / 1000.0;
+    printf("%s, %d SMs, max clock %.0f MHz (rates assume max clock)\n", p.name, p.multiProcessorCount, mhz);
+    const int s = p.multiProcessorCount;
+    run<0>("VIADDMNMX.S16x2", 1, s, mhz);
+    run<9>("VIADDMNMX.S16x2.RELU", 1, s, mhz);
+    run<1>("VIMNMX3.S16x2", 1, s, mhz);
+    run<13>("VIMNMX3.S16x2.RELU", 1, s, mhz);
+    run<2>("VIMNMX.S16x2", 1, s, mhz);
+    run<3>("VIADD.16x2", 1, s, mhz);
+    run<4>("PRMT", 1, s, mhz);
+    run<5>("LOP3", 1, s, mhz);
+    run<6>("IMAD", 1, s, mhz);
+    run<7>("VIADDMNMX + IMAD (2 per iter)", 2, s, mhz);
+    run<8>("VIADDMNMX + VIMNMX (2 per iter)", 2, s, mhz);
+    run<10>("VIADDMNMX + LOP3 (2 per iter)", 2, s, mhz);
+    run<11>("VIADDMNMX 3-reg x2 (2 per iter)", 2, s, mhz);
+    run<12>("VIMNMX + IMAD (2 per iter)", 2, s, mhz);
+    return 0;
+}
