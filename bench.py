@@ -14,8 +14,9 @@ min-length), processed as chunks of --chunk reads through the C ABI (libfadegpu.
          D2H) and fadegpu_wait scatters the results; double-buffered; the flags are read back.
   roofline  the INT16x2 ALU roofline of SURVEY.md 8(d): cells/s against 2*R_alu/9 with R_alu
          measured live by fadegpu_measure_alu_peak (packed VIADDMNMX.S16x2 issue rate).
-  cpu_baseline  the oracle port (oracle/fade_oracle.c, scalar, OpenMP on all host cores) timed
-         on a bounded sample of the same reads.  `--impl reference` prints that arm on its own.
+  cpu_baseline  a CPU port of the path (oracle/fade_oracle_simd.c: AVX2, 16 alignments per vector,
+         trace table + traceback, OpenMP on the host cores; validated against the scalar oracle)
+         timed on a bounded sample of the same reads.  `--impl reference` prints that arm alone.
 
 Multi-GPU: launched under torchrun, one rank per GPU; every rank holds its own reference copy
 and its own shard of reads (weak scaling, no data-path collective); value = all ranks' reads /
@@ -53,8 +54,11 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=N_READS, help="reads per GPU per step")
     ap.add_argument("--ref-len", type=int, default=REF_LEN)
     ap.add_argument("--chunk", type=int, default=CHUNK)
-    ap.add_argument("--cpu-sample", type=int, default=40_000, help="reads in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="reads in the cpu_baseline sample")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2 = BASELINE configs[1] (default, the bench line); c4 = stress sweep configs[3]: 2x250 reads, "
+                         "--window-size 1000, clip law U{1..40} (use with --reads 2000000)")
     return ap.parse_args()
 
 
@@ -112,23 +116,31 @@ def make_workload(args, rank: int):
     from fade_b200 import sim
     t0 = time.time()
     ref = sim.make_contig(REF_SEED, 0, args.ref_len, 0, 0, 0.0)
-    cfg = sim.default_cfg(read_seed=READ_SEED)
+    if getattr(args, "workload", "c2") == "c4":
+        cfg = sim.default_cfg(read_seed=2004, read_len=250, window=1000, frag_mean=600, frag_sd=80, short_clip_law=1)
+    else:
+        cfg = sim.default_cfg(read_seed=READ_SEED)
     from fade_b200 import shard
     first, last = shard.weak_range(args.reads, rank)      # every rank owns its slice of the read stream
     rd = sim.make_reads(cfg, first, last - first, [ref], with_records=False)
     return ref, cfg, rd, time.time() - t0
 
 
-def cpu_baseline(ref, rd, n_sample: int, threads: int):
-    """Oracle port on the host cores over the first n_sample reads: reads/s, GCUPS."""
+CPU_KIND = ("AVX2 16-lane inter-sequence port of the path (oracle/fade_oracle_simd.c: SW fill with trace table, "
+            "traceback, predicates; in-memory reference), validated against the scalar oracle")
+
+
+def cpu_baseline(ref, rd, n_sample: int, threads: int, window: int = 300):
+    """CPU port of the path on the host cores over the first n_sample reads: reads/s, GCUPS."""
     from oracle import oracle as orc
+    prm = orc.default_params(window_size=window)
     n = min(n_sample, rd.n)
     sl = slice(0, n)
     off = rd.seq_off[: n + 1]
     contigs = [ref.tobytes()]
     t0 = time.perf_counter()
     res, _ = orc.align_batch(rd.seq4[: int(off[n])], off, rd.l_qseq[sl], rd.tid[sl], rd.pos[sl], rd.aligned_len[sl],
-                             rd.clip_left[sl], rd.clip_right[sl], contigs, n_threads=threads)
+                             rd.clip_left[sl], rd.clip_right[sl], contigs, params=prm, n_threads=threads, simd=True)
     dt = time.perf_counter() - t0
     al = res["aligned"] == 1
     cells = int((rd.l_qseq[sl][al].astype(np.int64) * res["tlen"][al]).sum())
@@ -147,11 +159,11 @@ def run_reference(args, rank: int, world: int):
     _sim.set_threads(threads)
     vals, gc = [], []
     for i in range(args.warmup + args.steps):
-        v, g, n, dt = cpu_baseline(ref, rd, args.cpu_sample, threads)
+        v, g, n, dt = cpu_baseline(ref, rd, args.cpu_sample, threads, 1000 if args.workload == "c4" else 300)
         if i >= args.warmup:
             vals.append(v); gc.append(g)
     v = statistics.mean(vals)
-    sample = f"first {args.cpu_sample} reads of the workload per step, scalar oracle port, OpenMP {threads} threads"
+    sample = f"first {args.cpu_sample} reads of the workload per step; {CPU_KIND}; OpenMP {threads} threads"
     line = {
         "impl": "reference", "metric": "annotate_reads_per_sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.cpu_sample / v,
@@ -164,8 +176,13 @@ def run_reference(args, rank: int, world: int):
 
 
 def workload_config(args) -> dict:
-    return {"workload": f"{args.reads} simulated 2x150 paired reads (seed {READ_SEED}) vs synthetic "
-                        f"{args.ref_len} bp chromosome (seed {REF_SEED}), window-size 300, min-length 5, per GPU",
+    if getattr(args, "workload", "c2") == "c4":
+        desc = (f"{args.reads} simulated 2x250 paired reads (seed 2004, clip lengths U(1..40)) vs synthetic "
+                f"{args.ref_len} bp chromosome (seed {REF_SEED}), window-size 1000, min-length 5, per GPU")
+    else:
+        desc = (f"{args.reads} simulated 2x150 paired reads (seed {READ_SEED}) vs synthetic "
+                f"{args.ref_len} bp chromosome (seed {REF_SEED}), window-size 300, min-length 5, per GPU")
+    return {"workload": desc,
             "chunk_reads": args.chunk,
             "l2": "inputs + checkpoint scratch per chunk (>2 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -218,7 +235,8 @@ def main():
     from fade_b200 import default_params
     from fade_b200 import api as _api
     # compact results (fadegpu_get_results): fadegpu_wait scatters only flags[] and the result index
-    ctx = Context(local_rank, default_params(host_threads=host_threads, flags=_api.F_NO_SCATTER))
+    ctx = Context(local_rank, default_params(host_threads=host_threads, flags=_api.F_NO_SCATTER,
+                                             window_size=1000 if args.workload == "c4" else 300))
     ctx.load_reference(["chrS"], [ref.tobytes()])
     alu_ops, max_mhz = ctx.measure_alu_peak()
 
@@ -331,7 +349,7 @@ def main():
         # algorithmic HBM bytes per alignment: window 2-bit + N mask, query, metadata, result
         n_al = max(agg["aligned"], 1)
         hbm_bytes = agg["h2d"] + agg["d2h"] + n_al * 270
-        cb_v, cb_g, cb_n, cb_dt = cpu_baseline(ref, rd, args.cpu_sample, host_threads)
+        cb_v, cb_g, cb_n, cb_dt = cpu_baseline(ref, rd, args.cpu_sample, host_threads, 1000 if args.workload == "c4" else 300)
         line = {
             "metric": "annotate_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -356,7 +374,7 @@ def main():
                                  "peak_gbs": peak_hbm()}},
             "cpu_baseline": {"value": cb_v, "unit": "reads/s", "cores": host_threads, "kind": "port",
                              "gcups": cb_g,
-                             "sample": f"first {cb_n} reads of the workload, scalar oracle port, OpenMP {host_threads} threads, {cb_dt:.1f} s"},
+                             "sample": f"first {cb_n} reads of the workload; {CPU_KIND}; OpenMP {host_threads} threads, {cb_dt:.1f} s"},
             "gen_seconds": gen_s,
         }
         print(json.dumps(line), file=out, flush=True)

@@ -122,6 +122,15 @@ int fo_align_batch(int64_t n, const uint8_t *seq4, const int64_t *seq_off, const
                    const fo_params *p, fo_read_result *res, uint32_t *ops_out, int ops_cap,
                    int n_threads);
 
+/* AVX2 inter-sequence implementation of the same contract (fade_oracle_simd.c): the CPU baseline
+ * of bench.py.  Falls back to fo_align_batch on CPUs without AVX2. */
+int fo_align_batch_simd(int64_t n, const uint8_t *seq4, const int64_t *seq_off, const int32_t *l_qseq,
+                        const int32_t *tid, const int64_t *pos, const int32_t *aligned_len,
+                        const int32_t *clip_left, const int32_t *clip_right,
+                        int n_contigs, const char *const *contigs, const int64_t *contig_len,
+                        const fo_params *p, fo_read_result *res, uint32_t *ops_out, int ops_cap,
+                        int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,7 +52,8 @@ _lib = None
 
 def build(force: bool = False) -> str:
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(
-            os.path.join(_HERE, "fade_oracle.c")):
+            os.path.join(_HERE, "fade_oracle.c")) or os.path.getmtime(_SO) < os.path.getmtime(
+            os.path.join(_HERE, "fade_oracle_simd.c")):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
@@ -82,6 +83,8 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_char_p),
                                      C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.fo_align_batch.restype = C.c_int
+        L.fo_align_batch_simd.argtypes = L.fo_align_batch.argtypes
+        L.fo_align_batch_simd.restype = C.c_int
         _lib = L
     return _lib
 
@@ -218,7 +221,7 @@ def annotate_record(*, is_mapped: bool, has_sa: bool, cigar, seq4, qual, l_qseq:
 
 
 def align_batch(seq4, seq_off, l_qseq, tid, pos, aligned_len, clip_left, clip_right, contigs: list[bytes],
-                params: Params | None = None, ops_cap: int = 32, n_threads: int = 0):
+                params: Params | None = None, ops_cap: int = 32, n_threads: int = 0, simd: bool = False):
     """fo_align_read over struct-of-arrays inputs; returns (structured results array, ops[n, ops_cap])."""
     p = params or default_params()
     n = len(l_qseq)
@@ -234,7 +237,8 @@ def align_batch(seq4, seq_off, l_qseq, tid, pos, aligned_len, clip_left, clip_ri
     clen = np.array([len(c) for c in contigs], dtype=np.int64)
     res = (ReadResult * n)()
     ops = np.zeros((n, ops_cap), dtype=np.uint32)
-    rc = lib().fo_align_batch(n, seq4.ctypes.data, seq_off.ctypes.data, l_qseq.ctypes.data, tid.ctypes.data,
+    fn = lib().fo_align_batch_simd if simd else lib().fo_align_batch
+    rc = fn(n, seq4.ctypes.data, seq_off.ctypes.data, l_qseq.ctypes.data, tid.ctypes.data,
                               pos.ctypes.data, aligned_len.ctypes.data, clip_left.ctypes.data,
                               clip_right.ctypes.data, len(contigs), names, clen.ctypes.data, C.byref(p),
                               C.addressof(res), ops.ctypes.data, ops_cap, n_threads)

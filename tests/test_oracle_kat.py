@@ -141,3 +141,37 @@ def test_golden_fixture_c1_head():
         got.append(orc.cigar_string(ops[k, : res["n_ops"][k]]))
         got.append(int(res["win_start"][k]))
         assert got == e, (int(k), got, e)
+
+
+def test_simd_cpu_baseline_equals_scalar_oracle():
+    """oracle/fade_oracle_simd.c (the AVX2 CPU baseline timed by bench.py) must reproduce the scalar
+    oracle bit for bit: simulated reads, ragged lengths / contig ends, wildcard letters, other flags."""
+    import random as _random
+
+    import readsets
+    from fade_b200 import sim
+
+    def same(rd, contigs, prm):
+        a, oa = orc.align_batch(rd.seq4, rd.seq_off, rd.l_qseq, rd.tid, rd.pos, rd.aligned_len, rd.clip_left,
+                                rd.clip_right, contigs, params=prm)
+        b, ob = orc.align_batch(rd.seq4, rd.seq_off, rd.l_qseq, rd.tid, rd.pos, rd.aligned_len, rd.clip_left,
+                                rd.clip_right, contigs, params=prm, simd=True, n_threads=3)
+        for f in a.dtype.names:
+            assert np.array_equal(a[f], b[f]), f
+        k = np.minimum(a["n_ops"], 32)
+        m = np.arange(32)[None, :] < k[:, None]
+        assert np.array_equal(np.where(m, oa, 0), np.where(m, ob, 0))
+        return int(a["aligned"].sum())
+
+    names, contigs, cfg, _ = sim.config_c1()
+    rd = sim.make_reads(cfg, 0, 3000, contigs)
+    assert same(rd, [c.tobytes() for c in contigs], orc.default_params()) > 300
+    assert same(rd, [c.tobytes() for c in contigs], orc.default_params(min_length=20, window_size=40)) > 50
+    rng = _random.Random(21)
+    base = bytearray(readsets.random_ref(rng, 5000))
+    for _ in range(30):
+        base[rng.randrange(len(base))] = ord(rng.choice("RYKMNn"))
+    cs = [bytes(base), readsets.random_ref(rng, 400)]
+    rs = readsets.build(readsets.ragged_reads(rng, cs, 1200, wild_read_rate=0.002, alpha="ACGTN"))
+    assert same(rs, cs, orc.default_params()) > 200
+    assert same(rs, cs, orc.default_params(gap_open=12, gap_extend=3, match=9, mismatch=-9)) > 200
