@@ -1,0 +1,63 @@
+"""`fade-b200 annotate` (C++ host driver over the C ABI, mirror of source/anno.d:16-52) on SAM text:
+every record's rs / am / as / ar / ab equal the oracle's annotateTask, the other fields and tags are
+untouched, and the @PG line of anno.d:25-32 is appended."""
+import os
+import subprocess
+
+import pytest
+
+import samio
+from fade_b200 import sim
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "fade_b200", "bin", "fade-b200")
+
+
+@pytest.mark.parametrize("extra,min_length,window", [([], 5, 300), (["--min-length", "12", "-w", "100", "--batch", "700"], 12, 100)])
+def test_cli_annotate_matches_oracle(tmp_path, extra, min_length, window):
+    names, contigs, cfg, _ = sim.config_c1()
+    contigs = [contigs[0][:300_000]]
+    rd = sim.make_reads(cfg, 0, 3000, contigs)
+    fa, sam, out = tmp_path / "ref.fa", tmp_path / "in.sam", tmp_path / "out.sam"
+    samio.write_fasta(fa, names, contigs)
+    samio.write_sam(sam, names, contigs, rd)
+    with open(out, "w") as fo:
+        p = subprocess.run([BIN, "annotate", *extra, str(sam), str(fa)], stdout=fo, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    header, recs = samio.read_sam_tags(out)
+    assert header[-1].startswith("@PG\tID:fade-annotate\tPN:fade\tVN:") and "\tPP:simulator\t" in header[-1]
+    assert "CL:" in header[-1] and len(recs) == rd.n
+    prm = orc.default_params(min_length=min_length, window_size=window)
+    L = rd.read_len
+    stride = (L + 1) // 2
+    refb = contigs[0].tobytes()
+    n_art = 0
+    for k in range(rd.n):
+        fields, tags = recs[f"r{k}"]
+        exp = orc.annotate_record(is_mapped=not (rd.flag[k] & 4), has_sa=bool(rd.has_sa[k]),
+                                  cigar=rd.cigar[k, : rd.n_cigar[k]], seq4=rd.seq4[k * stride:(k + 1) * stride],
+                                  qual=rd.qual[k * L:(k + 1) * L], l_qseq=L, pos=int(rd.pos[k]), contig_name=names[0],
+                                  ref_seq=refb, params=prm)
+        got = {t: tags[t] for t in ("rs", "am", "as", "ar", "ab") if t in tags}
+        assert got == exp, (k, got, exp)
+        assert tags["NM"] == 0 and fields[3] == str(int(rd.pos[k]) + 1)
+        n_art += "am" in exp
+    assert n_art > 50
+
+
+def test_cli_reannotation_replaces_old_tags(tmp_path):
+    names, contigs, cfg, _ = sim.config_c1()
+    contigs = [contigs[0][:200_000]]
+    rd = sim.make_reads(cfg, 0, 800, contigs)
+    fa, sam, o1, o2 = tmp_path / "ref.fa", tmp_path / "in.sam", tmp_path / "o1.sam", tmp_path / "o2.sam"
+    samio.write_fasta(fa, names, contigs)
+    samio.write_sam(sam, names, contigs, rd)
+    for src, dst in ((sam, o1), (o1, o2)):
+        with open(dst, "w") as fo:
+            assert subprocess.run([BIN, "annotate", str(src), str(fa)], stdout=fo, stderr=subprocess.DEVNULL).returncode == 0
+    _, a = samio.read_sam_tags(o1)
+    h2, b = samio.read_sam_tags(o2)
+    assert {k: v[1] for k, v in a.items()} == {k: v[1] for k, v in b.items()}
+    assert h2[-1].split("\t")[1:4:2] == ["ID:fade-annotate", "VN:fade-b200-0.1"] and "PP:fade-annotate" in h2[-1]
