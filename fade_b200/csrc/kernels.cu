@@ -691,7 +691,7 @@ static cudaError_t launch_trace_tt(KernelArgs a, cudaStream_t s, int sm_count, i
     int grid = std::min((n + 127) / 128, sm_count * 8);
     trace_init_kernel<R><<<grid, 128, 0, s>>>(a);
     int nl = 1;
-    constexpr int FULL_ROUNDS = 7;   // covers paths up to ~6 blocks; the rest goes to the tail kernel
+    constexpr int FULL_ROUNDS = 10;  // covers paths up to ~9 blocks (any 2x250 read); the rest goes to the tail kernel
     const int quads = (n + 7) / 8;
     int r = 0;
     for (; r < a.max_rounds && r < FULL_ROUNDS; ++r) {
