@@ -13,6 +13,7 @@ MAX_OPS = 32
 R_ALIGNED, R_ART_LEFT, R_ART_RIGHT, R_OPS_TRUNC, R_GENERIC = 1, 2, 4, 8, 16
 F_FORCE_GENERIC = 1
 F_NO_SCATTER = 2
+F_NO_SHORTCUT = 8
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_query", "<i4"), ("end_ref", "<i4"), ("beg_query", "<i4"),
                          ("beg_ref", "<i4"), ("n_ops", "<i4"), ("flags", "<u4"), ("read", "<i4"),
                          ("ops", "<u4", (32,))])

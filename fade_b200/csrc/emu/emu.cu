@@ -97,7 +97,7 @@ int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
     ctl_init(ctl[1], qlen_b, tlen_b);
     constexpr int RW = trace_words<R>();
     std::vector<uint32_t> tr((size_t)tile_words<R>());
-    const bool tg = tagged && k.tagged_ok;
+    const bool tg = (tagged & 1) && k.tagged_ok;
     int guard = 0;
     while (ctl[0].phase != 2 || ctl[1].phase != 2) {
         if (++guard > 4 * nblk + 16) return -2;
@@ -179,7 +179,8 @@ extern "C" int fadeemu_align_pair(int R, const uint8_t *qa, int qlen_a, const ui
                                   int tagged, int min_length, const uint32_t *clips /*[4]: la ra lb rb*/,
                                   AlnOut *out_a, AlnOut *out_b)
 {
-    const SwConsts k = make_consts(open, extend, match, mismatch);
+    SwConsts k = make_consts(open, extend, match, mismatch);
+    k.shortcut = (tagged & 2) ? 0 : 1;   // bit 1 of `tagged`: disable the ungapped-diagonal shortcut
 #define CASE(RR)                                                                                   \
     case RR:                                                                                       \
         return align_pair<RR>(qa, qlen_a, ta, tlen_a, qb, qlen_b, tb, tlen_b, k, extra_blocks,    \

@@ -362,6 +362,7 @@ int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
         c->host_threads = c->p.host_threads > 0 ? std::min(c->p.host_threads, 4 * hw) : hw;
     }
     c->k = make_consts(pp.gap_open, pp.gap_extend, pp.match, pp.mismatch);
+    if (pp.flags & FADEGPU_F_NO_SHORTCUT) c->k.shortcut = 0;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_cursor, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&c->d_alu, 64)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||

@@ -362,6 +362,7 @@ __device__ __forceinline__ void advance_round(const KernelArgs &a, int round, un
                 if (cur != 0) { if (l == 0) c.ring[nrev % OPS_CAP] = cur; ++nrev; }
                 cur = ((uint32_t)n << 4) | op;
             };
+            int forced = 0;   // > 0: the next `forced` steps are DIAG by the ungapped-diagonal proof
             for (;;) {
                 if (i < 0 || j < 0) { done = true; break; }
                 if (mode == 0 && hval <= 0) { done = true; break; }   // ZERO
@@ -375,12 +376,13 @@ __device__ __forceinline__ void advance_round(const KernelArgs &a, int round, un
                     uint32_t nib = 0;
                     int sc = 0;
                     bool eq = false;
-                    if (inblk) {
-                        nib = (tile[tile_index<R>(t % FBLK, g, r >> 2)] >> (sh + 4 * (r & 3))) & 0xfu;
+                    if (valid && (inblk || forced > 0)) {
                         eq = acc.qcode(ii) == acc.tcode(jj);
                         sc = eq ? k.match : k.mismatch;
                     }
-                    const bool diag = inblk && (nib >> 2) == 2u;
+                    if (inblk && forced == 0)
+                        nib = (tile[tile_index<R>(t % FBLK, g, r >> 2)] >> (sh + 4 * (r & 3))) & 0xfu;
+                    const bool diag = forced > 0 ? (valid && l < forced) : (inblk && (nib >> 2) == 2u);
                     if (!diag) sc = 0;
                     int pre = sc;                       // inclusive prefix sum over lanes
 #pragma unroll
@@ -407,10 +409,43 @@ __device__ __forceinline__ void advance_round(const KernelArgs &a, int round, un
                         const int hlast = __shfl_sync(FULL, hv - sc, L - 1);
                         hval = hlast;
                         i -= L; j -= L;
+                        if (forced > 0) forced -= L;
                         continue;
                     }
                     // lane 0's own cell is not a diagonal step
                     if (!__shfl_sync(FULL, (int)inblk, 0)) {
+                        // Out of the replayed block in state H with the exact H known: try the ungapped-
+                        // diagonal proof (see ctl_advance in sw_core.cuh) before asking for a replay.
+                        bool proven = false;
+                        int steps = 0;
+                        if (k.shortcut) {
+                            int rem = hval, pi = i, pj = j;
+                            for (;;) {
+                                const int qi = pi - l, qj = pj - l;
+                                const bool v2 = qi >= 0 && qj >= 0;
+                                int s2 = 0;
+                                if (v2) s2 = acc.qcode(qi) == acc.tcode(qj) ? k.match : k.mismatch;
+                                int p2 = s2;
+#pragma unroll
+                                for (int o = 1; o < 32; o <<= 1) {
+                                    const int v = __shfl_up_sync(FULL, p2, o);
+                                    if (l >= o) p2 += v;
+                                }
+                                const int rl = rem - p2;     // remainder after this lane's step
+                                const unsigned hit = __ballot_sync(FULL, v2 && rl <= 0);
+                                const unsigned inv = __ballot_sync(FULL, !v2);
+                                const int fh = hit ? __ffs(hit) - 1 : 32, fi = inv ? __ffs(inv) - 1 : 32;
+                                if (fh < fi) {
+                                    proven = __shfl_sync(FULL, rl, fh) == 0;
+                                    steps += fh + 1;
+                                    break;
+                                }
+                                if (fi < 32) break;          // the diagonal leaves the matrix: nothing proven
+                                rem = __shfl_sync(FULL, rl, 31);
+                                steps += 32; pi -= 32; pj -= 32;
+                            }
+                        }
+                        if (proven) { forced = steps; continue; }
                         const int g0 = i / R;
                         need = (j + g0) / FBLK;
                         break;

@@ -45,6 +45,7 @@ struct SwConsts {
     uint32_t neg_e16_e;         // packed -16*extend + 1 (E extension tag)
     uint32_t neg_e16_f;         // packed -16*extend + 2 (F extension tag)
     int32_t tagged_ok;          // scoring fits the tagged encoding
+    int32_t shortcut;           // traceback may use the ungapped-diagonal proof instead of a replay
 };
 
 FD SwConsts make_consts(int open, int extend, int match, int mismatch)
@@ -67,6 +68,7 @@ FD SwConsts make_consts(int open, int extend, int match, int mismatch)
     k.neg_o16 = o16 | (o16 << 16);
     k.neg_e16_e = ee | (ee << 16);
     k.neg_e16_f = ef | (ef << 16);
+    k.shortcut = 1;
     return k;
 }
 
@@ -428,7 +430,31 @@ FD void ctl_advance(LaneCtl &c, const uint32_t *tile, int lane, const Acc &acc, 
         const int g = i / R, r = i - g * R;
         const int t = j + g;
         const int blk = t / FBLK, u = t % FBLK;
-        if (blk != cur_blk) { need = blk; break; }
+        if (blk != cur_blk) {
+            // Ungapped-diagonal proof (no replay needed): we are in state H at a cell whose exact value
+            // hval is known.  Any ungapped alignment of k steps ending here scores at most hval, so the
+            // remainder R_k = hval - sum of the k step scores is never negative; if it reaches exactly 0,
+            // H == Hdiag + s holds at every cell on the way (induction over H >= Hdiag + s and
+            // H >= R), DIAG has priority in the traceback (P4), and the cell after the last step holds
+            // 0 (ZERO).  So the remaining path IS this diagonal.  If the diagonal leaves the matrix
+            // first, nothing is proven and the block is replayed.
+            if (mode == 0 && k.shortcut) {
+                int rem = hval, steps = 0;
+                bool proven = false;
+                for (int ii = i, jj = j; ii >= 0 && jj >= 0; --ii, --jj) {
+                    rem -= acc.qcode(ii) == acc.tcode(jj) ? k.match : k.mismatch;
+                    ++steps;
+                    if (rem <= 0) { proven = rem == 0; break; }
+                }
+                if (proven) {
+                    for (int m = 0; m < steps; ++m) push(acc.qcode(i - m) == acc.tcode(j - m) ? OP_EQ : OP_X);
+                    i -= steps; j -= steps; hval = 0;
+                    continue;
+                }
+            }
+            need = blk;
+            break;
+        }
         const uint32_t nib = (tile[tile_index<R>(u, g, r >> 2)] >> (16 * lane + 4 * (r & 3))) & 0xfu;
         if (mode == 0) {
             const uint32_t src = nib >> 2;

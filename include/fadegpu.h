@@ -64,6 +64,8 @@ typedef struct fadegpu_params {
 
 /* params.flags */
 #define FADEGPU_F_FORCE_GENERIC 1u /* route every alignment through the generic (slow) kernel */
+#define FADEGPU_F_NO_SHORTCUT 8u   /* traceback: always replay blocks, never use the ungapped-diagonal proof
+                                      (A/B switch; results are identical) */
 #define FADEGPU_F_NO_SCATTER 2u    /* fadegpu_wait fills only flags[] and the compact results
                                       (fadegpu_get_results), not the other per-read output arrays */
 

@@ -58,12 +58,12 @@ def got(x):
             [x.ops[k] for k in range(min(x.n_ops, 32))])
 
 
-@pytest.mark.parametrize("tagged", [1, 0])
+@pytest.mark.parametrize("tagged", [1, 0, 3, 2])   # bit 0: tagged trace, bit 1: no diagonal shortcut
 @pytest.mark.parametrize("R,maxq,maxt,iters", [(1, 8, 40, 300), (2, 16, 90, 300), (3, 24, 120, 200),
                                                (5, 40, 200, 120), (13, 104, 300, 40), (19, 152, 400, 40),
                                                (32, 256, 500, 12)])
 def test_group_emulation_matches_oracle(R, maxq, maxt, iters, tagged):
-    rng = random.Random(1000 * R + tagged)
+    rng = random.Random(1000 * R + (tagged & 1))
     for _ in range(iters):
         qa, ta = case(rng, maxq, maxt)
         qb, tb = case(rng, maxq, maxt)
@@ -72,8 +72,10 @@ def test_group_emulation_matches_oracle(R, maxq, maxt, iters, tagged):
         assert got(xb) == expect(qb, tb), (R, qb, tb)
 
 
-def test_long_gaps_and_long_alignments():
-    """gap runs longer than one checkpoint block and full-length alignments across many blocks."""
+@pytest.mark.parametrize("tagged", [1, 3])
+def test_long_gaps_and_long_alignments(tagged):
+    """gap runs longer than one checkpoint block and full-length alignments across many blocks,
+    with and without the ungapped-diagonal shortcut of the traceback."""
     rng = random.Random(5)
     for _ in range(30):
         core = rnd(rng, 150)
@@ -81,7 +83,7 @@ def test_long_gaps_and_long_alignments():
         cut = rng.randint(40, 110)
         t = rnd(rng, rng.randint(0, 200)) + core[:cut] + rnd(rng, gap) + core[cut:] + rnd(rng, rng.randint(0, 200))
         q2 = core[:cut] + core[cut + rng.randint(1, 30):]      # deletion from the query side
-        xa, xb = E.align_pair(19, core, t, q2 or "A", t)
+        xa, xb = E.align_pair(19, core, t, q2 or "A", t, tagged=tagged)
         assert got(xa) == expect(core, t)
         assert got(xb) == expect(q2 or "A", t)
 
@@ -117,3 +119,28 @@ def test_prmt_emulation_matches_ptx_semantics():
     assert L.fadeemu_prmt(0xFDFDFD02, 0xFDFDFDFD, 0x8091) == 0x0002FFFD      # lane a mismatch (-3)
     for nib, code in {1: 2, 2: 3, 4: 1, 8: 0, 15: 4, 0: 5, 3: 5, 5: 5}.items():
         assert L.fadeemu_comp_code_of_nt16(nib) == code
+
+
+@pytest.mark.parametrize("tagged", [1, 3])
+def test_diagonal_shortcut_edge_cases(tagged):
+    """paths that start exactly at query row 0 / target column 0, long mismatch-rich diagonals and
+    competing gapped alternatives: the proof-based shortcut must agree with the replayed traceback."""
+    rng = random.Random(77)
+    for _ in range(150):
+        n = rng.randint(40, 150)
+        core = rnd(rng, n)
+        noisy = "".join(c if rng.random() > 0.08 else rng.choice("ACGT") for c in core)
+        kind = rng.randrange(4)
+        if kind == 0:      # alignment begins at target column 0 and query row 0
+            q, t = noisy, core + rnd(rng, rng.randint(0, 150))
+        elif kind == 1:    # begins at target column 0, query has a prefix
+            q, t = rnd(rng, rng.randint(1, 40))[: 152 - n] + noisy, core + rnd(rng, rng.randint(0, 100))
+        elif kind == 2:    # begins at query row 0 deep inside the target
+            q, t = noisy, rnd(rng, rng.randint(33, 300)) + core + rnd(rng, rng.randint(0, 60))
+        else:              # a gap in the middle: the diagonal proof must fail and the replay take over
+            cut = rng.randint(15, n - 15)
+            q, t = noisy, rnd(rng, rng.randint(0, 200)) + core[:cut] + rnd(rng, rng.randint(1, 6)) + core[cut:]
+        q = q[:152]
+        xa, xb = E.align_pair(19, q, t, q[::-1], t, tagged=tagged, extra_blocks=rng.randint(0, 1))
+        assert got(xa) == expect(q, t), (q, t)
+        assert got(xb) == expect(q[::-1], t)

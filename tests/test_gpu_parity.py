@@ -236,3 +236,20 @@ def test_compact_results_and_no_scatter():
         o1, o2 = np.argsort(ref_rec["read"]), np.argsort(rec2["read"])
         assert np.array_equal(ref_rec[o1], rec2[o2])
         b.close()
+
+
+def test_no_shortcut_flag_gives_identical_results():
+    """the ungapped-diagonal proof of the traceback is an optimisation only: with it disabled every
+    block on the path is replayed and the records must be identical."""
+    names, contigs, cfg, n = sim.config_c1()
+    rd = sim.make_reads(cfg, 0, 6000, contigs)
+    recs = []
+    for fl in (0, api.F_NO_SHORTCUT):
+        with _ctx(flags=fl) as ctx:
+            ctx.load_reference(names, [c.tobytes() for c in contigs])
+            b = run_gpu(ctx, rd)
+            compare(b, rd, contigs, oracle_params(ctx.params))
+            rec, ws, ridx = b.results()
+            recs.append(rec[np.argsort(rec["read"])].copy())
+            b.close()
+    assert np.array_equal(recs[0], recs[1])
