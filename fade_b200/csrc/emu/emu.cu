@@ -99,6 +99,7 @@ int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
     std::vector<uint32_t> tr((size_t)tile_words<R>());
     const bool tg = (tagged & 1) && k.tagged_ok;
     int guard = 0;
+    bool first_iter = true;
     while (ctl[0].phase != 2 || ctl[1].phase != 2) {
         if (++guard > 4 * nblk + 16) return -2;
         int blk[2];
@@ -163,8 +164,11 @@ int align_pair(const uint8_t *qa, int qlen_a, const uint8_t *ta, int tlen_a,
         for (int L = 0; L < 2; ++L)
             for (int g = 0; g < FG; ++g)
                 if (scan[L][g] && !found[L][g]) return -3;  // a candidate must find its cell
-        ctl_advance<R>(ctl[0], tr.data(), 0, StagedAcc{ tw.data(), qc.data(), 0 }, k);
-        ctl_advance<R>(ctl[1], tr.data(), 1, StagedAcc{ tw.data(), qc.data(), 1 }, k);
+        // bit 2 of `tagged`: the first (scan) replay of a lane records no trace, like round 0 on the device
+        const bool so0 = (tagged & 4) && ctl[0].phase == 0 && first_iter, so1 = (tagged & 4) && ctl[1].phase == 0 && first_iter;
+        ctl_advance<R>(ctl[0], so0 ? nullptr : tr.data(), 0, StagedAcc{ tw.data(), qc.data(), 0 }, k);
+        ctl_advance<R>(ctl[1], so1 ? nullptr : tr.data(), 1, StagedAcc{ tw.data(), qc.data(), 1 }, k);
+        first_iter = false;
     }
     finalize_result(ctl[0], *out_a, 0, clipl_a, clipr_a, min_length);
     finalize_result(ctl[1], *out_b, 1, clipl_b, clipr_b, min_length);

@@ -3,6 +3,8 @@
 // emulation.  Reference semantics: source/analysis.d:34-80,98-104 + parasail rules P1-P5.
 #include "kernels.cuh"
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 namespace fade {
 
@@ -170,10 +172,14 @@ __global__ void __launch_bounds__(128) trace_init_kernel(const KernelArgs a)
     }
 }
 
-template <int R, bool TAGGED>
+// MODE 0: tagged trace recording, 1: plain trace recording, 2: scan only (round 0: find the end cell,
+// no trace tile; the traceback then tries the ungapped-diagonal proof before asking for a traced replay)
+template <int R, int MODE>
 __device__ __forceinline__ void replay_round(const KernelArgs &a, int round, unsigned warp0, unsigned nwarps,
                                              uint16_t (*tws_all)[40])
 {
+    constexpr bool TAGGED = MODE == 0;
+    constexpr bool SCAN_ONLY = MODE == 2;
     constexpr int RW = trace_words<R>();
     constexpr int CW = ck_words<R>();
     constexpr int MUL = TAGGED ? 16 : 1;
@@ -260,14 +266,19 @@ __device__ __forceinline__ void replay_round(const KernelArgs &a, int round, uns
             uint32_t fin = __shfl_up_sync(FULL, fout, 1, FG);
             if (g == 0) { hu = 0u; fin = e_init; }
             const uint32_t ts = twp[u];
-            uint32_t cmax = 0u, trw[RW];
-            if (TAGGED) trace_step_tagged<R>(H, E, qs, ts, hu_prev, fin, fout, k, trw, cmax);
-            else trace_step_plain<R>(H, E, qs, ts, hu_prev, fin, fout, k, trw, cmax);
-            hu_prev = hu;
-            if (store) {
+            uint32_t cmax = 0u;
+            if (SCAN_ONLY) {
+                fill_step<R>(H, E, qs, cmax, ts, hu_prev, fin, fout, k);
+            } else {
+                uint32_t trw[RW];
+                if (TAGGED) trace_step_tagged<R>(H, E, qs, ts, hu_prev, fin, fout, k, trw, cmax);
+                else trace_step_plain<R>(H, E, qs, ts, hu_prev, fin, fout, k, trw, cmax);
+                if (store) {
 #pragma unroll
-                for (int w = 0; w < RW; ++w) tile[tile_index<R>(u, g, w)] = trw[w];
+                    for (int w = 0; w < RW; ++w) tile[tile_index<R>(u, g, w)] = trw[w];
+                }
             }
+            hu_prev = hu;
             if (need0 && lane_lo(cmax) == S[0]) {
                 need0 = false;
                 int fr = 0;
@@ -284,16 +295,17 @@ __device__ __forceinline__ void replay_round(const KernelArgs &a, int round, uns
                 a.state[aln[1]].fj[g] = blk[1] * FBLK + u - g;
                 a.state[aln[1]].fr[g] = fr;
             }
+            if (SCAN_ONLY && !__any_sync(FULL, need0 || need1)) break;   // every end-cell candidate found
         }
     }
 }
 
-template <int R, bool TAGGED>
+template <int R, int MODE>
 __global__ void __launch_bounds__(128) trace_replay_kernel(const KernelArgs a)
 {
     __shared__ uint16_t tws_all[16][40];
     if (blockIdx.x == 0 && threadIdx.x == 0) a.qcount[(a.round & 1) ^ 1] = 0u;   // next round's queue starts empty
-    replay_round<R, TAGGED>(a, a.round, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5),
+    replay_round<R, MODE>(a, a.round, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5),
                             gridDim.x * (blockDim.x >> 5), tws_all);
 }
 
@@ -321,6 +333,7 @@ __device__ __forceinline__ void advance_round(const KernelArgs &a, int round, un
     const unsigned long long *queue = a.queue[rin];
     const int l = threadIdx.x & 31;
     const SwConsts &k = a.k;
+    const bool tile_valid = !(round == 0 && k.shortcut);   // round 0 only scans for the end cell
     for (unsigned idx = warp0; idx < cnt; idx += nwarps) {
         const int aln = (int)(uint32_t)(queue[idx] & 0xffffffffu);
         const AlnDesc d = a.aln[aln];
@@ -372,7 +385,7 @@ __device__ __forceinline__ void advance_round(const KernelArgs &a, int round, un
                     const bool valid = ii >= 0 && jj >= 0;
                     const int g = valid ? ii / R : 0, r = valid ? ii - g * R : 0;
                     const int t = jj + g;
-                    const bool inblk = valid && (t / FBLK) == cur_blk;
+                    const bool inblk = valid && tile_valid && (t / FBLK) == cur_blk;
                     uint32_t nib = 0;
                     int sc = 0;
                     bool eq = false;
@@ -456,7 +469,7 @@ __device__ __forceinline__ void advance_round(const KernelArgs &a, int round, un
                 } else {
                     const int g = i / R, r = i - g * R;
                     const int t = j + g;
-                    if (t / FBLK != cur_blk) { need = t / FBLK; break; }
+                    if (t / FBLK != cur_blk || !tile_valid) { need = t / FBLK; break; }
                     const uint32_t nib = (tile[tile_index<R>(t % FBLK, g, r >> 2)] >> (sh + 4 * (r & 3))) & 0xfu;
                     if (mode == 1) {
                         if (!(nib & 2u)) { hval = gval + k.open; mode = 0; }
@@ -515,7 +528,7 @@ __global__ void __launch_bounds__(128) trace_tail_kernel(const KernelArgs a)
         __syncthreads();
         if (threadIdx.x == 0) a.qcount[(r & 1) ^ 1] = 0u;
         __syncthreads();
-        replay_round<R, TAGGED>(a, r, threadIdx.x >> 5, blockDim.x >> 5, tws_all);
+        replay_round<R, TAGGED ? 0 : 1>(a, r, threadIdx.x >> 5, blockDim.x >> 5, tws_all);
         __threadfence_block();
         __syncthreads();
         advance_round<R>(a, r, threadIdx.x >> 5, blockDim.x >> 5, adv);
@@ -734,7 +747,14 @@ static cudaError_t launch_trace_tt(KernelArgs a, cudaStream_t s, int sm_count, i
         // the queue shrinks quickly: smaller grid-stride grids for the later rounds
         const int g1 = std::min((quads + 3) / 4, r < 3 ? sm_count * 4 : sm_count);
         const int g2 = std::min((n + 3) / 4, r < 3 ? sm_count * 16 : sm_count * 2);   // a warp per request
-        trace_replay_kernel<R, TAGGED><<<std::max(g1, 1), 128, 0, s>>>(a);
+        if (getenv("FADEGPU_DEBUG_ROUNDS")) {   // development aid: requests per round (synchronising!)
+            unsigned int qc[2] = { 0, 0 };
+            cudaStreamSynchronize(s);
+            cudaMemcpy(qc, a.qcount, sizeof(qc), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[fadegpu] round %d: %u requests (n_aln %d)\n", r, qc[r & 1], n);
+        }
+        if (r == 0 && a.k.shortcut) trace_replay_kernel<R, 2><<<std::max(g1, 1), 128, 0, s>>>(a);
+        else trace_replay_kernel<R, TAGGED ? 0 : 1><<<std::max(g1, 1), 128, 0, s>>>(a);
         trace_advance_kernel<R><<<std::max(g2, 1), 128, 0, s>>>(a);
         nl += 2;
     }

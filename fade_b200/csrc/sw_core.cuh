@@ -430,7 +430,7 @@ FD void ctl_advance(LaneCtl &c, const uint32_t *tile, int lane, const Acc &acc, 
         const int g = i / R, r = i - g * R;
         const int t = j + g;
         const int blk = t / FBLK, u = t % FBLK;
-        if (blk != cur_blk) {
+        if (blk != cur_blk || tile == nullptr) {   // tile == nullptr: the block was only scanned, not traced
             // Ungapped-diagonal proof (no replay needed): we are in state H at a cell whose exact value
             // hval is known.  Any ungapped alignment of k steps ending here scores at most hval, so the
             // remainder R_k = hval - sum of the k step scores is never negative; if it reaches exactly 0,

@@ -58,7 +58,7 @@ def got(x):
             [x.ops[k] for k in range(min(x.n_ops, 32))])
 
 
-@pytest.mark.parametrize("tagged", [1, 0, 3, 2])   # bit 0: tagged trace, bit 1: no diagonal shortcut
+@pytest.mark.parametrize("tagged", [1, 0, 3, 2, 5])   # bit 0: tagged trace, 1: no diagonal shortcut, 2: scan-only first replay
 @pytest.mark.parametrize("R,maxq,maxt,iters", [(1, 8, 40, 300), (2, 16, 90, 300), (3, 24, 120, 200),
                                                (5, 40, 200, 120), (13, 104, 300, 40), (19, 152, 400, 40),
                                                (32, 256, 500, 12)])
@@ -72,7 +72,7 @@ def test_group_emulation_matches_oracle(R, maxq, maxt, iters, tagged):
         assert got(xb) == expect(qb, tb), (R, qb, tb)
 
 
-@pytest.mark.parametrize("tagged", [1, 3])
+@pytest.mark.parametrize("tagged", [1, 3, 5])
 def test_long_gaps_and_long_alignments(tagged):
     """gap runs longer than one checkpoint block and full-length alignments across many blocks,
     with and without the ungapped-diagonal shortcut of the traceback."""
@@ -121,7 +121,7 @@ def test_prmt_emulation_matches_ptx_semantics():
         assert L.fadeemu_comp_code_of_nt16(nib) == code
 
 
-@pytest.mark.parametrize("tagged", [1, 3])
+@pytest.mark.parametrize("tagged", [1, 3, 5])
 def test_diagonal_shortcut_edge_cases(tagged):
     """paths that start exactly at query row 0 / target column 0, long mismatch-rich diagonals and
     competing gapped alternatives: the proof-based shortcut must agree with the replayed traceback."""
