@@ -364,8 +364,13 @@ def main():
                     "host_ms_last_chunks": {kx: round(v, 3) for kx, v in host_ms.items()}},
             "gpu_launches": agg["launches"] * args.steps,
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "GCUPS",
-                         "frac": achieved / peak if peak > 0 else None, "traffic": None,
-                         "kernel": "sw_fill_kernel<19> + sw_trace_kernel<19> (whole path)",
+                         "frac": achieved / peak if peak > 0 else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (sw_fill_kernel<19>)
+                         # per launch, from the ncu --set full capture of a 1 M-read chunk of this workload
+                         # (profiles/r01_prof_fill_final_raw.csv); only meaningful for the default configuration
+                         "traffic": 2.398e9 if (args.workload == "c2" and chunk == 1_000_000) else None,
+                         "kernel": "dominant: sw_fill_kernel<19> (80 % of the path); achieved = cells / time of ALL "
+                                   "kernels of the path (fill + traceback rounds + generic)",
                          "fill_only_gcups": fill_gcups,
                          "fill_ms": k_fill / args.steps, "trace_ms": k_trace / args.steps,
                          "generic_ms": k_gen / args.steps,
