@@ -190,7 +190,7 @@ extern "C" int fadeemu_align_pair(int R, const uint8_t *qa, int qlen_a, const ui
         return align_pair<RR>(qa, qlen_a, ta, tlen_a, qb, qlen_b, tb, tlen_b, k, extra_blocks,    \
                               tagged, min_length, clips[0], clips[1], clips[2], clips[3], out_a, out_b);
     switch (R) {
-        CASE(1) CASE(2) CASE(3) CASE(5) CASE(13) CASE(19) CASE(32)
+        CASE(1) CASE(2) CASE(3) CASE(5) CASE(13) CASE(19) CASE(25) CASE(32) CASE(38)
     default: return -10;
     }
 #undef CASE

@@ -142,15 +142,19 @@ RefDev ref_dev(const fadegpu_ctx *c)
     return r;
 }
 
-int cls_rank(int cls) { return cls == 13 ? 0 : cls == 19 ? 1 : cls == 32 ? 2 : 3; }
+// rank of a row class inside ROW_CLASSES; N_ROW_CLASSES = the generic list
+int cls_rank(int cls)
+{
+    for (int k = 0; k < N_ROW_CLASSES; ++k) if (ROW_CLASSES[k] == cls) return k;
+    return N_ROW_CLASSES;
+}
 
 int class_of(const fadegpu_ctx *c, int qlen, int tlen)
 {
     if (c->p.flags & FADEGPU_F_FORCE_GENERIC) return 0;
     if (qlen > QMAX_FAST || tlen > TMAX_FAST) return 0;
-    if (qlen <= FG * 13) return 13;
-    if (qlen <= FG * 19) return 19;
-    return 32;
+    for (int k = 0; k < N_ROW_CLASSES; ++k) if (qlen <= FG * ROW_CLASSES[k]) return ROW_CLASSES[k];
+    return 0;
 }
 
 size_t ck_words_of(int R) { return (size_t)(2 * R + 2); }
@@ -623,7 +627,7 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
             const int cls = class_of(c, ql, tlen);
             const int rk = cls_rank(cls);
             // key = class rank (13, 19, 32, generic) then descending window length (generic: input order)
-            const int key = rk * (TMAX_FAST + 2) + (rk == 3 ? 0 : TMAX_FAST - tlen);
+            const int key = rk * (TMAX_FAST + 2) + (rk == N_ROW_CLASSES ? 0 : TMAX_FAST - tlen);
             loc.push_back(AlnTmp{ start, so, (int32_t)r, tlen, cls, ql, tid, key, cl, cr });
             cells += (int64_t)ql * tlen;
         }
@@ -649,14 +653,14 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
         }
     }
     // counting sort of the INDICES (stable: equal keys keep read order)
-    const int KEYS = 4 * (TMAX_FAST + 2);
+    const int KEYS = (N_ROW_CLASSES + 1) * (TMAX_FAST + 2);
     std::vector<int32_t> &cnt = b->cnt;
     cnt.assign((size_t)KEYS + 1, 0);
     for (const AlnTmp &a : all) ++cnt[(size_t)a.key + 1];
     for (int kx = 0; kx < KEYS; ++kx) cnt[(size_t)kx + 1] += cnt[(size_t)kx];
-    int64_t cls_first[5];
-    for (int rk = 0; rk < 4; ++rk) cls_first[rk] = cnt[(size_t)rk * (TMAX_FAST + 2)];
-    cls_first[4] = n_aln;
+    int64_t cls_first[N_ROW_CLASSES + 2];
+    for (int rk = 0; rk <= N_ROW_CLASSES; ++rk) cls_first[rk] = cnt[(size_t)rk * (TMAX_FAST + 2)];
+    cls_first[N_ROW_CLASSES + 1] = n_aln;
     for (int64_t kx = 0; kx < n_aln; ++kx) order[(size_t)cnt[(size_t)all[(size_t)kx].key]++] = (uint32_t)kx;
 
     b->st.host_sort_ms = ms_since(t_sort);
@@ -702,11 +706,11 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
 
     b->st.host_gather_ms = ms_since(t_gather);
     // ---- 4. launch plan ----
-    static const int CLS[4] = { 13, 19, 32, 0 };
+
     int64_t n_items = 0;
     size_t ck_needed = 0, gen_needed = 0, trace_needed = 0;
-    for (int rk = 0; rk < 4; ++rk) {
-        const int R = CLS[rk];
+    for (int rk = 0; rk <= N_ROW_CLASSES; ++rk) {
+        const int R = rk < N_ROW_CLASSES ? ROW_CLASSES[rk] : 0;
         const int64_t first_aln = cls_first[rk], last_aln = cls_first[rk + 1];
         if (last_aln <= first_aln) continue;
         if (R == 0) {

@@ -780,7 +780,9 @@ cudaError_t launch_fill(int R, const KernelArgs &a, cudaStream_t s)
     switch (R) {
     case 13: return launch_fill_t<13>(a, s);
     case 19: return launch_fill_t<19>(a, s);
+    case 25: return launch_fill_t<25>(a, s);
     case 32: return launch_fill_t<32>(a, s);
+    case 38: return launch_fill_t<38>(a, s);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -791,7 +793,9 @@ cudaError_t launch_trace(int R, const KernelArgs &a, cudaStream_t s, int sm_coun
     switch (R) {
     case 13: return launch_trace_t<13>(a, s, sm_count, launches);
     case 19: return launch_trace_t<19>(a, s, sm_count, launches);
+    case 25: return launch_trace_t<25>(a, s, sm_count, launches);
     case 32: return launch_trace_t<32>(a, s, sm_count, launches);
+    case 38: return launch_trace_t<38>(a, s, sm_count, launches);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -801,7 +805,9 @@ size_t trace_tile_bytes(int R)
     switch (R) {
     case 13: return (size_t)tile_words<13>() * 4;
     case 19: return (size_t)tile_words<19>() * 4;
-    default: return (size_t)tile_words<32>() * 4;
+    case 25: return (size_t)tile_words<25>() * 4;
+    case 32: return (size_t)tile_words<32>() * 4;
+    default: return (size_t)tile_words<38>() * 4;
     }
 }
 

@@ -83,7 +83,10 @@ struct GenericArgs {
 };
 
 constexpr int FILL_THREADS = 128;
-constexpr int QMAX_FAST = FG * 32;   // rows covered by the largest packed instantiation
+// row classes: R rows per thread x 8 threads cover reads of up to 104 / 152 / 200 / 256 / 304 bases
+constexpr int N_ROW_CLASSES = 5;
+constexpr int ROW_CLASSES[N_ROW_CLASSES] = { 13, 19, 25, 32, 38 };
+constexpr int QMAX_FAST = FG * 38;   // rows covered by the largest packed instantiation
 constexpr int TMAX_FAST = 4000;      // window length covered by the packed kernels
 
 size_t fill_smem_bytes(int tw_stride);

@@ -61,7 +61,7 @@ def got(x):
 @pytest.mark.parametrize("tagged", [1, 0, 3, 2, 5])   # bit 0: tagged trace, 1: no diagonal shortcut, 2: scan-only first replay
 @pytest.mark.parametrize("R,maxq,maxt,iters", [(1, 8, 40, 300), (2, 16, 90, 300), (3, 24, 120, 200),
                                                (5, 40, 200, 120), (13, 104, 300, 40), (19, 152, 400, 40),
-                                               (32, 256, 500, 12)])
+                                               (25, 200, 400, 10), (32, 256, 500, 12), (38, 304, 500, 8)])
 def test_group_emulation_matches_oracle(R, maxq, maxt, iters, tagged):
     rng = random.Random(1000 * R + (tagged & 1))
     for _ in range(iters):

@@ -48,17 +48,17 @@ def _ctx(**kw):
 
 
 def test_ragged_lengths_contig_ends_and_short_clips():
-    """query lengths 20..250 (all three packed instantiations), windows clamped at contig starts
-    and ends, clips at / below the length floor, several contigs."""
+    """query lengths 20..320 (all five packed instantiations + the generic kernel above 304),
+    windows clamped at contig starts and ends, clips at / below the length floor, several contigs."""
     rng = random.Random(11)
-    contigs = [readsets.random_ref(rng, n) for n in (5000, 1200, 700, 260)]
-    reads = readsets.ragged_reads(rng, contigs, 3000)
+    contigs = [readsets.random_ref(rng, n) for n in (5000, 1200, 700, 330)]
+    reads = readsets.ragged_reads(rng, contigs, 3000, max_len=320)
     rd = readsets.build(reads)
     with _ctx() as ctx:
         ctx.load_reference([f"c{i}" for i in range(4)], contigs)
         b = run_gpu(ctx, rd)
         n_al = compare(b, rd, contigs, oracle_params(ctx.params))
-        assert n_al > 500 and b.stats().n_generic == 0
+        assert n_al > 500 and 0 < b.stats().n_generic < 200
         b.close()
 
 
