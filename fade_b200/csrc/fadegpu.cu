@@ -644,24 +644,61 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     std::vector<uint32_t> &order = b->order;
     all.resize((size_t)n_aln);
     order.resize((size_t)n_aln);
+    // parallel, stable counting sort of the INDICES: per-thread histograms over the thread's own
+    // (read-ordered) slice, one prefix pass over (key, thread), per-thread scatter
+    const int KEYS = (N_ROW_CLASSES + 1) * (TMAX_FAST + 2);
+    std::vector<int32_t> &hist = b->cnt;
+    hist.resize((size_t)nthr * (size_t)(KEYS + 1));
+    std::vector<int64_t> toff((size_t)nthr + 1, 0);
+    std::vector<int> kmin((size_t)nthr, KEYS), kmax((size_t)nthr, -1);
+    for (int t = 0; t < nthr; ++t) toff[(size_t)t + 1] = toff[(size_t)t] + (int64_t)b->tl_aln[(size_t)t].size();
+#pragma omp parallel num_threads(nthr)
     {
-        int64_t o = 0;
-        for (int t = 0; t < nthr; ++t) {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        if (t < nthr) {
             const auto &loc = b->tl_aln[(size_t)t];
-            if (!loc.empty()) memcpy(all.data() + o, loc.data(), loc.size() * sizeof(AlnTmp));
-            o += (int64_t)loc.size();
+            int32_t *h = hist.data() + (size_t)t * (size_t)(KEYS + 1);
+            memset(h, 0, (size_t)(KEYS + 1) * sizeof(int32_t));
+            if (!loc.empty()) memcpy(all.data() + toff[(size_t)t], loc.data(), loc.size() * sizeof(AlnTmp));
+            int lo = KEYS, hi = -1;
+            for (const AlnTmp &a : loc) { ++h[a.key]; lo = std::min(lo, a.key); hi = std::max(hi, a.key); }
+            kmin[(size_t)t] = lo; kmax[(size_t)t] = hi;
         }
     }
-    // counting sort of the INDICES (stable: equal keys keep read order)
-    const int KEYS = (N_ROW_CLASSES + 1) * (TMAX_FAST + 2);
-    std::vector<int32_t> &cnt = b->cnt;
-    cnt.assign((size_t)KEYS + 1, 0);
-    for (const AlnTmp &a : all) ++cnt[(size_t)a.key + 1];
-    for (int kx = 0; kx < KEYS; ++kx) cnt[(size_t)kx + 1] += cnt[(size_t)kx];
     int64_t cls_first[N_ROW_CLASSES + 2];
-    for (int rk = 0; rk <= N_ROW_CLASSES; ++rk) cls_first[rk] = cnt[(size_t)rk * (TMAX_FAST + 2)];
-    cls_first[N_ROW_CLASSES + 1] = n_aln;
-    for (int64_t kx = 0; kx < n_aln; ++kx) order[(size_t)cnt[(size_t)all[(size_t)kx].key]++] = (uint32_t)kx;
+    {
+        int64_t run = 0;
+        int klo = KEYS, khi = -1;
+        for (int t = 0; t < nthr; ++t) { klo = std::min(klo, kmin[(size_t)t]); khi = std::max(khi, kmax[(size_t)t]); }
+        for (int rk = 0; rk <= N_ROW_CLASSES; ++rk) cls_first[rk] = -1;
+        for (int key = std::max(klo, 0); key <= khi; ++key) {
+            const int rk = key / (TMAX_FAST + 2);
+            if (cls_first[rk] < 0) cls_first[rk] = run;   // first key seen of this class
+            for (int t = 0; t < nthr; ++t) {
+                int32_t &hv = hist[(size_t)t * (size_t)(KEYS + 1) + (size_t)key];
+                const int32_t c0 = hv;
+                hv = (int32_t)run;
+                run += c0;
+            }
+        }
+        cls_first[N_ROW_CLASSES + 1] = n_aln;
+        for (int rk = N_ROW_CLASSES; rk >= 0; --rk) if (cls_first[rk] < 0) cls_first[rk] = cls_first[rk + 1];   // empty classes
+    }
+#pragma omp parallel num_threads(nthr)
+    {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        if (t < nthr) {
+            int32_t *h = hist.data() + (size_t)t * (size_t)(KEYS + 1);
+            const int64_t o0 = toff[(size_t)t], o1 = toff[(size_t)t + 1];
+            for (int64_t kx = o0; kx < o1; ++kx) order[(size_t)h[all[(size_t)kx].key]++] = (uint32_t)kx;
+        }
+    }
 
     b->st.host_sort_ms = ms_since(t_sort);
     const auto t_gather = std::chrono::steady_clock::now();
