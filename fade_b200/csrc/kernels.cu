@@ -59,7 +59,7 @@ __device__ __forceinline__ AlnDesc load_desc(const KernelArgs &a, int idx)
 // score-only wavefront with checkpoints
 // ------------------------------------------------------------------------------------------------
 template <int R>
-__global__ void __launch_bounds__(FILL_THREADS) sw_fill_kernel(const KernelArgs a)
+__global__ void __launch_bounds__(FILL_THREADS, (R <= 19 ? 5 : 1)) sw_fill_kernel(const KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
