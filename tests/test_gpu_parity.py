@@ -253,3 +253,35 @@ def test_no_shortcut_flag_gives_identical_results():
             recs.append(rec[np.argsort(rec["read"])].copy())
             b.close()
     assert np.array_equal(recs[0], recs[1])
+
+
+def test_share_reference_and_concurrent_contexts():
+    """fadegpu_share_reference (device-to-device copy of the packed reference) and two contexts
+    driven concurrently from two host threads (the C ABI's threading contract)."""
+    import threading
+    names, contigs, cfg, n = sim.config_c1()
+    rds = [sim.make_reads(cfg, k * 5000, 5000, contigs) for k in range(2)]
+    src = Context(0)
+    src.load_reference(names, [c.tobytes() for c in contigs])
+    dst = Context(0)
+    dst.share_reference_from(src)
+    assert dst.reference_info() == src.reference_info()
+    errs = []
+
+    def work(ctx, rd):
+        try:
+            for _ in range(3):
+                b = run_gpu(ctx, rd)
+                compare(b, rd, contigs, oracle_params(ctx.params))
+                b.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(c, r)) for c, r in zip((src, dst), rds)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    src.close()
+    dst.close()
+    assert not errs, errs
