@@ -622,7 +622,10 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
             if (start < 0) start = 0;
             int64_t end = in->pos[r] + (int64_t)in->aligned_len[r] + W;
             if (end > c->clen[tid]) end = c->clen[tid];
-            if (end <= start || end - start > 0x7fffffff) continue;  // empty window: nothing to align
+            if (end <= start) continue;                              // empty window: nothing to align
+            // a window this large (spliced alignment spanning megabases) would need a multi-GB trace
+            // for ONE read in the reference as well; refuse it loudly instead of running for hours
+            if (end - start > 0x7fffffff || (end - start) * (int64_t)ql > ((int64_t)1 << 31)) { bad = 2; continue; }
             const int tlen = (int)(end - start);
             const int cls = class_of(c, ql, tlen);
             const int rk = cls_rank(cls);
@@ -632,7 +635,8 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
             cells += (int64_t)ql * tlen;
         }
     }
-    if (bad) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
+    if (bad & 1) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
+    if (bad & 2) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: a read's window exceeds 2^31 DP cells (aligned_len too large)");
     b->st.cells = cells;
     b->st.host_classify_ms = ms_since(t_begin);
     const auto t_sort = std::chrono::steady_clock::now();

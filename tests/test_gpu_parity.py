@@ -285,3 +285,31 @@ def test_share_reference_and_concurrent_contexts():
     src.close()
     dst.close()
     assert not errs, errs
+
+
+def test_long_windows_use_generic_kernel_and_absurd_ones_are_refused():
+    """spliced-style records (huge aligned_len): windows beyond the packed kernels' 4000 columns go
+    to the generic kernel on the device; a window of > 2^31 DP cells is refused with an error."""
+    rng = random.Random(31)
+    contigs = [readsets.random_ref(rng, 60_000)]
+    reads = readsets.ragged_reads(rng, contigs, 40, min_len=100, max_len=150)
+    for r in reads[:20]:
+        r["aligned_len"] = rng.randint(5_000, 12_000)      # an N-spanning CIGAR
+        r["pos"] = rng.randint(0, 40_000)
+    rd = readsets.build(reads)
+    with _ctx() as ctx:
+        ctx.load_reference(["c"], contigs)
+        b = run_gpu(ctx, rd)
+        compare(b, rd, contigs, oracle_params(ctx.params))
+        assert b.stats().n_generic >= 5
+        b.close()
+    big = [bytes(40_000_000)]
+    rd2 = readsets.build([dict(seq="ACGT" * 30, tid=0, pos=100, aligned_len=39_000_000, clip_left=20, clip_right=0)])
+    with _ctx() as ctx:
+        ctx.load_reference(["z"], big)
+        b = ctx.alloc_batch(1, 64)
+        b.fill(rd2.seq4, rd2.seq_off, rd2.l_qseq, rd2.tid, rd2.pos, rd2.aligned_len, rd2.clip_left, rd2.clip_right)
+        with pytest.raises(Exception) as e:
+            b.run()
+        assert "2^31" in str(e.value)
+        b.close()
