@@ -96,6 +96,9 @@ bool read_fasta(const std::string &path, std::map<std::string, std::string> &seq
 int usage()
 {
     fprintf(stderr,
+            "fade-b200 <annotate|out|extract> ...\n"
+            "fade-b200 out [-c] <annotated SAM or ->      removes (or with -c hard-clips) artifact reads\n"
+            "fade-b200 extract <annotated SAM or ->       emits the artifacts in their re-mapped state\n"
             "fade-b200 annotate: marks artifact reads in bam tags (B200 implementation of `fade annotate`)\n"
             "usage: fade-b200 annotate [options] <SAM or -> <FASTA>   (SAM text in, SAM text out)\n"
             "  -t, --threads N      host threads (default: all cores)\n"
@@ -108,11 +111,8 @@ int usage()
 
 }  // namespace
 
-int main(int argc, char **argv)
+static int cmd_annotate(int argc, char **argv, const std::string &cl)
 {
-    std::string cl;
-    for (int i = 0; i < argc; ++i) { if (i) cl += " "; cl += argv[i]; }
-    if (argc < 2 || strcmp(argv[1], "annotate") != 0) { usage(); return argc < 2 ? 0 : 1; }
     fadegpu_params prm;
     fadegpu_default_params(&prm);
     int64_t batch_n = 1 << 20;
@@ -296,4 +296,297 @@ int main(int argc, char **argv)
     fadegpu_free_batch(bt);
     fadegpu_destroy(ctx);
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Consumers of the tags, pure host code on SAM text:
+//   fade-b200 out [-c]   source/filter.d:15-91,127-269 + source/stats.d:45-72
+//   fade-b200 extract    source/remap.d:11-87
+// Uncertain point U9 (dhtslib / htslib are not available here): a blank `SAMRecord(header)` is
+// htslib's bam_init1() = calloc, so every core field is 0 -> RNAME first contig, POS 1, RNEXT "=",
+// PNEXT 1 in SAM text.  oracle/consumers.py restates the same functions independently.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct SamRec {
+    std::vector<std::string> f;   // 11 mandatory fields
+    std::vector<std::string> tags;
+    bool has(const char *k) const { for (auto &t : tags) if (t.compare(0, 2, k) == 0) return true; return false; }
+    std::string tag(const char *k) const { for (auto &t : tags) if (t.compare(0, 2, k) == 0) return t.substr(5); return ""; }
+    std::string line() const
+    {
+        std::string o;
+        for (size_t k = 0; k < f.size(); ++k) { if (k) o += '\t'; o += f[k]; }
+        for (auto &t : tags) { o += '\t'; o += t; }
+        return o;
+    }
+};
+
+struct Sam {
+    std::vector<std::string> header, contigs;
+    std::vector<SamRec> recs;
+    std::string last_pg;
+};
+
+bool read_sam(const std::string &path, Sam &sam)
+{
+    std::istream *in = &std::cin;
+    std::ifstream fin;
+    if (path != "-") { fin.open(path); if (!fin) return false; in = &fin; }
+    std::string line;
+    while (std::getline(*in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty()) continue;
+        if (line[0] == '@') {
+            sam.header.push_back(line);
+            const auto f = split_tab(line);
+            if (f[0] == "@SQ") for (auto &x : f) if (x.rfind("SN:", 0) == 0) sam.contigs.push_back(x.substr(3));
+            if (f[0] == "@PG") for (auto &x : f) if (x.rfind("ID:", 0) == 0) sam.last_pg = x.substr(3);
+            continue;
+        }
+        auto f = split_tab(line);
+        if (f.size() < 11) return false;
+        SamRec r;
+        r.f.assign(f.begin(), f.begin() + 11);
+        r.tags.assign(f.begin() + 11, f.end());
+        sam.recs.push_back(std::move(r));
+    }
+    return true;
+}
+
+void write_header(const Sam &sam, const char *id, const std::string &cl)
+{
+    for (auto &h : sam.header) { fputs(h.c_str(), stdout); fputc('\n', stdout); }
+    std::string pg = std::string("@PG\tID:") + id + "\tPN:fade\tVN:" + kVersion;   // filter.d:171-178, remap.d:19-26
+    if (!sam.last_pg.empty()) pg += "\tPP:" + sam.last_pg;
+    pg += "\tCL:" + cl;
+    fputs(pg.c_str(), stdout); fputc('\n', stdout);
+}
+
+typedef std::vector<std::pair<long, char>> Cig;
+Cig cig_parse(const std::string &s)
+{
+    Cig o;
+    if (s == "*") return o;
+    long n = 0;
+    for (char c : s) { if (c >= '0' && c <= '9') n = n * 10 + (c - '0'); else { o.push_back({ n, c }); n = 0; } }
+    return o;
+}
+std::string cig_str(const Cig &c)
+{
+    std::string o;
+    for (auto &x : c) o += std::to_string(x.first) + x.second;
+    return o.empty() ? "*" : o;
+}
+bool q_consuming(char op) { return strchr("MIS=X", op) != nullptr; }
+bool r_consuming(char op) { return strchr("MDN=X", op) != nullptr; }
+long cig_span(const Cig &c) { long s = 0; for (auto &x : c) if (r_consuming(x.second)) s += x.first; return s; }
+
+std::string am_field(const std::string &am, int side, int idx)
+{
+    std::vector<std::string> sides;
+    size_t a = 0;
+    for (;;) { size_t b = am.find(';', a); if (b == std::string::npos) { sides.push_back(am.substr(a)); break; } sides.push_back(am.substr(a, b - a)); a = b + 1; }
+    if ((size_t)side >= sides.size()) return "";
+    const std::string &s = sides[(size_t)side];
+    a = 0;
+    for (int k = 0;; ++k) {
+        size_t b = s.find(',', a);
+        if (k == idx) return s.substr(a, b == std::string::npos ? std::string::npos : b - a);
+        if (b == std::string::npos) return "";
+        a = b + 1;
+    }
+}
+
+SamRec blank_record(const SamRec &r, const std::string &seq, const std::string &qual, const Sam &sam)   // U9
+{
+    SamRec o;
+    const bool hc = !sam.contigs.empty();
+    o.f = { r.f[0], "0", hc ? sam.contigs[0] : "*", hc ? "1" : "0", "0", "*", hc ? "=" : "*", hc ? "1" : "0", "0", seq, qual };
+    return o;
+}
+
+// source/filter.d:15-91
+SamRec clip_read(const SamRec &rec, int rs, const Sam &sam)
+{
+    Cig nc = cig_parse(rec.f[5]);
+    long pos = atol(rec.f[3].c_str());
+    std::string seq = rec.f[9], qual = rec.f[10];
+    const std::string am = rec.tag("am");
+    if (rs & 2) {
+        long to_trim = cig_span(cig_parse(am_field(am, 0, 2)));
+        long hard = 0;
+        if (to_trim < cig_span(cig_parse(rec.f[5]))) {
+            while (to_trim) {
+                if (q_consuming(nc[0].second)) { seq.erase(0, 1); qual.erase(0, 1); ++hard; }
+                if (r_consuming(nc[0].second)) { ++pos; --to_trim; }
+                if (--nc[0].first == 0) nc.erase(nc.begin());
+            }
+        } else return blank_record(rec, seq, qual, sam);
+        nc.insert(nc.begin(), { hard, 'H' });
+    }
+    if (rs & 4) {
+        long to_trim = cig_span(cig_parse(am_field(am, 1, 2)));
+        long hard = 0;
+        if (to_trim < cig_span(nc)) {
+            while (to_trim) {
+                if (q_consuming(nc.back().second)) { seq.pop_back(); qual.pop_back(); ++hard; }
+                if (r_consuming(nc.back().second)) --to_trim;
+                if (--nc.back().first == 0) nc.pop_back();
+            }
+        } else return blank_record(rec, seq, qual, sam);
+        nc.push_back({ hard, 'H' });
+    }
+    SamRec o = rec;
+    o.f[3] = std::to_string(pos); o.f[5] = cig_str(nc); o.f[9] = seq; o.f[10] = qual;
+    return o;
+}
+
+// source/filter.d:127-165
+int natural_compare(std::string a, std::string b)
+{
+    auto isd = [](char c) { return c >= '0' && c <= '9'; };
+    while (!a.empty() && !b.empty()) {
+        if (!isd(a[0]) && !isd(b[0])) {
+            if (a[0] == b[0]) { a.erase(0, 1); b.erase(0, 1); continue; }
+            return a[0] < b[0] ? -1 : 1;
+        }
+        auto take = [&](std::string &s) { long v = -1; size_t k = 0; while (k < s.size() && isd(s[k])) ++k; if (k) { v = atol(s.substr(0, k).c_str()); s.erase(0, k); } return v; };
+        const std::string a0 = a, b0 = b;
+        const long ai = take(a), bi = take(b);
+        if (ai == bi) { if (a == a0 && b == b0) return 0; continue; }
+        return ai < bi ? -1 : 1;
+    }
+    return a.size() == b.size() ? 0 : (a.size() < b.size() ? -1 : 1);
+}
+
+struct OutStats {   // source/stats.d:16-72
+    long read_count = 0, clipped = 0, sup = 0, art_sup = 0, art = 0, aln_l = 0, aln_r = 0;
+    void parse(int rs)
+    {
+        const int al = (rs >> 1) & 1, ar = (rs >> 2) & 1, sp = (rs >> 5) & 1;
+        clipped += rs & 1; art += al | ar; sup += sp; art_sup += (al | ar) & sp; aln_l += al; aln_r += ar;
+    }
+    void print() const
+    {
+        const double n = read_count ? (double)read_count : 0.0 / 0.0;
+        fprintf(stderr, "read count:\t%ld\nClipped %%:\t%g\n%% With Supplementary alns:\t%g\nArtifact rate:\t%g\n"
+                        "%% With Supplementary alns and artifacts:\t%g\nArtifact rate left only:\t%g\nArtifact rate right only:\t%g\n",
+                read_count, clipped / n, sup / n, art / n, art_sup / n, aln_l / n, aln_r / n);
+    }
+};
+
+int rs_of(const SamRec &r, bool &have)
+{
+    have = r.has("rs");
+    return have ? (atoi(r.tag("rs").c_str()) & 0xff) : 0;
+}
+
+int cmd_out(int argc, char **argv, const std::string &cl)
+{
+    bool clip = false;
+    std::string path;
+    for (int i = 2; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a == "-c" || a == "--clip") clip = true;
+        else if (a == "-t" || a == "--threads") ++i;
+        else if (a == "-b" || a == "-u" || a == "--bam" || a == "--ubam") { fprintf(stderr, "fade-b200: SAM text only\n"); return 1; }
+        else path = a;
+    }
+    if (path.empty()) return usage();
+    Sam sam;
+    if (!read_sam(path, sam)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
+    write_header(sam, "fade-extract", cl);   // sic: filter.d:173 uses the ID of extract
+    OutStats st;
+    auto put = [](const SamRec &r) { fputs(r.line().c_str(), stdout); fputc('\n', stdout); };
+    if (clip) {   // filter.d:182-208
+        for (auto &r : sam.recs) {
+            ++st.read_count;
+            bool have;
+            const int rs = rs_of(r, have);
+            if (!have) { put(r); continue; }
+            st.parse(rs);
+            if (!(rs & 6)) put(r); else put(clip_read(r, rs, sam));
+        }
+    } else {      // filter.d:209-266
+        bool sorted = true;
+        for (size_t k = 0; k + 1 < sam.recs.size() && k + 1 < 10; ++k)
+            if (natural_compare(sam.recs[k + 1].f[0], sam.recs[k].f[0]) < 0) sorted = false;
+        if (sorted) {
+            fprintf(stderr, "[W::fade-out] Output looks name-sorted, ejecting all reads with same readname if any have an artifact\n");
+            size_t k = 0;
+            while (k < sam.recs.size()) {
+                size_t e = k + 1;
+                while (e < sam.recs.size() && sam.recs[e].f[0] == sam.recs[e - 1].f[0]) ++e;
+                bool art = false;
+                for (size_t x = k; x < e; ++x) {
+                    ++st.read_count;
+                    bool have;
+                    const int rs = rs_of(sam.recs[x], have);
+                    if (!have) continue;
+                    st.parse(rs);
+                    if (rs & 6) art = true;
+                }
+                if (!art) for (size_t x = k; x < e; ++x) put(sam.recs[x]);
+                k = e;
+            }
+        } else {
+            fprintf(stderr, "[W::fade-out] Output doesn't look name-sorted, ejecting by only reads with an artifact\n");
+            for (auto &r : sam.recs) {
+                ++st.read_count;
+                bool have;
+                const int rs = rs_of(r, have);
+                if (!have) continue;
+                st.parse(rs);
+                if (!(rs & 6)) put(r);
+            }
+        }
+    }
+    st.print();
+    return 0;
+}
+
+int cmd_extract(int argc, char **argv, const std::string &cl)
+{
+    if (argc < 3) return usage();
+    Sam sam;
+    if (!read_sam(argv[argc - 1], sam)) { fprintf(stderr, "fade-b200: cannot read %s\n", argv[argc - 1]); return 1; }
+    write_header(sam, "fade-extract", cl);
+    static const char comp[] = "=TGKCYSBAWRDMHVN";   // complement of "=ACMGRSVTWYHKDBN" (util.d:18-21)
+    static const char nt16[] = "=ACMGRSVTWYHKDBN";
+    for (auto &r : sam.recs) {   // remap.d:29-85
+        bool have;
+        const int rs = rs_of(r, have);
+        if (!have || !(rs & 6) || !r.has("am")) continue;
+        const std::string am = r.tag("am");
+        for (int side = 0; side < 2; ++side) {
+            if (!(rs & (side == 0 ? 2 : 4))) continue;
+            const std::string chrom = am_field(am, side, 0), pos0 = am_field(am, side, 1), cig = am_field(am, side, 2);
+            int tid = -1;
+            for (size_t t = 0; t < sam.contigs.size(); ++t) if (sam.contigs[t] == chrom) tid = (int)t;
+            std::string seq(r.f[9].rbegin(), r.f[9].rend());
+            for (auto &ch : seq) { const char *p = strchr(nt16, toupper((unsigned char)ch)); ch = (p && ch) ? comp[p - nt16] : 'N'; }
+            const std::string qual(r.f[10].rbegin(), r.f[10].rend());
+            const int flag = (atoi(r.f[1].c_str()) & 16) ? 0 : 16;
+            const bool hc = !sam.contigs.empty();
+            fprintf(stdout, "%s\t%d\t%s\t%ld\t0\t%s\t%s\t%s\t0\t%s\t%s\n", r.f[0].c_str(), flag, tid >= 0 ? chrom.c_str() : "*",
+                    atol(pos0.c_str()) + 1, cig.c_str(), tid == 0 ? "=" : (hc ? sam.contigs[0].c_str() : "*"), hc ? "1" : "0",
+                    seq.c_str(), qual.c_str());
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    std::string cl;
+    for (int i = 0; i < argc; ++i) { if (i) cl += " "; cl += argv[i]; }
+    if (argc < 2) { usage(); return 0; }
+    if (strcmp(argv[1], "annotate") == 0) return cmd_annotate(argc, argv, cl);
+    if (strcmp(argv[1], "out") == 0) return cmd_out(argc, argv, cl);
+    if (strcmp(argv[1], "extract") == 0) return cmd_extract(argc, argv, cl);
+    usage();
+    return 1;
 }

@@ -1,0 +1,119 @@
+"""`fade-b200 out [-c]` and `fade-b200 extract` (C++, SAM text) against the
+independent Python restatement oracle/consumers.py.  Pure host code: runs without a GPU.  PARITY
+UNPINNED with respect to real fade (filter.d / remap.d cannot be executed here)."""
+import os
+import random
+import subprocess
+
+import pytest
+
+import samio
+from fade_b200 import sim
+from oracle import consumers as cons
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "fade_b200", "bin", "fade-b200")
+
+
+def annotated_sam(tmp_path, n=2500, name_sorted=True, with_untagged=True):
+    """An annotated SAM as `fade annotate` would write it, produced with the ORACLE (no GPU)."""
+    names, contigs, cfg, _ = sim.config_c1()
+    contigs = [contigs[0][:300_000]]
+    rd = sim.make_reads(cfg, 0, n, contigs)
+    path = tmp_path / "anno.sam"
+    L = rd.read_len
+    stride = (L + 1) // 2
+    refb = contigs[0].tobytes()
+    lines = ["@HD\tVN:1.6\tSO:queryname", f"@SQ\tSN:{names[0]}\tLN:{len(contigs[0])}", "@SQ\tSN:chrOther\tLN:1000",
+             "@PG\tID:fade-annotate\tPN:fade"]
+    order = list(range(n))
+    if not name_sorted:
+        random.Random(3).shuffle(order)
+    for k in order:
+        seq = orc.decode_nt16(rd.seq4[k * stride:(k + 1) * stride], L)
+        qual = "".join(chr(int(q) + 33) for q in rd.qual[k * L:(k + 1) * L])
+        cig = orc.cigar_string(rd.cigar[k, : rd.n_cigar[k]]) or "*"
+        t = orc.annotate_record(is_mapped=not (rd.flag[k] & 4), has_sa=bool(rd.has_sa[k]), cigar=rd.cigar[k, : rd.n_cigar[k]],
+                                seq4=rd.seq4[k * stride:(k + 1) * stride], qual=rd.qual[k * L:(k + 1) * L], l_qseq=L,
+                                pos=int(rd.pos[k]), contig_name=names[0], ref_seq=refb)
+        f = [f"r{k // 2}", str(int(rd.flag[k])), names[0], str(int(rd.pos[k]) + 1), "60", cig, "=", "1", "0", seq, qual, "NM:i:1"]
+        if not (with_untagged and k % 97 == 0):
+            f.append(f"rs:i:{t['rs']}")
+            for tag in ("am", "as", "ar", "ab"):
+                if tag in t:
+                    f.append(f"{tag}:Z:{t[tag]}")
+        lines.append("\t".join(f))
+    path.write_text("\n".join(lines) + "\n")
+    return path, [names[0], "chrOther"]
+
+
+def run_cli(args, path):
+    p = subprocess.run([BIN, *args, str(path)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    body = [ln for ln in p.stdout.splitlines() if not ln.startswith("@")]
+    head = [ln for ln in p.stdout.splitlines() if ln.startswith("@")]
+    return head, body, p.stderr
+
+
+def load(path):
+    recs = [cons.parse_sam_line(ln) for ln in open(path) if not ln.startswith("@")]
+    return recs
+
+
+@pytest.mark.parametrize("name_sorted", [True, False])
+def test_out_filter_mode(tmp_path, name_sorted):
+    path, contigs = annotated_sam(tmp_path, name_sorted=name_sorted)
+    head, body, err = run_cli(["out"], path)
+    exp, st = cons.fade_out(load(path), clip=False, contigs=contigs)
+    assert body == [cons.format_sam_line(r) for r in exp]
+    assert 0 < len(body) < 2500
+    assert head[-1].startswith("@PG\tID:fade-extract\tPN:fade\tVN:") and "PP:fade-annotate" in head[-1]   # filter.d:173 (sic)
+    assert ("looks name-sorted" in err) == name_sorted
+    assert err.strip().splitlines()[-7:] == st.lines()
+
+
+def test_out_clip_mode(tmp_path):
+    path, contigs = annotated_sam(tmp_path)
+    head, body, err = run_cli(["out", "-c"], path)
+    recs = load(path)
+    exp, st = cons.fade_out(recs, clip=True, contigs=contigs)
+    assert body == [cons.format_sam_line(r) for r in exp] and len(body) == len(recs)
+    changed = [(a, b) for a, b in zip(recs, exp) if cons.format_sam_line(a) != cons.format_sam_line(b)]
+    assert len(changed) > 50
+    for a, b in changed[:200]:
+        if b["cigar"] == "*":
+            continue                                    # whole alignment was artifact: blank record (U9)
+        ops = cons.cigar_ops(b["cigar"])
+        assert "H" in (ops[0][1], ops[-1][1])
+        assert sum(n for n, op in ops if op in cons.QUERY_OPS) == len(b["seq"]) == len(b["qual"])
+        assert sum(n for n, op in ops if op in "MIS=XH") == len(a["seq"])
+    assert err.strip().splitlines()[-7:] == st.lines()
+
+
+def test_extract(tmp_path):
+    path, contigs = annotated_sam(tmp_path)
+    head, body, err = run_cli(["extract"], path)
+    exp = cons.fade_extract(load(path), contigs)
+    assert body == [cons.format_sam_line(r) for r in exp] and len(body) > 50
+    for ln in body[:100]:
+        r = cons.parse_sam_line(ln)
+        ops = cons.cigar_ops(r["cigar"])
+        assert sum(n for n, op in ops if op in cons.QUERY_OPS) == len(r["seq"])      # am CIGAR covers the RC'd read
+        assert r["flag"] in (0, 16) and r["rname"] == contigs[0]
+
+
+def test_natural_compare_and_clip_units():
+    c = cons.natural_compare
+    assert c("r2", "r10") < 0 and c("r10", "r2") > 0 and c("a", "a") == 0 and c("r1a", "r1b") < 0 and c("r1", "r1x") < 0
+    r = cons.parse_sam_line("q\t0\tchr1\t101\t60\t30S120M\t*\t0\t0\t" + "A" * 150 + "\t" + "I" * 150 +
+                            "\trs:i:3\tam:Z:chr1,50,126S24=;")
+    out = cons.clip_read(r, 3, ["chr1"])
+    assert (out["cigar"], out["pos"], len(out["seq"])) == ("54H96M", 125, 96)
+    r = cons.parse_sam_line("q\t16\tchr1\t101\t60\t110M40S\t*\t0\t0\t" + "A" * 150 + "\t" + "I" * 150 +
+                            "\trs:i:5\tam:Z:;chr1,500,30=120S")
+    out = cons.clip_read(r, 5, ["chr1"])
+    assert (out["cigar"], out["pos"], len(out["seq"])) == ("80M70H", 101, 80)
+    r["tags"]["am"] = ("Z", ";chr1,500,120=30S")          # artifact spans the whole alignment -> blank record
+    out = cons.clip_read(r, 5, ["chr1"])
+    assert out["cigar"] == "*" and out["flag"] == 0 and not out["tags"]

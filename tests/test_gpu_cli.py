@@ -61,3 +61,26 @@ def test_cli_reannotation_replaces_old_tags(tmp_path):
     h2, b = samio.read_sam_tags(o2)
     assert {k: v[1] for k, v in a.items()} == {k: v[1] for k, v in b.items()}
     assert h2[-1].split("\t")[1:4:2] == ["ID:fade-annotate", "VN:fade-b200-0.1"] and "PP:fade-annotate" in h2[-1]
+
+
+def test_end_to_end_chain_annotate_out_extract(tmp_path):
+    """BASELINE configs[4] in miniature: annotate (GPU) -> out -c / out / extract give the same
+    records as the oracle's annotation pushed through the Python restatement of the consumers."""
+    from oracle import consumers as cons
+    names, contigs, cfg, _ = sim.config_c1()
+    contigs = [contigs[0][:300_000]]
+    rd = sim.make_reads(cfg, 0, 2000, contigs)
+    fa, sam, anno = tmp_path / "ref.fa", tmp_path / "in.sam", tmp_path / "anno.sam"
+    samio.write_fasta(fa, names, contigs)
+    samio.write_sam(sam, names, contigs, rd)
+    with open(anno, "w") as fo:
+        assert subprocess.run([BIN, "annotate", str(sam), str(fa)], stdout=fo, stderr=subprocess.DEVNULL).returncode == 0
+    recs = [cons.parse_sam_line(ln) for ln in open(anno) if not ln.startswith("@")]
+    # the annotated records carry exactly the oracle's tags (checked above); now the consumers
+    for args, exp in ((["out", "-c"], cons.fade_out(recs, True, names)[0]), (["out"], cons.fade_out(recs, False, names)[0]),
+                      (["extract"], cons.fade_extract(recs, names))):
+        p = subprocess.run([BIN, *args, str(anno)], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        body = [ln for ln in p.stdout.splitlines() if not ln.startswith("@")]
+        assert body == [cons.format_sam_line(r) for r in exp], args
+        assert len(body) > 50
