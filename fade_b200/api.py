@@ -14,6 +14,7 @@ R_ALIGNED, R_ART_LEFT, R_ART_RIGHT, R_OPS_TRUNC, R_GENERIC = 1, 2, 4, 8, 16
 F_FORCE_GENERIC = 1
 F_NO_SCATTER = 2
 F_NO_SHORTCUT = 8
+F_HOST_BINNING = 16
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_query", "<i4"), ("end_ref", "<i4"), ("beg_query", "<i4"),
                          ("beg_ref", "<i4"), ("n_ops", "<i4"), ("flags", "<u4"), ("read", "<i4"),
                          ("ops", "<u4", (32,))])
@@ -126,14 +127,18 @@ class Batch:
         self.clip_left = _np_view(v.clip_left, n, np.int32)
         self.clip_right = _np_view(v.clip_right, n, np.int32)
         self.flags = _np_view(v.flags, n, np.uint8)
-        self.score = _np_view(v.score, n, np.int32)
-        self.beg_query = _np_view(v.beg_query, n, np.int32)
-        self.end_query = _np_view(v.end_query, n, np.int32)
-        self.beg_ref = _np_view(v.beg_ref, n, np.int32)
-        self.end_ref = _np_view(v.end_ref, n, np.int32)
-        self.win_start = _np_view(v.win_start, n, np.int64)
-        self.n_ops = _np_view(v.n_ops, n, np.int32)
-        self.ops = _np_view(v.ops, n * MAX_OPS, np.uint32).reshape(n, MAX_OPS)
+        if v.score:     # per-read output arrays exist unless the ctx has F_NO_SCATTER
+            self.score = _np_view(v.score, n, np.int32)
+            self.beg_query = _np_view(v.beg_query, n, np.int32)
+            self.end_query = _np_view(v.end_query, n, np.int32)
+            self.beg_ref = _np_view(v.beg_ref, n, np.int32)
+            self.end_ref = _np_view(v.end_ref, n, np.int32)
+            self.win_start = _np_view(v.win_start, n, np.int64)
+            self.n_ops = _np_view(v.n_ops, n, np.int32)
+            self.ops = _np_view(v.ops, n * MAX_OPS, np.uint32).reshape(n, MAX_OPS)
+        else:
+            self.score = self.beg_query = self.end_query = self.beg_ref = self.end_ref = None
+            self.win_start = self.n_ops = self.ops = None
         self.n = 0
 
     def fill(self, seq4, seq_off, l_qseq, tid, pos, aligned_len, clip_left, clip_right):

@@ -56,6 +56,8 @@ struct fadegpu_ctx {
     unsigned int *d_qcount = nullptr;
     int sm_count = 148;
     int host_threads = 1;
+    cudaStream_t stream2 = nullptr;      // uploads + binning of the next batch while the previous one computes
+    int64_t *d_clen = nullptr, *d_coff = nullptr;   // contig tables for the device-side binning
     std::string err;
 };
 
@@ -99,6 +101,19 @@ struct fadegpu_batch {
     std::vector<AlnTmp> all_aln;
     std::vector<int32_t> cnt;
     std::vector<int64_t> soff, aln_start;
+    std::vector<int32_t> sorted_tlen;
+    // ---- device-side binning (submits from the pinned view) ----
+    bool dev_binning = false;          // the last submit used it
+    uint8_t *d_in_seq4 = nullptr;
+    int64_t *d_in_seq_off = nullptr, *d_in_pos = nullptr, *d_start = nullptr, *d_aln_start = nullptr;
+    int32_t *d_in_lq = nullptr, *d_in_tid = nullptr, *d_in_alen = nullptr, *d_in_cl = nullptr, *d_in_cr = nullptr;
+    int32_t *d_key = nullptr, *d_tlen = nullptr, *d_hist = nullptr, *d_keybase = nullptr, *d_cursor = nullptr, *d_ridx = nullptr;
+    uint8_t *d_rflags = nullptr;
+    unsigned long long *d_stats = nullptr;
+    int32_t *h_hist = nullptr, *h_keybase = nullptr;   // pinned
+    unsigned long long *h_stats = nullptr;            // pinned
+    int64_t *h_aln_start = nullptr;                   // pinned
+    cudaEvent_t ev_prep = nullptr, ev_ready = nullptr;
 };
 
 namespace {
@@ -130,8 +145,20 @@ void free_dev(T *&p) { if (p) cudaFree(p); p = nullptr; }
 void free_reference(fadegpu_ctx *c)
 {
     free_dev(c->d_two); free_dev(c->d_n); free_dev(c->d_x); free_dev(c->d_xpos); free_dev(c->d_xchr);
+    free_dev(c->d_clen); free_dev(c->d_coff);
     c->n_x = 0; c->ref_bytes = 0; c->n_contigs = 0; c->total_bases = c->padded_bases = 0;
     c->names.clear(); c->clen.clear(); c->coff.clear();
+}
+
+int upload_contig_tables(fadegpu_ctx *c)
+{
+    const size_t nb = std::max<size_t>(1, (size_t)c->n_contigs) * sizeof(int64_t);
+    CU(c, cudaMalloc(&c->d_clen, nb)); CU(c, cudaMalloc(&c->d_coff, nb));
+    if (c->n_contigs > 0) {
+        CU(c, cudaMemcpy(c->d_clen, c->clen.data(), (size_t)c->n_contigs * 8, cudaMemcpyHostToDevice));
+        CU(c, cudaMemcpy(c->d_coff, c->coff.data(), (size_t)c->n_contigs * 8, cudaMemcpyHostToDevice));
+    }
+    return 0;
 }
 
 RefDev ref_dev(const fadegpu_ctx *c)
@@ -207,6 +234,78 @@ size_t gen_slot_bytes(int qmax, int tmax)
     return (b + 15) & ~(size_t)15;
 }
 
+// Launch plan from the sorted order: cls_first[rk] = first sorted position of row class rk (the
+// generic list is rank N_ROW_CLASSES), sorted_tlen[pos] = window length at sorted position pos.
+// Fills b->plan, b->h_items and grows the ctx scratch buffers.
+int build_plan(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_aln, const int64_t *cls_first, const int32_t *sorted_tlen,
+               int qmax_all, int tmax_all, int gen_qmax, int gen_tmax)
+{
+    int64_t n_items = 0;
+    size_t ck_needed = 0, gen_needed = 0, trace_needed = 0;
+    b->plan.clear();
+    b->st.n_generic = 0;
+    for (int rk = 0; rk <= N_ROW_CLASSES; ++rk) {
+        const int R = rk < N_ROW_CLASSES ? ROW_CLASSES[rk] : 0;
+        const int64_t first_aln = cls_first[rk], last_aln = cls_first[rk + 1];
+        if (last_aln <= first_aln) continue;
+        if (R == 0) {
+            Launch L{};
+            L.R = 0; L.aln_first = (int)first_aln; L.n_aln = (int)(last_aln - first_aln); L.qmax = gen_qmax; L.tmax = gen_tmax;
+            b->plan.push_back(L);
+            gen_needed = std::max(gen_needed, gen_slot_bytes(gen_qmax, gen_tmax));
+            b->st.n_generic += last_aln - first_aln;
+            continue;
+        }
+        // warp items of 8 alignments; split into launches that fit the checkpoint scratch
+        const size_t cw = ck_words_of(R);
+        int64_t a0 = first_aln;
+        while (a0 < last_aln) {
+            Launch L{};
+            L.R = R; L.aln_first = (int)a0; L.item_first = (int)n_items; L.qmax = qmax_all; L.tmax = tmax_all;
+            size_t words = 0;
+            int nblk_max = 1;
+            int64_t a1 = a0;
+            while (a1 < last_aln) {
+                const int nblk = num_blocks(sorted_tlen[a1]);  // longest of the 8 (sorted descending)
+                const size_t wds = (size_t)(nblk - 1) * cw * 32;
+                if (a1 > a0 && (words + wds) * 4 > (size_t)c->p.scratch_bytes) break;
+                if (n_items >= b->cap_items) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: internal error (item capacity)");
+                WarpItem &it = b->h_items[n_items++];
+                it.ck_off = (int64_t)words;
+                it.first = (int32_t)(a1 - a0);
+                it.nblk = (int16_t)nblk;
+                it.pad = 0;
+                it.nsteps = sorted_tlen[a1] + FG - 1;
+                words += wds;
+                nblk_max = std::max(nblk_max, nblk);
+                a1 = std::min<int64_t>(a1 + 8, last_aln);
+            }
+            L.n_aln = (int)(a1 - a0);
+            L.n_items = (int)(n_items - L.item_first);
+            L.tw_stride = tw_stride_for(nblk_max);
+            L.nblk_max = nblk_max;
+            ck_needed = std::max(ck_needed, words * 4);
+            trace_needed = std::max(trace_needed, trace_scratch_bytes(R, L.n_aln));
+            b->plan.push_back(L);
+            a0 = a1;
+        }
+    }
+    b->n_aln = n_aln; b->n_items = n_items;
+    b->qmax_all = qmax_all; b->tmax_all = tmax_all;
+    b->st.n_aligned = n_aln;
+    b->st.scratch_bytes = (int64_t)ck_needed;
+    // a slot for wildcard alignments discovered on the device, sized for the largest problem
+    if (n_aln > 0) gen_needed = std::max(gen_needed, gen_slot_bytes(qmax_all, tmax_all));
+    if (ck_needed) { int rc = ensure_ck(c, ck_needed); if (rc) return rc; }
+    if (trace_needed) { int rc = ensure_trace(c, trace_needed); if (rc) return rc; }
+    if (gen_needed) {
+        const size_t want = std::min<size_t>(GEN_BUDGET, gen_needed * 1024);
+        int rc = ensure_gen(c, std::max(want, gen_needed));
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 // queue every kernel of the batch's plan on the ctx stream; stage times via optional events
 int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, float *gen_ms, int *launches)
 {
@@ -225,7 +324,7 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
             a.n_aln = L.n_aln;
             a.items = b->d_items + L.item_first;
             a.n_items = L.n_items;
-            a.seq = b->d_seq;
+            a.seq = b->dev_binning ? b->d_in_seq4 : b->d_seq;
             a.ref = ref_dev(c);
             a.ck = c->d_ck;
             a.fillres = b->d_fillres + (size_t)L.item_first * 32;
@@ -252,7 +351,7 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
             CU(c, launch_trace(L.R, a, c->stream, c->sm_count, &nl));
             // wildcard letters found by the packed kernels -> generic kernel over the flagged ones
             GenericArgs ga;
-            ga.aln = a.aln; ga.n_aln = L.n_aln; ga.aln_flags = a.aln_flags; ga.seq = b->d_seq; ga.ref = a.ref;
+            ga.aln = a.aln; ga.n_aln = L.n_aln; ga.aln_flags = a.aln_flags; ga.seq = a.seq; ga.ref = a.ref;
             ga.out = a.out; ga.cursor = c->d_cursor; ga.scratch = c->d_gen;
             ga.qmax = L.qmax; ga.tmax = L.tmax;
             ga.slot_bytes = (int64_t)gen_slot_bytes(L.qmax, L.tmax);
@@ -277,7 +376,7 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
             }
         } else {
             GenericArgs ga;
-            ga.aln = b->d_aln + L.aln_first; ga.n_aln = L.n_aln; ga.aln_flags = nullptr; ga.seq = b->d_seq;
+            ga.aln = b->d_aln + L.aln_first; ga.n_aln = L.n_aln; ga.aln_flags = nullptr; ga.seq = b->dev_binning ? b->d_in_seq4 : b->d_seq;
             ga.ref = ref_dev(c); ga.out = b->d_out + L.aln_first; ga.cursor = c->d_cursor; ga.scratch = c->d_gen;
             ga.qmax = L.qmax; ga.tmax = L.tmax;
             ga.slot_bytes = (int64_t)gen_slot_bytes(L.qmax, L.tmax);
@@ -370,6 +469,7 @@ int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_cursor, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&c->d_alu, 64)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "fadegpu_create");
         delete c;
@@ -384,6 +484,7 @@ void fadegpu_destroy(fadegpu_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     free_reference(c);
     free_dev(c->d_ck); free_dev(c->d_gen); free_dev(c->d_cursor); free_dev(c->d_alu); free_dev(c->d_trace); free_dev(c->d_qcount);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -474,6 +575,7 @@ int fadegpu_load_reference(fadegpu_ctx *c, int32_t n_contigs, const char *const 
         CU(c, cudaMemcpy(c->d_xchr, xchr.data(), xchr.size(), cudaMemcpyHostToDevice));
     }
     c->ref_bytes = w2 * 4 + 2 * w1 * 4 + xpos.size() * 9;
+    { int rc = upload_contig_tables(c); if (rc) return rc; }
     return FADEGPU_OK;
 }
 
@@ -498,6 +600,7 @@ int fadegpu_share_reference(fadegpu_ctx *dst, const fadegpu_ctx *src)
         CU(dst, cudaMemcpyPeer(dst->d_xchr, dst->device, src->d_xchr, src->device, (size_t)src->n_x));
     }
     dst->ref_bytes = src->ref_bytes;
+    { int rc = upload_contig_tables(dst); if (rc) return rc; }
     return FADEGPU_OK;
 }
 
@@ -514,7 +617,7 @@ void fadegpu_free_batch(fadegpu_batch *b)
 {
     if (!b) return;
     fadegpu_ctx *c = b->ctx;
-    if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); }
+    if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); if (c->stream2) cudaStreamSynchronize(c->stream2); }
     fadegpu_batch_view &v = b->v;
     free_host(v.seq4); free_host(v.seq_off); free_host(v.l_qseq); free_host(v.tid); free_host(v.pos);
     free_host(v.aligned_len); free_host(v.clip_left); free_host(v.clip_right);
@@ -523,6 +626,13 @@ void fadegpu_free_batch(fadegpu_batch *b)
     free_host(b->h_aln); free_host(b->h_items); free_host(b->h_seq); free_host(b->h_out); free_host(b->h_ridx);
     free_dev(b->d_aln); free_dev(b->d_items); free_dev(b->d_seq); free_dev(b->d_out); free_dev(b->d_flags);
     free_dev(b->d_fillres);
+    free_dev(b->d_in_seq4); free_dev(b->d_in_seq_off); free_dev(b->d_in_pos); free_dev(b->d_in_lq); free_dev(b->d_in_tid);
+    free_dev(b->d_in_alen); free_dev(b->d_in_cl); free_dev(b->d_in_cr); free_dev(b->d_key); free_dev(b->d_tlen); free_dev(b->d_start);
+    free_dev(b->d_aln_start); free_dev(b->d_hist); free_dev(b->d_keybase); free_dev(b->d_cursor); free_dev(b->d_ridx);
+    free_dev(b->d_rflags); free_dev(b->d_stats);
+    free_host(b->h_hist); free_host(b->h_keybase); free_host(b->h_stats); free_host(b->h_aln_start);
+    if (b->ev_prep) cudaEventDestroy(b->ev_prep);
+    if (b->ev_ready) cudaEventDestroy(b->ev_ready);
     for (auto &e : b->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     delete b;
 }
@@ -547,13 +657,26 @@ int fadegpu_alloc_batch(fadegpu_ctx *c, int64_t max_reads, int64_t max_seq_bytes
     auto D = [&](auto **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc((void **)p, std::max<size_t>(bytes, 16)); };
     H(&v.seq4, (size_t)max_seq_bytes); H(&v.seq_off, (n + 1) * 8); H(&v.l_qseq, n * 4); H(&v.tid, n * 4);
     H(&v.pos, n * 8); H(&v.aligned_len, n * 4); H(&v.clip_left, n * 4); H(&v.clip_right, n * 4);
-    H(&v.flags, n); H(&v.score, n * 4); H(&v.beg_query, n * 4); H(&v.end_query, n * 4); H(&v.beg_ref, n * 4);
-    H(&v.end_ref, n * 4); H(&v.win_start, n * 8); H(&v.n_ops, n * 4); H(&v.ops, n * 4 * FADEGPU_MAX_OPS);
-    H(&b->h_aln, n * sizeof(AlnDesc)); H(&b->h_items, (size_t)b->cap_items * sizeof(WarpItem));
-    H(&b->h_seq, (size_t)b->cap_seq); H(&b->h_out, n * sizeof(AlnOut)); H(&b->h_ridx, n * 4);
+    H(&v.flags, n);
+    if (!(c->p.flags & FADEGPU_F_NO_SCATTER)) {   // the per-read output arrays are only filled without NO_SCATTER
+        H(&v.score, n * 4); H(&v.beg_query, n * 4); H(&v.end_query, n * 4); H(&v.beg_ref, n * 4);
+        H(&v.end_ref, n * 4); H(&v.win_start, n * 8); H(&v.n_ops, n * 4); H(&v.ops, n * 4 * FADEGPU_MAX_OPS);
+    }
+    H(&b->h_items, (size_t)b->cap_items * sizeof(WarpItem));
+    H(&b->h_out, n * sizeof(AlnOut)); H(&b->h_ridx, n * 4);
+    // h_aln / h_seq / d_seq (staging of the host-binning path) are allocated on its first use
     D(&b->d_aln, n * sizeof(AlnDesc)); D(&b->d_items, (size_t)b->cap_items * sizeof(WarpItem));
-    D(&b->d_seq, (size_t)b->cap_seq); D(&b->d_out, n * sizeof(AlnOut)); D(&b->d_flags, n * 4);
+    D(&b->d_out, n * sizeof(AlnOut)); D(&b->d_flags, n * 4);
     D(&b->d_fillres, (size_t)b->cap_items * 32 * sizeof(uint2));
+    // device-side binning: mirrors of the inputs, keys, histogram, per-read result index
+    D(&b->d_in_seq4, (size_t)max_seq_bytes + 16); D(&b->d_in_seq_off, (n + 1) * 8); D(&b->d_in_pos, n * 8);
+    D(&b->d_in_lq, n * 4); D(&b->d_in_tid, n * 4); D(&b->d_in_alen, n * 4); D(&b->d_in_cl, n * 4); D(&b->d_in_cr, n * 4);
+    D(&b->d_key, n * 4); D(&b->d_tlen, n * 4); D(&b->d_start, n * 8); D(&b->d_aln_start, n * 8);
+    D(&b->d_hist, (size_t)BIN_KEYS * 4); D(&b->d_keybase, (size_t)BIN_KEYS * 4); D(&b->d_cursor, (size_t)BIN_KEYS * 4);
+    D(&b->d_ridx, n * 4); D(&b->d_rflags, n); D(&b->d_stats, 64);
+    H(&b->h_hist, (size_t)BIN_KEYS * 4); H(&b->h_keybase, (size_t)BIN_KEYS * 4); H(&b->h_stats, 64); H(&b->h_aln_start, n * 8);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_prep);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_ready);
     for (auto &ev : b->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e != cudaSuccess) {
         int rc = cuda_fail(c, e, "fadegpu_alloc_batch");
@@ -571,6 +694,16 @@ int fadegpu_get_batch_view(fadegpu_batch *b, fadegpu_batch_view *view)
     return FADEGPU_OK;
 }
 
+static int ensure_host_staging(fadegpu_ctx *c, fadegpu_batch *b)
+{
+    if (b->h_aln) return 0;
+    const size_t n = (size_t)b->v.max_reads;
+    CU(c, cudaHostAlloc((void **)&b->h_aln, n * sizeof(AlnDesc), cudaHostAllocDefault));
+    CU(c, cudaHostAlloc((void **)&b->h_seq, (size_t)b->cap_seq, cudaHostAllocDefault));
+    CU(c, cudaMalloc((void **)&b->d_seq, (size_t)b->cap_seq));
+    return 0;
+}
+
 int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, const fadegpu_inputs *in)
 {
     if (!c || !b || b->ctx != c || !in) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: bad ctx/batch/inputs");
@@ -581,9 +714,11 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
                         !in->clip_left || !in->clip_right))
         return fail(c, FADEGPU_E_ARG, "fadegpu_submit: null input array");
     CU(c, cudaSetDevice(c->device));
+    { int rc = ensure_host_staging(c, b); if (rc) return rc; }
     const int64_t n = n_reads;
     b->n_reads = n;
     b->plan.clear();
+    b->dev_binning = false;
     memset(&b->st, 0, sizeof(b->st));
     b->st.n_reads = n;
 
@@ -747,71 +882,14 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
 
     b->st.host_gather_ms = ms_since(t_gather);
     // ---- 4. launch plan ----
-
-    int64_t n_items = 0;
-    size_t ck_needed = 0, gen_needed = 0, trace_needed = 0;
-    for (int rk = 0; rk <= N_ROW_CLASSES; ++rk) {
-        const int R = rk < N_ROW_CLASSES ? ROW_CLASSES[rk] : 0;
-        const int64_t first_aln = cls_first[rk], last_aln = cls_first[rk + 1];
-        if (last_aln <= first_aln) continue;
-        if (R == 0) {
-            int qmax = 1, tmax = 1;
-            for (int64_t kx = first_aln; kx < last_aln; ++kx) {
-                qmax = std::max(qmax, b->h_aln[kx].qlen); tmax = std::max(tmax, b->h_aln[kx].tlen);
-            }
-            Launch L{};
-            L.R = 0; L.aln_first = (int)first_aln; L.n_aln = (int)(last_aln - first_aln); L.qmax = qmax; L.tmax = tmax;
-            b->plan.push_back(L);
-            gen_needed = std::max(gen_needed, gen_slot_bytes(qmax, tmax));
-            b->st.n_generic += last_aln - first_aln;
-            continue;
-        }
-        // warp items of 8 alignments; split into launches that fit the checkpoint scratch
-        const size_t cw = ck_words_of(R);
-        int64_t a0 = first_aln;
-        while (a0 < last_aln) {
-            Launch L{};
-            L.R = R; L.aln_first = (int)a0; L.item_first = (int)n_items; L.qmax = qmax_all; L.tmax = tmax_all;
-            size_t words = 0;
-            int nblk_max = 1;
-            int64_t a1 = a0;
-            while (a1 < last_aln) {
-                const int nblk = num_blocks(b->h_aln[a1].tlen);  // longest of the 8 (sorted descending)
-                const size_t wds = (size_t)(nblk - 1) * cw * 32;
-                if (a1 > a0 && (words + wds) * 4 > (size_t)c->p.scratch_bytes) break;
-                WarpItem &it = b->h_items[n_items++];
-                it.ck_off = (int64_t)words;
-                it.first = (int32_t)(a1 - a0);
-                it.nblk = (int16_t)nblk;
-                it.pad = 0;
-                it.nsteps = b->h_aln[a1].tlen + FG - 1;
-                words += wds;
-                nblk_max = std::max(nblk_max, nblk);
-                a1 = std::min<int64_t>(a1 + 8, last_aln);
-            }
-            L.n_aln = (int)(a1 - a0);
-            L.n_items = (int)(n_items - L.item_first);
-            L.tw_stride = tw_stride_for(nblk_max);
-            L.nblk_max = nblk_max;
-            ck_needed = std::max(ck_needed, words * 4);
-            trace_needed = std::max(trace_needed, trace_scratch_bytes(R, L.n_aln));
-            b->plan.push_back(L);
-            a0 = a1;
-        }
-    }
-    b->n_aln = n_aln; b->n_items = n_items; b->seq_bytes = seq_bytes;
-    b->qmax_all = qmax_all; b->tmax_all = tmax_all;
-    b->st.n_aligned = n_aln;
-    b->st.scratch_bytes = (int64_t)ck_needed;
-    // a slot for wildcard alignments discovered on the device, sized for the largest problem
-    if (n_aln > 0) gen_needed = std::max(gen_needed, gen_slot_bytes(qmax_all, tmax_all));
-    if (ck_needed) { int rc = ensure_ck(c, ck_needed); if (rc) return rc; }
-    if (trace_needed) { int rc = ensure_trace(c, trace_needed); if (rc) return rc; }
-    if (gen_needed) {
-        const size_t want = std::min<size_t>(GEN_BUDGET, gen_needed * 1024);
-        int rc = ensure_gen(c, std::max(want, gen_needed));
-        if (rc) return rc;
-    }
+    std::vector<int32_t> &stl = b->sorted_tlen;
+    stl.resize((size_t)n_aln);
+    for (int64_t kx = 0; kx < n_aln; ++kx) stl[(size_t)kx] = b->h_aln[kx].tlen;
+    int gq = 1, gt = 1;
+    for (int64_t kx = cls_first[N_ROW_CLASSES]; kx < n_aln; ++kx) { gq = std::max(gq, b->h_aln[kx].qlen); gt = std::max(gt, b->h_aln[kx].tlen); }
+    b->seq_bytes = seq_bytes;
+    { int rc = build_plan(c, b, n_aln, cls_first, stl.data(), qmax_all, tmax_all, gq, gt); if (rc) return rc; }
+    const int64_t n_items = b->n_items;
 
     // ---- 5. queue copies and kernels ----
     CU(c, cudaEventRecord(b->ev[0], c->stream));
@@ -836,12 +914,130 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     return FADEGPU_OK;
 }
 
+// Submit from the pinned view with the binning done on the device: the per-read arrays go to the
+// GPU as they are (DMA from the pinned view), a classify kernel evaluates the length floor and the
+// window arithmetic and histograms the reads by (row class, window length), the host turns the
+// 96 KB histogram into the launch plan, a scatter kernel writes the sorted descriptors.  The host
+// cores touch nothing per read; uploads and binning of batch k+1 run on a second stream while
+// batch k computes.
+static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n)
+{
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    const fadegpu_batch_view &v = b->v;
+    b->n_reads = n;
+    b->plan.clear();
+    b->dev_binning = true;
+    memset(&b->st, 0, sizeof(b->st));
+    b->st.n_reads = n;
+    b->st.host_threads = 1;
+    b->n_aln = 0; b->n_items = 0;
+    cudaStream_t s2 = c->stream2;
+    CU(c, cudaEventRecord(b->ev[0], s2));
+    const int64_t seq_total = n > 0 ? v.seq_off[n] : 0;
+    int64_t n_aln = 0;
+    if (n > 0) {
+        auto up = [&](void *d, const void *h, size_t bytes) { return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s2); };
+        CU(c, up(b->d_in_seq4, v.seq4, (size_t)seq_total));
+        CU(c, up(b->d_in_seq_off, v.seq_off, (size_t)(n + 1) * 8));
+        CU(c, up(b->d_in_lq, v.l_qseq, (size_t)n * 4)); CU(c, up(b->d_in_tid, v.tid, (size_t)n * 4));
+        CU(c, up(b->d_in_pos, v.pos, (size_t)n * 8)); CU(c, up(b->d_in_alen, v.aligned_len, (size_t)n * 4));
+        CU(c, up(b->d_in_cl, v.clip_left, (size_t)n * 4)); CU(c, up(b->d_in_cr, v.clip_right, (size_t)n * 4));
+        CU(c, cudaMemsetAsync(b->d_hist, 0, (size_t)BIN_KEYS * 4, s2));
+        CU(c, cudaMemsetAsync(b->d_cursor, 0, (size_t)BIN_KEYS * 4, s2));
+        CU(c, cudaMemsetAsync(b->d_stats, 0, 64, s2));
+        BinArgs ba{};
+        ba.seq4 = b->d_in_seq4; ba.seq_off = b->d_in_seq_off; ba.l_qseq = b->d_in_lq; ba.tid = b->d_in_tid; ba.pos = b->d_in_pos;
+        ba.aligned_len = b->d_in_alen; ba.clip_left = b->d_in_cl; ba.clip_right = b->d_in_cr;
+        ba.n = n; ba.seq_total = seq_total; ba.clen = c->d_clen; ba.coff = c->d_coff; ba.n_contigs = c->n_contigs;
+        ba.window = c->p.window_size; ba.min_length = c->p.min_length; ba.flags = c->p.flags;
+        ba.key = b->d_key; ba.tlen = b->d_tlen; ba.start = b->d_start; ba.hist = b->d_hist; ba.stats = b->d_stats;
+        ba.keybase = b->d_keybase; ba.cursor = b->d_cursor; ba.aln = b->d_aln; ba.aln_start = b->d_aln_start;
+        CU(c, launch_bin_classify(ba, s2));
+        CU(c, cudaMemcpyAsync(b->h_hist, b->d_hist, (size_t)BIN_KEYS * 4, cudaMemcpyDeviceToHost, s2));
+        CU(c, cudaMemcpyAsync(b->h_stats, b->d_stats, 64, cudaMemcpyDeviceToHost, s2));
+        CU(c, cudaEventRecord(b->ev_prep, s2));
+        CU(c, cudaEventSynchronize(b->ev_prep));   // the previous batch keeps computing on c->stream meanwhile
+        b->st.host_classify_ms = ms_since(t_begin);
+        if (b->h_stats[6] & 1ull) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
+        if (b->h_stats[6] & 2ull) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: a read's window exceeds 2^31 DP cells (aligned_len too large)");
+        // ---- plan from the histogram ----
+        const auto t_sort = std::chrono::steady_clock::now();
+        n_aln = (int64_t)b->h_stats[1];
+        b->st.cells = (int64_t)b->h_stats[0];
+        int64_t cls_first[N_ROW_CLASSES + 2];
+        std::vector<int32_t> &stl = b->sorted_tlen;
+        stl.resize((size_t)n_aln);
+        int64_t run = 0;
+        for (int rk = 0; rk <= N_ROW_CLASSES; ++rk) {
+            cls_first[rk] = run;
+            const int k0 = rk * (TMAX_FAST + 2), k1 = k0 + (TMAX_FAST + 2);
+            for (int key = k0; key < k1; ++key) {
+                const int32_t cnt = b->h_hist[key];
+                b->h_keybase[key] = (int32_t)run;
+                if (!cnt) continue;
+                const int tl = rk == N_ROW_CLASSES ? (int)b->h_stats[5] : TMAX_FAST - (key - k0);
+                std::fill(stl.begin() + run, stl.begin() + run + cnt, tl);
+                run += cnt;
+            }
+        }
+        cls_first[N_ROW_CLASSES + 1] = run;
+        if (run != n_aln) return fail(c, FADEGPU_E_CUDA, "fadegpu_submit: internal error (histogram does not add up)");
+        {
+            int rc = build_plan(c, b, n_aln, cls_first, stl.data(), std::max(1, (int)b->h_stats[2]), std::max(1, (int)b->h_stats[3]),
+                                std::max(1, (int)b->h_stats[4]), std::max(1, (int)b->h_stats[5]));
+            if (rc) return rc;
+        }
+        b->st.host_sort_ms = ms_since(t_sort);
+        if (n_aln > 0) {
+            CU(c, cudaMemcpyAsync(b->d_keybase, b->h_keybase, (size_t)BIN_KEYS * 4, cudaMemcpyHostToDevice, s2));
+            if (b->n_items > 0)
+                CU(c, cudaMemcpyAsync(b->d_items, b->h_items, (size_t)b->n_items * sizeof(WarpItem), cudaMemcpyHostToDevice, s2));
+            CU(c, launch_bin_scatter(ba, s2));
+        }
+    }
+    CU(c, cudaEventRecord(b->ev_ready, s2));
+    // ---- compute stream ----
+    CU(c, cudaStreamWaitEvent(c->stream, b->ev_ready, 0));
+    CU(c, cudaEventRecord(b->ev[1], c->stream));
+    int nl = 0;
+    { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl); if (rc) return rc; }
+    b->st.kernel_launches = nl + (n > 0 ? 2 : 0) + (n_aln > 0 ? 1 : 0);
+    CU(c, cudaEventRecord(b->ev[2], c->stream));
+    if (n > 0) {
+        CU(c, cudaMemsetAsync(b->d_rflags, 0, (size_t)n, c->stream));
+        CU(c, cudaMemsetAsync(b->d_ridx, 0xff, (size_t)n * 4, c->stream));
+        CU(c, launch_result_index(b->d_out, (int)n_aln, n, b->d_rflags, b->d_ridx, c->stream));
+        CU(c, cudaMemcpyAsync(b->v.flags, b->d_rflags, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(b->h_ridx, b->d_ridx, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (n_aln > 0) {
+        CU(c, cudaMemcpyAsync(b->h_out, b->d_out, (size_t)n_aln * sizeof(AlnOut), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(b->h_aln_start, b->d_aln_start, (size_t)n_aln * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    b->st.h2d_bytes = seq_total + (n + 1) * 8 + n * 28 + (int64_t)BIN_KEYS * 4 + b->n_items * (int64_t)sizeof(WarpItem);
+    b->st.d2h_bytes = n_aln * (int64_t)(sizeof(AlnOut) + 8) + n * 5 + (int64_t)BIN_KEYS * 4 + 64;
+    CU(c, cudaEventRecord(b->ev[3], c->stream));
+    b->in_flight = true;
+    b->st.host_submit_ms = ms_since(t_begin);
+    return FADEGPU_OK;
+}
+
 int fadegpu_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
 {
-    if (!b) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: null batch");
+    if (!c || !b || b->ctx != c) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: bad ctx/batch");
     const fadegpu_batch_view &v = b->v;
-    if (n_reads > 0 && n_reads <= v.max_reads && (v.seq_off[n_reads] < 0 || v.seq_off[n_reads] > v.max_seq_bytes))
+    if (n_reads < 0 || n_reads > v.max_reads) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: n_reads out of range");
+    if (n_reads > 0 && (v.seq_off[n_reads] < 0 || v.seq_off[n_reads] > v.max_seq_bytes))
         return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off[n] exceeds max_seq_bytes");
+    if (!(c->p.flags & FADEGPU_F_HOST_BINNING)) {
+        if (!c->d_two) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: no reference loaded");
+        if (b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: batch already in flight (call fadegpu_wait)");
+        CU(c, cudaSetDevice(c->device));
+        return submit_device_binning(c, b, n_reads);
+    }
     fadegpu_inputs in;
     in.seq4 = v.seq4; in.seq_off = v.seq_off; in.l_qseq = v.l_qseq; in.tid = v.tid; in.pos = v.pos;
     in.aligned_len = v.aligned_len; in.clip_left = v.clip_left; in.clip_right = v.clip_right;
@@ -861,11 +1057,29 @@ int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
     const auto t_scatter = std::chrono::steady_clock::now();
     fadegpu_batch_view &v = b->v;
     const int64_t n = b->n_reads;
-    memset(v.flags, 0, (size_t)n);   // the other per-read outputs are defined only where FADEGPU_R_ALIGNED is set
-    memset(b->h_ridx, 0xff, (size_t)n * sizeof(int32_t));
     int bad = 0;
     const int nthr = std::max(1, c->host_threads);
-    const bool scatter = !(c->p.flags & FADEGPU_F_NO_SCATTER);
+    const bool scatter = !(c->p.flags & FADEGPU_F_NO_SCATTER) && v.score != nullptr;
+    if (b->dev_binning) {
+        // flags[] and the result index were produced on the device; only validate (and, unless
+        // FADEGPU_F_NO_SCATTER, fill the per-read arrays)
+#pragma omp parallel for schedule(static) reduction(| : bad) num_threads(nthr)
+        for (int64_t k = 0; k < b->n_aln; ++k) {
+            const AlnOut &o = b->h_out[k];
+            const int64_t r = o.read;
+            if (r < 0 || r >= n || (o.flags & 0x80000000u) || b->h_ridx[r] != (int32_t)k) { bad = 1; continue; }
+            if (!scatter) continue;
+            v.score[r] = o.score; v.beg_query[r] = o.beg_query; v.end_query[r] = o.end_query;
+            v.beg_ref[r] = o.beg_ref; v.end_ref[r] = o.end_ref; v.n_ops[r] = o.n_ops;
+            v.win_start[r] = b->h_aln_start[k];
+            memcpy(v.ops + (size_t)r * FADEGPU_MAX_OPS, o.ops, sizeof(o.ops));
+        }
+        b->st.host_wait_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_scatter).count();
+        if (bad) return fail(c, FADEGPU_E_CUDA, "fadegpu_wait: a kernel did not produce a result record (internal error)");
+        return FADEGPU_OK;
+    }
+    memset(v.flags, 0, (size_t)n);   // the other per-read outputs are defined only where FADEGPU_R_ALIGNED is set
+    memset(b->h_ridx, 0xff, (size_t)n * sizeof(int32_t));
 #pragma omp parallel for schedule(static) reduction(| : bad) num_threads(nthr)
     for (int64_t k = 0; k < b->n_aln; ++k) {
         const AlnOut &o = b->h_out[k];
@@ -891,7 +1105,7 @@ int fadegpu_get_results(const fadegpu_batch *b, fadegpu_results_view *r)
     static_assert(sizeof(fadegpu_result) == sizeof(AlnOut), "fadegpu_result must mirror AlnOut");
     r->n_results = b->n_aln;
     r->results = reinterpret_cast<const fadegpu_result *>(b->h_out);
-    r->win_start = b->aln_start.data();
+    r->win_start = b->dev_binning ? b->h_aln_start : b->aln_start.data();
     r->result_index = b->h_ridx;
     return FADEGPU_OK;
 }

@@ -694,6 +694,100 @@ __global__ void __launch_bounds__(128) sw_generic_kernel(const GenericArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// binning on the device (submits from the pinned view): the per-read part of align_clip that the
+// host path evaluates while building descriptors -- length floor (analysis.d:34), window
+// arithmetic (analysis.d:45-59) -- plus the length binning, without touching host cores
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bin_classify_kernel(const BinArgs a)
+{
+    const uint32_t floor_u = (uint32_t)a.min_length;   // uint <= int compare of analysis.d:34
+    unsigned long long cells = 0, bad = 0;
+    int qmax = 0, tmax = 0, qmax_g = 0, tmax_g = 0, cnt = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (int64_t)gridDim.x * blockDim.x) {
+        int key = -1;
+        const uint32_t cl = (uint32_t)a.clip_left[r], cr = (uint32_t)a.clip_right[r];
+        const bool need = (cl != 0 && !(cl <= floor_u)) || (cr != 0 && !(cr <= floor_u));
+        if (need) {
+            const int tid = a.tid[r], ql = a.l_qseq[r];
+            if (tid >= 0 && tid < a.n_contigs && ql > 0) {
+                const int64_t so = a.seq_off[r];
+                if (so < 0 || so + (ql + 1) / 2 > a.seq_total) bad |= 1ull;
+                else {
+                    int64_t start = a.pos[r] - a.window;
+                    if (start < 0) start = 0;
+                    int64_t end = a.pos[r] + (int64_t)a.aligned_len[r] + a.window;
+                    if (end > a.clen[tid]) end = a.clen[tid];
+                    if (end > start) {
+                        if (end - start > 0x7fffffff || (end - start) * (int64_t)ql > ((int64_t)1 << 31)) bad |= 2ull;
+                        else {
+                            const int tl = (int)(end - start);
+                            const int rk = bin_rank(ql, tl, (a.flags & 1u) != 0);
+                            key = bin_key(rk, tl);
+                            a.tlen[r] = tl;
+                            a.start[r] = start;
+                            atomicAdd(&a.hist[key], 1);
+                            cells += (unsigned long long)ql * (unsigned long long)tl;
+                            ++cnt;
+                            qmax = max(qmax, ql); tmax = max(tmax, tl);
+                            if (rk == N_ROW_CLASSES) { qmax_g = max(qmax_g, ql); tmax_g = max(tmax_g, tl); }
+                        }
+                    }
+                }
+            }
+        }
+        a.key[r] = key;
+    }
+    // one set of atomics per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cells += __shfl_xor_sync(FULL, cells, o);
+        bad |= __shfl_xor_sync(FULL, bad, o);
+        cnt += __shfl_xor_sync(FULL, cnt, o);
+        qmax = max(qmax, __shfl_xor_sync(FULL, qmax, o)); tmax = max(tmax, __shfl_xor_sync(FULL, tmax, o));
+        qmax_g = max(qmax_g, __shfl_xor_sync(FULL, qmax_g, o)); tmax_g = max(tmax_g, __shfl_xor_sync(FULL, tmax_g, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (cells) atomicAdd(&a.stats[0], cells);
+        if (cnt) atomicAdd(&a.stats[1], (unsigned long long)cnt);
+        if (qmax) atomicMax(&a.stats[2], (unsigned long long)qmax);
+        if (tmax) atomicMax(&a.stats[3], (unsigned long long)tmax);
+        if (qmax_g) atomicMax(&a.stats[4], (unsigned long long)qmax_g);
+        if (tmax_g) atomicMax(&a.stats[5], (unsigned long long)tmax_g);
+        if (bad) atomicOr(&a.stats[6], bad);
+    }
+}
+
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const BinArgs a)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int key = a.key[r];
+        if (key < 0) continue;
+        const int slot = a.keybase[key] + atomicAdd(&a.cursor[key], 1);
+        AlnDesc d;
+        d.gstart = a.coff[a.tid[r]] + a.start[r];
+        d.seq_off = a.seq_off[r];
+        d.tlen = a.tlen[r];
+        d.qlen = a.l_qseq[r];
+        d.clip_left = (uint32_t)a.clip_left[r];
+        d.clip_right = (uint32_t)a.clip_right[r];
+        d.read = (int32_t)r;
+        d.pad = 0;
+        a.aln[slot] = d;
+        a.aln_start[slot] = a.start[r];
+    }
+}
+
+// per-read flags and index into the compact results (what fadegpu_wait scatters on the host path)
+__global__ void __launch_bounds__(256) result_index_kernel(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_aln; k += gridDim.x * blockDim.x) {
+        const int r = out[k].read;
+        const uint32_t f = out[k].flags;
+        if (r >= 0 && (int64_t)r < n_reads && !(f & 0x80000000u)) { flags[r] = (uint8_t)(f & 0xffu); ridx[r] = k; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // INT16x2 ALU issue-rate microbenchmark: 8 independent VIADDMNMX.S16x2 chains per thread
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) alu_peak_kernel(uint32_t *out, int iters)
@@ -809,6 +903,29 @@ size_t trace_tile_bytes(int R)
     case 32: return (size_t)tile_words<32>() * 4;
     default: return (size_t)tile_words<38>() * 4;
     }
+}
+
+cudaError_t launch_bin_classify(const BinArgs &a, cudaStream_t s)
+{
+    if (a.n <= 0) return cudaSuccess;
+    const int grid = (int)std::min<int64_t>((a.n + 255) / 256, 148 * 16);
+    bin_classify_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bin_scatter(const BinArgs &a, cudaStream_t s)
+{
+    if (a.n <= 0) return cudaSuccess;
+    const int grid = (int)std::min<int64_t>((a.n + 255) / 256, 148 * 16);
+    bin_scatter_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_result_index(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx, cudaStream_t s)
+{
+    if (n_aln <= 0) return cudaSuccess;
+    result_index_kernel<<<std::min((n_aln + 255) / 256, 148 * 8), 256, 0, s>>>(out, n_aln, n_reads, flags, ridx);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_generic(const GenericArgs &a, int n_slots, cudaStream_t s)

@@ -82,10 +82,37 @@ struct GenericArgs {
     int32_t open, extend, match, mismatch, min_length;
 };
 
+// ---- binning on the device (pinned-view submits): classify reads, histogram by (class, window
+//      length), scatter the alignment descriptors into sorted order ----
+struct BinArgs {
+    // device mirrors of the batch inputs
+    const uint8_t *seq4;
+    const int64_t *seq_off;
+    const int32_t *l_qseq, *tid;
+    const int64_t *pos;
+    const int32_t *aligned_len, *clip_left, *clip_right;
+    int64_t n, seq_total;
+    const int64_t *clen, *coff;     // contig lengths / global base offsets
+    int32_t n_contigs, window, min_length;
+    uint32_t flags;                 // FADEGPU_F_*
+    // classify outputs
+    int32_t *key;                   // [n] sort key, -1 = no SW for this read
+    int32_t *tlen;                  // [n]
+    int64_t *start;                 // [n] window start inside the contig
+    int32_t *hist;                  // [BIN_KEYS]
+    unsigned long long *stats;      // [8] cells, n_aln, qmax_all, tmax_all, qmax_generic, tmax_generic, bad
+    // scatter
+    const int32_t *keybase;         // [BIN_KEYS] first sorted position of each key
+    int32_t *cursor;                // [BIN_KEYS]
+    AlnDesc *aln;
+    int64_t *aln_start;
+};
+
 constexpr int FILL_THREADS = 128;
 // row classes: R rows per thread x 8 threads cover reads of up to 104 / 152 / 200 / 256 / 304 bases
 constexpr int N_ROW_CLASSES = 5;
-constexpr int ROW_CLASSES[N_ROW_CLASSES] = { 13, 19, 25, 32, 38 };
+__host__ __device__ constexpr int row_class(int k) { return k == 0 ? 13 : k == 1 ? 19 : k == 2 ? 25 : k == 3 ? 32 : 38; }
+constexpr int ROW_CLASSES[N_ROW_CLASSES] = { row_class(0), row_class(1), row_class(2), row_class(3), row_class(4) };
 constexpr int QMAX_FAST = FG * 38;   // rows covered by the largest packed instantiation
 constexpr int TMAX_FAST = 4000;      // window length covered by the packed kernels
 
@@ -93,6 +120,18 @@ size_t fill_smem_bytes(int tw_stride);
 size_t trace_tile_bytes(int R);
 int tw_stride_for(int nblk_max);
 
+constexpr int BIN_KEYS = (N_ROW_CLASSES + 1) * (TMAX_FAST + 2);
+// sort key: class rank (ROW_CLASSES order, then the generic list) and descending window length
+__host__ __device__ inline int bin_key(int rank, int tlen) { return rank * (TMAX_FAST + 2) + (rank == N_ROW_CLASSES ? 0 : TMAX_FAST - tlen); }
+__host__ __device__ inline int bin_rank(int qlen, int tlen, bool force_generic)
+{
+    if (force_generic || qlen > QMAX_FAST || tlen > TMAX_FAST) return N_ROW_CLASSES;
+    for (int k = 0; k < N_ROW_CLASSES; ++k) if (qlen <= FG * row_class(k)) return k;
+    return N_ROW_CLASSES;
+}
+cudaError_t launch_bin_classify(const BinArgs &a, cudaStream_t s);
+cudaError_t launch_bin_scatter(const BinArgs &a, cudaStream_t s);
+cudaError_t launch_result_index(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx, cudaStream_t s);
 cudaError_t launch_fill(int R, const KernelArgs &a, cudaStream_t s);
 cudaError_t launch_trace(int R, const KernelArgs &a, cudaStream_t s, int sm_count, int *launches);
 cudaError_t launch_generic(const GenericArgs &a, int n_slots, cudaStream_t s);

@@ -66,6 +66,8 @@ typedef struct fadegpu_params {
 #define FADEGPU_F_FORCE_GENERIC 1u /* route every alignment through the generic (slow) kernel */
 #define FADEGPU_F_NO_SHORTCUT 8u   /* traceback: always replay blocks, never use the ungapped-diagonal proof
                                       (A/B switch; results are identical) */
+#define FADEGPU_F_HOST_BINNING 16u  /* fadegpu_submit: bin the reads on the host (as fadegpu_submit_inputs
+                                      does) instead of uploading the pinned view and binning on the device */
 #define FADEGPU_F_NO_SCATTER 2u    /* fadegpu_wait fills only flags[] and the compact results
                                       (fadegpu_get_results), not the other per-read output arrays */
 
@@ -90,7 +92,8 @@ typedef struct fadegpu_batch_view {
     int32_t *clip_left;   /* [n] parse_clips(rec.cigar)[0].length, 0 = none or early-out record */
     int32_t *clip_right;  /* [n] parse_clips(rec.cigar)[1].length */
     /* ---- outputs: flags is written for every read; all the others are defined only for reads
-     *      whose flags have FADEGPU_R_ALIGNED set ---- */
+     *      whose flags have FADEGPU_R_ALIGNED set, and are NULL (not allocated) when the ctx was
+     *      created with FADEGPU_F_NO_SCATTER: use fadegpu_get_results then ---- */
     uint8_t *flags;       /* [n] FADEGPU_R_* */
     int32_t *score;       /* [n] res.score */
     int32_t *beg_query;   /* [n] */
@@ -141,7 +144,10 @@ int fadegpu_alloc_batch(fadegpu_ctx *ctx, int64_t max_reads, int64_t max_seq_byt
 int fadegpu_get_batch_view(fadegpu_batch *b, fadegpu_batch_view *view);
 void fadegpu_free_batch(fadegpu_batch *b);
 
-/* Asynchronous: host binning, H2D, kernels and D2H are queued on the ctx stream. */
+/* Asynchronous.  The per-read arrays of the pinned view are DMA'd to the device as they are and the
+ * binning (length floor, windows, sort by window length) runs on the GPU; the host only turns a
+ * small histogram into the launch plan.  Uploads and binning of one batch overlap with the kernels
+ * of the previous one. */
 int fadegpu_submit(fadegpu_ctx *ctx, fadegpu_batch *b, int64_t n_reads);
 
 /* Same, reading the inputs from caller-owned host arrays (pageable is fine: the library gathers
