@@ -9,9 +9,12 @@ min-length), processed as chunks of --chunk reads through the C ABI (libfadegpu.
 
   value  reads/s with the chunk's inputs already resident in HBM: CUDA-event time of ALL kernel
          launches of the chunk (fadegpu_replay_kernels), summed over the chunks of a step.
-  e2e    reads/s through the public C ABI with HOST buffers: per chunk fadegpu_submit_inputs reads
-         the caller's host arrays (host binning + gather into pinned staging + H2D + kernels +
-         D2H) and fadegpu_wait scatters the results; double-buffered; the flags are read back.
+  e2e    reads/s through the public C ABI with HOST buffers.  --e2e-path view (default): every
+         chunk's records sit in the pinned host view of its batch (where the caller's BAM reader
+         writes them); per chunk fadegpu_submit copies them to the device,
+         bins them there, runs the kernels and copies the results back; fadegpu_wait +
+         fadegpu_get_results hand them to the host, which reads them.  --e2e-path arrays:
+         fadegpu_submit_inputs on pageable caller arrays (host binning + gather into staging).
   roofline  the INT16x2 ALU roofline of SURVEY.md 8(d): cells/s against 2*R_alu/9 with R_alu
          measured live by fadegpu_measure_alu_peak (packed VIADDMNMX.S16x2 issue rate).
   cpu_baseline  a CPU port of the path (oracle/fade_oracle_simd.c: AVX2, 16 alignments per vector,
@@ -56,6 +59,9 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=CHUNK)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="reads in the cpu_baseline sample")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
+    ap.add_argument("--e2e-path", default="view", choices=["view", "arrays"],
+                    help="view = fadegpu_submit from the pinned batch views (binning on the device); "
+                         "arrays = fadegpu_submit_inputs from pageable arrays (binning on the host)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2 = BASELINE configs[1] (default, the bench line); c4 = stress sweep configs[3]: 2x250 reads, "
                          "--window-size 1000, clip law U{1..40} (use with --reads 2000000)")
@@ -244,7 +250,8 @@ def main():
     chunk = min(args.chunk, n)
     bounds = [(a, min(n, a + chunk)) for a in range(0, n, chunk)]
     stride = (cfg.read_len + 1) // 2
-    batches = [ctx.alloc_batch(chunk, chunk * stride) for _ in range(2)]
+    view_path = args.e2e_path == "view"
+    batches = [ctx.alloc_batch(chunk, chunk * stride) for _ in range(len(bounds) if view_path else 2)]
 
     def load_chunk(b, a, e):
         m = e - a
@@ -260,12 +267,19 @@ def main():
 
     agg = {"aligned": 0, "cells": 0, "h2d": 0, "d2h": 0, "launches": 0, "generic": 0, "art": 0}
 
+    if view_path:       # the host side of every chunk: its records in the pinned view of its batch
+        for b, (a, e) in zip(batches, bounds):
+            load_chunk(b, a, e)
+
     def kernel_step(collect: bool):
         """inputs resident: per chunk upload untimed, then time only the kernels (CUDA events)."""
         ms = fill = trace = gen = 0.0
-        for (a, e) in bounds:
-            b = batches[0]
-            load_chunk(b, a, e)
+        for i, (a, e) in enumerate(bounds):
+            if view_path:
+                b = batches[i]
+            else:
+                b = batches[0]
+                load_chunk(b, a, e)
             b.run()                          # untimed: makes the chunk resident in HBM
             ms += b.replay_kernels(1)        # timed on the ctx stream with CUDA events
             st = b.stats()
@@ -288,17 +302,29 @@ def main():
         pending = None
         acc = 0
         for i, (a, e) in enumerate(bounds):
-            b = batches[i & 1]
-            # host buffers (pageable numpy arrays) -> C ABI; seq_off holds absolute offsets into seq4
-            b.submit_arrays(e - a, rd.seq4, rd.seq_off[a:], rd.l_qseq[a:], rd.tid[a:], rd.pos[a:],
-                            rd.aligned_len[a:], rd.clip_left[a:], rd.clip_right[a:])
+            if view_path:
+                b = batches[i]
+                b.submit(e - a)              # pinned host view -> device, binning on the device
+            else:
+                b = batches[i & 1]
+                # host buffers (pageable numpy arrays) -> C ABI; seq_off holds absolute offsets into seq4
+                b.submit_arrays(e - a, rd.seq4, rd.seq_off[a:], rd.l_qseq[a:], rd.tid[a:], rd.pos[a:],
+                                rd.aligned_len[a:], rd.clip_left[a:], rd.clip_right[a:])
             if pending is not None:
                 pending.wait()
                 acc += consume(pending)
+                note_copies(pending)
             pending = b
         pending.wait()
         acc += consume(pending)
+        note_copies(pending)
         return time.perf_counter() - t0, acc
+
+    copies = {"h2d": 0, "d2h": 0}
+
+    def note_copies(b):
+        st = b.stats()
+        copies["h2d"] += st.h2d_bytes; copies["d2h"] += st.d2h_bytes
 
     host_ms = {}
 
@@ -325,6 +351,7 @@ def main():
     e_s = 0.0
     for s in range(args.steps):
         barrier()
+        copies["h2d"] = copies["d2h"] = 0
         dt, _ = e2e_step()
         e_s += dt
     barrier()
@@ -358,9 +385,9 @@ def main():
             "gcups": total_cells / (ms_per_step * 1e-3) / 1e9,
             "aligned_reads_per_step": total_aligned, "artifact_reads_rank0": agg["art"],
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": agg["h2d"],
-                    "d2h_bytes_per_step": agg["d2h"], "ms_per_step": 1e3 * e_s_max / args.steps,
-                    "host_threads_per_rank": host_threads,
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": copies["h2d"],
+                    "d2h_bytes_per_step": copies["d2h"], "ms_per_step": 1e3 * e_s_max / args.steps,
+                    "host_threads_per_rank": host_threads, "path": args.e2e_path,
                     "host_ms_last_chunks": {kx: round(v, 3) for kx, v in host_ms.items()}},
             "gpu_launches": agg["launches"] * args.steps,
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "GCUPS",

@@ -57,6 +57,7 @@ struct fadegpu_ctx {
     int sm_count = 148;
     int host_threads = 1;
     cudaStream_t stream2 = nullptr;      // uploads + binning of the next batch while the previous one computes
+    cudaStream_t stream3 = nullptr;      // result copies to the host, off the compute stream
     int64_t *d_clen = nullptr, *d_coff = nullptr;   // contig tables for the device-side binning
     std::string err;
 };
@@ -113,7 +114,7 @@ struct fadegpu_batch {
     int32_t *h_hist = nullptr, *h_keybase = nullptr;   // pinned
     unsigned long long *h_stats = nullptr;            // pinned
     int64_t *h_aln_start = nullptr;                   // pinned
-    cudaEvent_t ev_prep = nullptr, ev_ready = nullptr;
+    cudaEvent_t ev_prep = nullptr, ev_ready = nullptr, ev_done = nullptr;
 };
 
 namespace {
@@ -469,7 +470,8 @@ int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_cursor, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&c->d_alu, 64)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, -1)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, -1)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "fadegpu_create");
         delete c;
@@ -485,6 +487,7 @@ void fadegpu_destroy(fadegpu_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
     free_reference(c);
     free_dev(c->d_ck); free_dev(c->d_gen); free_dev(c->d_cursor); free_dev(c->d_alu); free_dev(c->d_trace); free_dev(c->d_qcount);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -617,7 +620,7 @@ void fadegpu_free_batch(fadegpu_batch *b)
 {
     if (!b) return;
     fadegpu_ctx *c = b->ctx;
-    if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); if (c->stream2) cudaStreamSynchronize(c->stream2); }
+    if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); if (c->stream2) cudaStreamSynchronize(c->stream2); if (c->stream3) cudaStreamSynchronize(c->stream3); }
     fadegpu_batch_view &v = b->v;
     free_host(v.seq4); free_host(v.seq_off); free_host(v.l_qseq); free_host(v.tid); free_host(v.pos);
     free_host(v.aligned_len); free_host(v.clip_left); free_host(v.clip_right);
@@ -633,6 +636,7 @@ void fadegpu_free_batch(fadegpu_batch *b)
     free_host(b->h_hist); free_host(b->h_keybase); free_host(b->h_stats); free_host(b->h_aln_start);
     if (b->ev_prep) cudaEventDestroy(b->ev_prep);
     if (b->ev_ready) cudaEventDestroy(b->ev_ready);
+    if (b->ev_done) cudaEventDestroy(b->ev_done);
     for (auto &e : b->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     delete b;
 }
@@ -677,6 +681,7 @@ int fadegpu_alloc_batch(fadegpu_ctx *c, int64_t max_reads, int64_t max_seq_bytes
     H(&b->h_hist, (size_t)BIN_KEYS * 4); H(&b->h_keybase, (size_t)BIN_KEYS * 4); H(&b->h_stats, 64); H(&b->h_aln_start, n * 8);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_prep);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_ready);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
     for (auto &ev : b->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e != cudaSuccess) {
         int rc = cuda_fail(c, e, "fadegpu_alloc_batch");
@@ -892,23 +897,29 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     const int64_t n_items = b->n_items;
 
     // ---- 5. queue copies and kernels ----
-    CU(c, cudaEventRecord(b->ev[0], c->stream));
+    // copies in on stream2, kernels on the compute stream, copies out on stream3: the DMA of one
+    // batch overlaps the kernels of its neighbours
+    CU(c, cudaEventRecord(b->ev[0], c->stream2));
     if (n_aln > 0) {
-        CU(c, cudaMemcpyAsync(b->d_aln, b->h_aln, (size_t)n_aln * sizeof(AlnDesc), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(b->d_aln, b->h_aln, (size_t)n_aln * sizeof(AlnDesc), cudaMemcpyHostToDevice, c->stream2));
         if (n_items > 0)
-            CU(c, cudaMemcpyAsync(b->d_items, b->h_items, (size_t)n_items * sizeof(WarpItem), cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaMemcpyAsync(b->d_seq, b->h_seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
+            CU(c, cudaMemcpyAsync(b->d_items, b->h_items, (size_t)n_items * sizeof(WarpItem), cudaMemcpyHostToDevice, c->stream2));
+        CU(c, cudaMemcpyAsync(b->d_seq, b->h_seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream2));
     }
     b->st.h2d_bytes = n_aln * (int64_t)sizeof(AlnDesc) + n_items * (int64_t)sizeof(WarpItem) + seq_bytes;
+    CU(c, cudaEventRecord(b->ev_ready, c->stream2));
+    CU(c, cudaStreamWaitEvent(c->stream, b->ev_ready, 0));
     CU(c, cudaEventRecord(b->ev[1], c->stream));
     int nl = 0;
     { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl); if (rc) return rc; }
     b->st.kernel_launches = nl;
     CU(c, cudaEventRecord(b->ev[2], c->stream));
+    CU(c, cudaEventRecord(b->ev_done, c->stream));
+    CU(c, cudaStreamWaitEvent(c->stream3, b->ev_done, 0));
     if (n_aln > 0)
-        CU(c, cudaMemcpyAsync(b->h_out, b->d_out, (size_t)n_aln * sizeof(AlnOut), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(b->h_out, b->d_out, (size_t)n_aln * sizeof(AlnOut), cudaMemcpyDeviceToHost, c->stream3));
     b->st.d2h_bytes = n_aln * (int64_t)sizeof(AlnOut);
-    CU(c, cudaEventRecord(b->ev[3], c->stream));
+    CU(c, cudaEventRecord(b->ev[3], c->stream3));
     b->in_flight = true;
     b->st.host_submit_ms = ms_since(t_begin);
     return FADEGPU_OK;
@@ -998,6 +1009,10 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n)
             CU(c, launch_bin_scatter(ba, s2));
         }
     }
+    if (n > 0) {
+        CU(c, cudaMemsetAsync(b->d_rflags, 0, (size_t)n, s2));
+        CU(c, cudaMemsetAsync(b->d_ridx, 0xff, (size_t)n * 4, s2));
+    }
     CU(c, cudaEventRecord(b->ev_ready, s2));
     // ---- compute stream ----
     CU(c, cudaStreamWaitEvent(c->stream, b->ev_ready, 0));
@@ -1006,20 +1021,21 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n)
     { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl); if (rc) return rc; }
     b->st.kernel_launches = nl + (n > 0 ? 2 : 0) + (n_aln > 0 ? 1 : 0);
     CU(c, cudaEventRecord(b->ev[2], c->stream));
+    if (n > 0) CU(c, launch_result_index(b->d_out, (int)n_aln, n, b->d_rflags, b->d_ridx, c->stream));
+    CU(c, cudaEventRecord(b->ev_done, c->stream));
+    cudaStream_t s3 = c->stream3;                    // results go home while the next batch computes
+    CU(c, cudaStreamWaitEvent(s3, b->ev_done, 0));
     if (n > 0) {
-        CU(c, cudaMemsetAsync(b->d_rflags, 0, (size_t)n, c->stream));
-        CU(c, cudaMemsetAsync(b->d_ridx, 0xff, (size_t)n * 4, c->stream));
-        CU(c, launch_result_index(b->d_out, (int)n_aln, n, b->d_rflags, b->d_ridx, c->stream));
-        CU(c, cudaMemcpyAsync(b->v.flags, b->d_rflags, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaMemcpyAsync(b->h_ridx, b->d_ridx, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(b->v.flags, b->d_rflags, (size_t)n, cudaMemcpyDeviceToHost, s3));
+        CU(c, cudaMemcpyAsync(b->h_ridx, b->d_ridx, (size_t)n * 4, cudaMemcpyDeviceToHost, s3));
     }
     if (n_aln > 0) {
-        CU(c, cudaMemcpyAsync(b->h_out, b->d_out, (size_t)n_aln * sizeof(AlnOut), cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaMemcpyAsync(b->h_aln_start, b->d_aln_start, (size_t)n_aln * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(b->h_out, b->d_out, (size_t)n_aln * sizeof(AlnOut), cudaMemcpyDeviceToHost, s3));
+        CU(c, cudaMemcpyAsync(b->h_aln_start, b->d_aln_start, (size_t)n_aln * 8, cudaMemcpyDeviceToHost, s3));
     }
     b->st.h2d_bytes = seq_total + (n + 1) * 8 + n * 28 + (int64_t)BIN_KEYS * 4 + b->n_items * (int64_t)sizeof(WarpItem);
     b->st.d2h_bytes = n_aln * (int64_t)(sizeof(AlnOut) + 8) + n * 5 + (int64_t)BIN_KEYS * 4 + 64;
-    CU(c, cudaEventRecord(b->ev[3], c->stream));
+    CU(c, cudaEventRecord(b->ev[3], s3));
     b->in_flight = true;
     b->st.host_submit_ms = ms_since(t_begin);
     return FADEGPU_OK;
