@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=CHUNK)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="reads in the cpu_baseline sample")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
+    ap.add_argument("--depth", type=int, default=3, help="chunks in flight in the e2e loop (view path)")
     ap.add_argument("--e2e-path", default="view", choices=["view", "arrays"],
                     help="view = fadegpu_submit from the pinned batch views (binning on the device); "
                          "arrays = fadegpu_submit_inputs from pageable arrays (binning on the host)")
@@ -294,18 +295,29 @@ def main():
     def consume(b):
         """read the step's results on the host: rs-relevant flags of every read + the compact records"""
         rec, ws, ridx = b.results()
-        return int(b.flags[: b.n].sum()) + int(rec["score"].sum()) + len(ws)
+        m8 = b.n & ~7                        # every flag byte, eight at a time
+        return int(b.flags[:m8].view(np.uint64).sum(dtype=np.uint64) & 0xffff) + int(b.flags[m8: b.n].sum()) \
+            + int(rec["score"].sum()) + len(ws)
 
     def e2e_step():
         """host buffers -> C ABI -> host results, double-buffered; wall clock around the whole step."""
         t0 = time.perf_counter()
         pending = None
         acc = 0
+        if view_path:
+            # pinned host views -> device (binning there) -> host results; fadegpu_submit only queues,
+            # so up to --depth chunks are in flight while the host reads the results of the oldest
+            issued = 0
+            for i in range(len(bounds)):
+                while issued < min(len(bounds), i + args.depth):
+                    batches[issued].submit(bounds[issued][1] - bounds[issued][0])
+                    issued += 1
+                batches[i].wait()
+                acc += consume(batches[i])
+                note_copies(batches[i])
+            return time.perf_counter() - t0, acc
         for i, (a, e) in enumerate(bounds):
-            if view_path:
-                b = batches[i]
-                b.submit(e - a)              # pinned host view -> device, binning on the device
-            else:
+            if True:
                 b = batches[i & 1]
                 # host buffers (pageable numpy arrays) -> C ABI; seq_off holds absolute offsets into seq4
                 b.submit_arrays(e - a, rd.seq4, rd.seq_off[a:], rd.l_qseq[a:], rd.tid[a:], rd.pos[a:],

@@ -15,6 +15,7 @@ F_FORCE_GENERIC = 1
 F_NO_SCATTER = 2
 F_NO_SHORTCUT = 8
 F_HOST_BINNING = 16
+F_SYNC_SUBMIT = 32
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_query", "<i4"), ("end_ref", "<i4"), ("beg_query", "<i4"),
                          ("beg_ref", "<i4"), ("n_ops", "<i4"), ("flags", "<u4"), ("read", "<i4"),
                          ("ops", "<u4", (32,))])

@@ -12,6 +12,10 @@
 #include <cstring>
 #include <new>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 #ifdef _OPENMP
@@ -60,6 +64,14 @@ struct fadegpu_ctx {
     cudaStream_t stream3 = nullptr;      // result copies to the host, off the compute stream
     int64_t *d_clen = nullptr, *d_coff = nullptr;   // contig tables for the device-side binning
     std::string err;
+    // asynchronous submits: fadegpu_submit queues the batch, this thread waits for the binning
+    // histogram, plans and launches; the caller goes on filling / reading other batches
+    std::thread worker;
+    std::mutex q_mu;
+    std::condition_variable q_cv, done_cv;
+    std::deque<std::pair<fadegpu_batch *, int64_t>> jobs;
+    bool worker_stop = false, worker_busy = false;
+    std::mutex submit_mu;                 // one submit body at a time (they size shared scratch and order the streams)
 };
 
 struct AlnTmp {       // a read that needs SW, captured in read order (sequential pass), before sorting
@@ -114,13 +126,29 @@ struct fadegpu_batch {
     int32_t *h_hist = nullptr, *h_keybase = nullptr;   // pinned
     unsigned long long *h_stats = nullptr;            // pinned
     int64_t *h_aln_start = nullptr;                   // pinned
+    // reads that pass the length floor, gathered by the host in read order (pinned, allocated on first use)
+    uint8_t *h_c_seq4 = nullptr;
+    int64_t *h_c_seq_off = nullptr, *h_c_pos = nullptr;
+    int32_t *h_c_lq = nullptr, *h_c_tid = nullptr, *h_c_alen = nullptr, *h_c_cl = nullptr, *h_c_cr = nullptr, *h_c_read = nullptr;
+    int32_t *d_in_read = nullptr;
+    int64_t n_c = 0, seq_c = 0;                        // gathered reads / their sequence bytes
+    bool job_gather = false;                           // the queued submit still has to gather from the view
     cudaEvent_t ev_prep = nullptr, ev_ready = nullptr, ev_done = nullptr;
+    // asynchronous submit (guarded by ctx->q_mu)
+    bool queued = false;
+    int submit_rc = 0;
+    std::string submit_err;
 };
+
+extern "C" { static void drain_submits(fadegpu_ctx *c); }
 
 namespace {
 
+std::mutex g_err_mu;
+
 int fail(fadegpu_ctx *ctx, int code, const std::string &msg)
 {
+    std::lock_guard<std::mutex> g(g_err_mu);
     if (ctx) ctx->err = msg;
     g_last_error = msg;
     return code;
@@ -484,6 +512,11 @@ int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
 void fadegpu_destroy(fadegpu_ctx *c)
 {
     if (!c) return;
+    if (c->worker.joinable()) {
+        { std::lock_guard<std::mutex> lk(c->q_mu); c->worker_stop = true; }
+        c->q_cv.notify_all();
+        c->worker.join();                 // finishes the queued submits first
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
@@ -499,6 +532,8 @@ int fadegpu_load_reference(fadegpu_ctx *c, int32_t n_contigs, const char *const 
 {
     if (!c) return fail(nullptr, FADEGPU_E_ARG, "fadegpu_load_reference: null ctx");
     if (n_contigs <= 0 || !lengths || !seqs) return fail(c, FADEGPU_E_ARG, "fadegpu_load_reference: bad arguments");
+    drain_submits(c);
+    std::lock_guard<std::mutex> submit_guard(c->submit_mu);
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
     free_reference(c);
@@ -586,6 +621,8 @@ int fadegpu_share_reference(fadegpu_ctx *dst, const fadegpu_ctx *src)
 {
     if (!dst || !src) return fail(dst, FADEGPU_E_ARG, "fadegpu_share_reference: null ctx");
     if (!src->d_two) return fail(dst, FADEGPU_E_STATE, "fadegpu_share_reference: source has no reference");
+    drain_submits(dst);
+    std::lock_guard<std::mutex> submit_guard(dst->submit_mu);
     CU(dst, cudaSetDevice(dst->device));
     CU(dst, cudaStreamSynchronize(dst->stream));
     free_reference(dst);
@@ -620,6 +657,7 @@ void fadegpu_free_batch(fadegpu_batch *b)
 {
     if (!b) return;
     fadegpu_ctx *c = b->ctx;
+    if (c) { std::unique_lock<std::mutex> lk(c->q_mu); c->done_cv.wait(lk, [&] { return !b->queued; }); }
     if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); if (c->stream2) cudaStreamSynchronize(c->stream2); if (c->stream3) cudaStreamSynchronize(c->stream3); }
     fadegpu_batch_view &v = b->v;
     free_host(v.seq4); free_host(v.seq_off); free_host(v.l_qseq); free_host(v.tid); free_host(v.pos);
@@ -634,6 +672,8 @@ void fadegpu_free_batch(fadegpu_batch *b)
     free_dev(b->d_aln_start); free_dev(b->d_hist); free_dev(b->d_keybase); free_dev(b->d_cursor); free_dev(b->d_ridx);
     free_dev(b->d_rflags); free_dev(b->d_stats);
     free_host(b->h_hist); free_host(b->h_keybase); free_host(b->h_stats); free_host(b->h_aln_start);
+    free_host(b->h_c_seq4); free_host(b->h_c_seq_off); free_host(b->h_c_pos); free_host(b->h_c_lq); free_host(b->h_c_tid);
+    free_host(b->h_c_alen); free_host(b->h_c_cl); free_host(b->h_c_cr); free_host(b->h_c_read); free_dev(b->d_in_read);
     if (b->ev_prep) cudaEventDestroy(b->ev_prep);
     if (b->ev_ready) cudaEventDestroy(b->ev_ready);
     if (b->ev_done) cudaEventDestroy(b->ev_done);
@@ -674,6 +714,7 @@ int fadegpu_alloc_batch(fadegpu_ctx *c, int64_t max_reads, int64_t max_seq_bytes
     D(&b->d_fillres, (size_t)b->cap_items * 32 * sizeof(uint2));
     // device-side binning: mirrors of the inputs, keys, histogram, per-read result index
     D(&b->d_in_seq4, (size_t)max_seq_bytes + 16); D(&b->d_in_seq_off, (n + 1) * 8); D(&b->d_in_pos, n * 8);
+    D(&b->d_in_read, n * 4);
     D(&b->d_in_lq, n * 4); D(&b->d_in_tid, n * 4); D(&b->d_in_alen, n * 4); D(&b->d_in_cl, n * 4); D(&b->d_in_cr, n * 4);
     D(&b->d_key, n * 4); D(&b->d_tlen, n * 4); D(&b->d_start, n * 8); D(&b->d_aln_start, n * 8);
     D(&b->d_hist, (size_t)BIN_KEYS * 4); D(&b->d_keybase, (size_t)BIN_KEYS * 4); D(&b->d_cursor, (size_t)BIN_KEYS * 4);
@@ -709,6 +750,9 @@ static int ensure_host_staging(fadegpu_ctx *c, fadegpu_batch *b)
     return 0;
 }
 
+static int gather_reads(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, const fadegpu_inputs &in);
+static int queue_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, bool gather);
+
 int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, const fadegpu_inputs *in)
 {
     if (!c || !b || b->ctx != c || !in) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: bad ctx/batch/inputs");
@@ -718,6 +762,13 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     if (n_reads > 0 && (!in->seq4 || !in->seq_off || !in->l_qseq || !in->tid || !in->pos || !in->aligned_len ||
                         !in->clip_left || !in->clip_right))
         return fail(c, FADEGPU_E_ARG, "fadegpu_submit: null input array");
+    if (!(c->p.flags & FADEGPU_F_HOST_BINNING)) {
+        // the caller's arrays are only read here; uploads, binning and launches follow on the ctx thread
+        CU(c, cudaSetDevice(c->device));
+        { int rc = gather_reads(c, b, n_reads, *in); if (rc) return rc; }
+        return queue_submit(c, b, n_reads, false);
+    }
+    std::lock_guard<std::mutex> submit_guard(c->submit_mu);
     CU(c, cudaSetDevice(c->device));
     { int rc = ensure_host_staging(c, b); if (rc) return rc; }
     const int64_t n = n_reads;
@@ -925,43 +976,108 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     return FADEGPU_OK;
 }
 
-// Submit from the pinned view with the binning done on the device: the per-read arrays go to the
-// GPU as they are (DMA from the pinned view), a classify kernel evaluates the length floor and the
-// window arithmetic and histograms the reads by (row class, window length), the host turns the
-// 96 KB histogram into the launch plan, a scatter kernel writes the sorted descriptors.  The host
-// cores touch nothing per read; uploads and binning of batch k+1 run on a second stream while
-// batch k computes.
-static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n)
+// Stage A of a submit: the host keeps the reads that pass the length floor (analysis.d:34, unsigned
+// compare) and copies their bases and per-read fields, in read order, into pinned staging.  One
+// streaming pass over clip_left / clip_right plus ~110 B per kept read; the window arithmetic, the
+// sort by window length and everything after it run on the device (stage B).
+static int gather_reads(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, const fadegpu_inputs &in)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!b->h_c_seq4) {
+        const size_t m = (size_t)b->v.max_reads;
+        auto H = [&](auto **p, size_t bytes) { return cudaHostAlloc((void **)p, std::max<size_t>(bytes, 16), cudaHostAllocDefault); };
+        CU(c, H(&b->h_c_seq4, (size_t)b->cap_seq + 16)); CU(c, H(&b->h_c_seq_off, (m + 1) * 8)); CU(c, H(&b->h_c_pos, m * 8));
+        CU(c, H(&b->h_c_lq, m * 4)); CU(c, H(&b->h_c_tid, m * 4)); CU(c, H(&b->h_c_alen, m * 4));
+        CU(c, H(&b->h_c_cl, m * 4)); CU(c, H(&b->h_c_cr, m * 4)); CU(c, H(&b->h_c_read, m * 4));
+    }
+    const uint32_t floor_u = (uint32_t)c->p.min_length;
+    const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(c->host_threads, 64), n / 4096));
+    std::vector<int64_t> cnt((size_t)T + 1, 0), bytes((size_t)T + 1, 0);
+    int bad = 0;
+    auto need = [&](int64_t r) {
+        const uint32_t cl = (uint32_t)in.clip_left[r], cr = (uint32_t)in.clip_right[r];
+        return (cl != 0 && !(cl <= floor_u)) || (cr != 0 && !(cr <= floor_u));
+    };
+#pragma omp parallel for schedule(static, 1) reduction(| : bad) num_threads(T)
+    for (int t = 0; t < T; ++t) {
+        const int64_t r0 = n * t / T, r1 = n * (t + 1) / T;
+        int64_t k = 0, by = 0;
+        for (int64_t r = r0; r < r1; ++r) {
+            if (!need(r)) continue;
+            const int ql = in.l_qseq[r];
+            const int64_t nb = ql > 0 ? (ql + 1) / 2 : 0;
+            if (in.seq_off[r] < 0 || (ql > 0 && in.seq_off[r + 1] - in.seq_off[r] < nb)) { bad = 1; continue; }
+            ++k; by += nb;
+        }
+        cnt[(size_t)t + 1] = k; bytes[(size_t)t + 1] = by;
+    }
+    if (bad) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
+    for (int t = 0; t < T; ++t) { cnt[(size_t)t + 1] += cnt[(size_t)t]; bytes[(size_t)t + 1] += bytes[(size_t)t]; }
+    if (bytes[(size_t)T] > b->cap_seq) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: sequence bytes exceed max_seq_bytes");
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t) {
+        const int64_t r0 = n * t / T, r1 = n * (t + 1) / T;
+        int64_t k = cnt[(size_t)t], by = bytes[(size_t)t];
+        for (int64_t r = r0; r < r1; ++r) {
+            if (!need(r)) continue;
+            const int ql = in.l_qseq[r];
+            const int64_t nb = ql > 0 ? (ql + 1) / 2 : 0;
+            memcpy(b->h_c_seq4 + by, in.seq4 + in.seq_off[r], (size_t)nb);
+            b->h_c_seq_off[k] = by; b->h_c_pos[k] = in.pos[r];
+            b->h_c_lq[k] = ql; b->h_c_tid[k] = in.tid[r]; b->h_c_alen[k] = in.aligned_len[r];
+            b->h_c_cl[k] = in.clip_left[r]; b->h_c_cr[k] = in.clip_right[r]; b->h_c_read[k] = (int32_t)r;
+            ++k; by += nb;
+        }
+    }
+    b->n_c = cnt[(size_t)T]; b->seq_c = bytes[(size_t)T];
+    b->h_c_seq_off[b->n_c] = b->seq_c;
+    b->n_reads = n;
+    b->st.host_gather_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    b->st.host_threads = T;
+    return FADEGPU_OK;
+}
+
+// Stage B: the gathered reads go to the GPU, a classify kernel does the window arithmetic
+// (analysis.d:45-59) and histograms them by (row class, window length), the host turns the 96 KB
+// histogram into the launch plan, a scatter kernel writes the sorted descriptors, the SW kernels
+// follow on the compute stream and the results come back on a third stream.  Uploads and binning of
+// batch k+1 overlap the kernels of batch k.
+static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
 {
     const auto t_begin = std::chrono::steady_clock::now();
     auto ms_since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
-    const fadegpu_batch_view &v = b->v;
-    b->n_reads = n;
+    b->n_reads = n_reads;
     b->plan.clear();
     b->dev_binning = true;
-    memset(&b->st, 0, sizeof(b->st));
-    b->st.n_reads = n;
-    b->st.host_threads = 1;
+    {
+        const float g = b->st.host_gather_ms; const int32_t th = b->st.host_threads;
+        memset(&b->st, 0, sizeof(b->st));
+        b->st.host_gather_ms = g; b->st.host_threads = th;
+    }
+    b->st.n_reads = n_reads;
     b->n_aln = 0; b->n_items = 0;
     cudaStream_t s2 = c->stream2;
     CU(c, cudaEventRecord(b->ev[0], s2));
-    const int64_t seq_total = n > 0 ? v.seq_off[n] : 0;
+    const int64_t n = b->n_c;                 // reads past the length floor, in read order
+    const int64_t seq_total = b->seq_c;
     int64_t n_aln = 0;
     if (n > 0) {
         auto up = [&](void *d, const void *h, size_t bytes) { return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s2); };
-        CU(c, up(b->d_in_seq4, v.seq4, (size_t)seq_total));
-        CU(c, up(b->d_in_seq_off, v.seq_off, (size_t)(n + 1) * 8));
-        CU(c, up(b->d_in_lq, v.l_qseq, (size_t)n * 4)); CU(c, up(b->d_in_tid, v.tid, (size_t)n * 4));
-        CU(c, up(b->d_in_pos, v.pos, (size_t)n * 8)); CU(c, up(b->d_in_alen, v.aligned_len, (size_t)n * 4));
-        CU(c, up(b->d_in_cl, v.clip_left, (size_t)n * 4)); CU(c, up(b->d_in_cr, v.clip_right, (size_t)n * 4));
-        CU(c, cudaMemsetAsync(b->d_hist, 0, (size_t)BIN_KEYS * 4, s2));
+        CU(c, up(b->d_in_seq4, b->h_c_seq4, (size_t)seq_total));
+        CU(c, up(b->d_in_seq_off, b->h_c_seq_off, (size_t)(n + 1) * 8));
+        CU(c, up(b->d_in_lq, b->h_c_lq, (size_t)n * 4)); CU(c, up(b->d_in_tid, b->h_c_tid, (size_t)n * 4));
+        CU(c, up(b->d_in_pos, b->h_c_pos, (size_t)n * 8)); CU(c, up(b->d_in_alen, b->h_c_alen, (size_t)n * 4));
+        CU(c, up(b->d_in_cl, b->h_c_cl, (size_t)n * 4)); CU(c, up(b->d_in_cr, b->h_c_cr, (size_t)n * 4));
+        CU(c, up(b->d_in_read, b->h_c_read, (size_t)n * 4));
+    CU(c, cudaMemsetAsync(b->d_hist, 0, (size_t)BIN_KEYS * 4, s2));
         CU(c, cudaMemsetAsync(b->d_cursor, 0, (size_t)BIN_KEYS * 4, s2));
         CU(c, cudaMemsetAsync(b->d_stats, 0, 64, s2));
         BinArgs ba{};
         ba.seq4 = b->d_in_seq4; ba.seq_off = b->d_in_seq_off; ba.l_qseq = b->d_in_lq; ba.tid = b->d_in_tid; ba.pos = b->d_in_pos;
         ba.aligned_len = b->d_in_alen; ba.clip_left = b->d_in_cl; ba.clip_right = b->d_in_cr;
+        ba.read = b->d_in_read;
         ba.n = n; ba.seq_total = seq_total; ba.clen = c->d_clen; ba.coff = c->d_coff; ba.n_contigs = c->n_contigs;
         ba.window = c->p.window_size; ba.min_length = c->p.min_length; ba.flags = c->p.flags;
         ba.key = b->d_key; ba.tlen = b->d_tlen; ba.start = b->d_start; ba.hist = b->d_hist; ba.stats = b->d_stats;
@@ -973,6 +1089,7 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n)
         CU(c, cudaEventSynchronize(b->ev_prep));   // the previous batch keeps computing on c->stream meanwhile
         b->st.host_classify_ms = ms_since(t_begin);
         if (b->h_stats[6] & 1ull) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
+        b->h_stats[7] = 0;
         if (b->h_stats[6] & 2ull) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: a read's window exceeds 2^31 DP cells (aligned_len too large)");
         // ---- plan from the histogram ----
         const auto t_sort = std::chrono::steady_clock::now();
@@ -1009,9 +1126,9 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n)
             CU(c, launch_bin_scatter(ba, s2));
         }
     }
-    if (n > 0) {
-        CU(c, cudaMemsetAsync(b->d_rflags, 0, (size_t)n, s2));
-        CU(c, cudaMemsetAsync(b->d_ridx, 0xff, (size_t)n * 4, s2));
+    if (n_reads > 0) {
+        CU(c, cudaMemsetAsync(b->d_rflags, 0, (size_t)n_reads, s2));
+        CU(c, cudaMemsetAsync(b->d_ridx, 0xff, (size_t)n_reads * 4, s2));
     }
     CU(c, cudaEventRecord(b->ev_ready, s2));
     // ---- compute stream ----
@@ -1019,26 +1136,94 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n)
     CU(c, cudaEventRecord(b->ev[1], c->stream));
     int nl = 0;
     { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl); if (rc) return rc; }
-    b->st.kernel_launches = nl + (n > 0 ? 2 : 0) + (n_aln > 0 ? 1 : 0);
+    b->st.kernel_launches = nl + (n > 0 ? 1 : 0) + (n_aln > 0 ? 2 : 0);
     CU(c, cudaEventRecord(b->ev[2], c->stream));
-    if (n > 0) CU(c, launch_result_index(b->d_out, (int)n_aln, n, b->d_rflags, b->d_ridx, c->stream));
+    if (n_aln > 0) CU(c, launch_result_index(b->d_out, (int)n_aln, n_reads, b->d_rflags, b->d_ridx, b->d_stats + 7, c->stream));
     CU(c, cudaEventRecord(b->ev_done, c->stream));
     cudaStream_t s3 = c->stream3;                    // results go home while the next batch computes
     CU(c, cudaStreamWaitEvent(s3, b->ev_done, 0));
-    if (n > 0) {
-        CU(c, cudaMemcpyAsync(b->v.flags, b->d_rflags, (size_t)n, cudaMemcpyDeviceToHost, s3));
-        CU(c, cudaMemcpyAsync(b->h_ridx, b->d_ridx, (size_t)n * 4, cudaMemcpyDeviceToHost, s3));
+    if (n_reads > 0) {
+        CU(c, cudaMemcpyAsync(b->v.flags, b->d_rflags, (size_t)n_reads, cudaMemcpyDeviceToHost, s3));
+        CU(c, cudaMemcpyAsync(b->h_ridx, b->d_ridx, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, s3));
     }
+    if (n_aln > 0) CU(c, cudaMemcpyAsync(b->h_stats + 7, b->d_stats + 7, 8, cudaMemcpyDeviceToHost, s3));
     if (n_aln > 0) {
         CU(c, cudaMemcpyAsync(b->h_out, b->d_out, (size_t)n_aln * sizeof(AlnOut), cudaMemcpyDeviceToHost, s3));
         CU(c, cudaMemcpyAsync(b->h_aln_start, b->d_aln_start, (size_t)n_aln * 8, cudaMemcpyDeviceToHost, s3));
     }
-    b->st.h2d_bytes = seq_total + (n + 1) * 8 + n * 28 + (int64_t)BIN_KEYS * 4 + b->n_items * (int64_t)sizeof(WarpItem);
-    b->st.d2h_bytes = n_aln * (int64_t)(sizeof(AlnOut) + 8) + n * 5 + (int64_t)BIN_KEYS * 4 + 64;
+    b->st.h2d_bytes = seq_total + (n + 1) * 8 + n * 32 + (int64_t)BIN_KEYS * 4 + b->n_items * (int64_t)sizeof(WarpItem);
+    b->st.d2h_bytes = n_aln * (int64_t)(sizeof(AlnOut) + 8) + n_reads * 5 + (int64_t)BIN_KEYS * 4 + 72;
     CU(c, cudaEventRecord(b->ev[3], s3));
     b->in_flight = true;
     b->st.host_submit_ms = ms_since(t_begin);
     return FADEGPU_OK;
+}
+
+static void worker_main(fadegpu_ctx *c);
+
+static fadegpu_inputs view_inputs(const fadegpu_batch_view &v)
+{
+    fadegpu_inputs in;
+    in.seq4 = v.seq4; in.seq_off = v.seq_off; in.l_qseq = v.l_qseq; in.tid = v.tid; in.pos = v.pos;
+    in.aligned_len = v.aligned_len; in.clip_left = v.clip_left; in.clip_right = v.clip_right;
+    return in;
+}
+
+static int submit_stages(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, bool gather)
+{
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, FADEGPU_E_CUDA, "fadegpu_submit: cudaSetDevice failed");
+    if (gather) { int rc = gather_reads(c, b, n, view_inputs(b->v)); if (rc) return rc; }
+    return submit_device_binning(c, b, n);
+}
+
+// queue stage B (and stage A when the inputs are the batch's own view) for the ctx thread
+static int queue_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, bool gather)
+{
+    if (c->p.flags & FADEGPU_F_SYNC_SUBMIT) {
+        std::lock_guard<std::mutex> g(c->submit_mu);
+        return submit_stages(c, b, n, gather);
+    }
+    std::lock_guard<std::mutex> lk(c->q_mu);
+    if (!c->worker.joinable()) c->worker = std::thread(worker_main, c);
+    b->queued = true; b->submit_rc = 0; b->job_gather = gather;
+    b->in_flight = true;
+    c->jobs.emplace_back(b, n);
+    c->q_cv.notify_one();
+    return FADEGPU_OK;
+}
+
+static void worker_main(fadegpu_ctx *c)
+{
+    cudaSetDevice(c->device);
+    std::unique_lock<std::mutex> lk(c->q_mu);
+    for (;;) {
+        c->q_cv.wait(lk, [&] { return c->worker_stop || !c->jobs.empty(); });
+        if (c->jobs.empty()) return;
+        auto job = c->jobs.front();
+        c->jobs.pop_front();
+        c->worker_busy = true;
+        lk.unlock();
+        int rc;
+        std::string err;
+        {
+            std::lock_guard<std::mutex> g(c->submit_mu);
+            rc = submit_stages(c, job.first, job.second, job.first->job_gather);
+            if (rc) { std::lock_guard<std::mutex> ge(g_err_mu); err = c->err; }
+        }
+        lk.lock();
+        job.first->submit_rc = rc;
+        job.first->submit_err = err;
+        job.first->queued = false;
+        c->worker_busy = false;
+        c->done_cv.notify_all();
+    }
+}
+
+// every queued submit has been planned and launched
+static void drain_submits(fadegpu_ctx *c)
+{
+    std::unique_lock<std::mutex> lk(c->q_mu);
+    c->done_cv.wait(lk, [&] { return c->jobs.empty() && !c->worker_busy; });
 }
 
 int fadegpu_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
@@ -1051,12 +1236,9 @@ int fadegpu_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
     if (!(c->p.flags & FADEGPU_F_HOST_BINNING)) {
         if (!c->d_two) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: no reference loaded");
         if (b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: batch already in flight (call fadegpu_wait)");
-        CU(c, cudaSetDevice(c->device));
-        return submit_device_binning(c, b, n_reads);
+        return queue_submit(c, b, n_reads, true);
     }
-    fadegpu_inputs in;
-    in.seq4 = v.seq4; in.seq_off = v.seq_off; in.l_qseq = v.l_qseq; in.tid = v.tid; in.pos = v.pos;
-    in.aligned_len = v.aligned_len; in.clip_left = v.clip_left; in.clip_right = v.clip_right;
+    fadegpu_inputs in = view_inputs(v);
     return fadegpu_submit_inputs(c, b, n_reads, &in);
 }
 
@@ -1064,6 +1246,16 @@ int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
 {
     if (!c || !b || b->ctx != c) return fail(c, FADEGPU_E_ARG, "fadegpu_wait: bad ctx/batch");
     if (!b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_wait: batch not submitted");
+    {   // a queued submit reports its outcome here
+        std::unique_lock<std::mutex> lk(c->q_mu);
+        c->done_cv.wait(lk, [&] { return !b->queued; });
+        if (b->submit_rc) {
+            b->in_flight = false;
+            const int rc = b->submit_rc;
+            b->submit_rc = 0;
+            return fail(c, rc, b->submit_err);
+        }
+    }
     CU(c, cudaSetDevice(c->device));
     b->in_flight = false;
     CU(c, cudaEventSynchronize(b->ev[3]));
@@ -1079,12 +1271,12 @@ int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
     if (b->dev_binning) {
         // flags[] and the result index were produced on the device; only validate (and, unless
         // FADEGPU_F_NO_SCATTER, fill the per-read arrays)
-#pragma omp parallel for schedule(static) reduction(| : bad) num_threads(nthr)
-        for (int64_t k = 0; k < b->n_aln; ++k) {
+        if (b->n_aln > 0 && (int64_t)b->h_stats[7] != b->n_aln) bad = 1;   // result records counted on the device
+#pragma omp parallel for schedule(static) reduction(| : bad) num_threads(nthr) if (scatter)
+        for (int64_t k = 0; k < (scatter ? b->n_aln : 0); ++k) {
             const AlnOut &o = b->h_out[k];
             const int64_t r = o.read;
             if (r < 0 || r >= n || (o.flags & 0x80000000u) || b->h_ridx[r] != (int32_t)k) { bad = 1; continue; }
-            if (!scatter) continue;
             v.score[r] = o.score; v.beg_query[r] = o.beg_query; v.end_query[r] = o.end_query;
             v.beg_ref[r] = o.beg_ref; v.end_ref[r] = o.end_ref; v.n_ops[r] = o.n_ops;
             v.win_start[r] = b->h_aln_start[k];
@@ -1138,6 +1330,8 @@ int fadegpu_replay_kernels(fadegpu_ctx *c, fadegpu_batch *b, int32_t iters, floa
     if (!c || !b || b->ctx != c || iters <= 0) return fail(c, FADEGPU_E_ARG, "fadegpu_replay_kernels: bad arguments");
     if (b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_replay_kernels: batch in flight");
     if (b->plan.empty() && b->n_aln > 0) return fail(c, FADEGPU_E_STATE, "fadegpu_replay_kernels: nothing submitted");
+    drain_submits(c);
+    std::lock_guard<std::mutex> submit_guard(c->submit_mu);
     CU(c, cudaSetDevice(c->device));
     // one pass with per-stage events (serialising), then `iters` untouched passes for the total
     float f = 0, t = 0, g = 0;

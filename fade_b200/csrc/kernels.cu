@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const BinArgs a)
         d.qlen = a.l_qseq[r];
         d.clip_left = (uint32_t)a.clip_left[r];
         d.clip_right = (uint32_t)a.clip_right[r];
-        d.read = (int32_t)r;
+        d.read = a.read ? a.read[r] : (int32_t)r;
         d.pad = 0;
         a.aln[slot] = d;
         a.aln_start[slot] = a.start[r];
@@ -778,13 +778,18 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const BinArgs a)
 }
 
 // per-read flags and index into the compact results (what fadegpu_wait scatters on the host path)
-__global__ void __launch_bounds__(256) result_index_kernel(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx)
+__global__ void __launch_bounds__(256) result_index_kernel(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx,
+                                                           unsigned long long *n_ok)
 {
+    int ok = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_aln; k += gridDim.x * blockDim.x) {
         const int r = out[k].read;
         const uint32_t f = out[k].flags;
-        if (r >= 0 && (int64_t)r < n_reads && !(f & 0x80000000u)) { flags[r] = (uint8_t)(f & 0xffu); ridx[r] = k; }
+        if (r >= 0 && (int64_t)r < n_reads && (f & 1u) && !(f & 0x80000000u)) { flags[r] = (uint8_t)(f & 0xffu); ridx[r] = k; ++ok; }
     }
+    // records written by the SW kernels, counted so that the host need not walk them to validate
+    ok = __reduce_add_sync(FULL, ok);
+    if ((threadIdx.x & 31) == 0 && ok) atomicAdd(n_ok, (unsigned long long)ok);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -921,10 +926,11 @@ cudaError_t launch_bin_scatter(const BinArgs &a, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_result_index(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx, cudaStream_t s)
+cudaError_t launch_result_index(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx, unsigned long long *n_ok,
+                                cudaStream_t s)
 {
     if (n_aln <= 0) return cudaSuccess;
-    result_index_kernel<<<std::min((n_aln + 255) / 256, 148 * 8), 256, 0, s>>>(out, n_aln, n_reads, flags, ridx);
+    result_index_kernel<<<std::min((n_aln + 255) / 256, 148 * 8), 256, 0, s>>>(out, n_aln, n_reads, flags, ridx, n_ok);
     return cudaGetLastError();
 }
 

@@ -91,6 +91,7 @@ struct BinArgs {
     const int32_t *l_qseq, *tid;
     const int64_t *pos;
     const int32_t *aligned_len, *clip_left, *clip_right;
+    const int32_t *read;            // [n] index of each entry in the caller's batch (nullptr = identity)
     int64_t n, seq_total;
     const int64_t *clen, *coff;     // contig lengths / global base offsets
     int32_t n_contigs, window, min_length;
@@ -131,7 +132,8 @@ __host__ __device__ inline int bin_rank(int qlen, int tlen, bool force_generic)
 }
 cudaError_t launch_bin_classify(const BinArgs &a, cudaStream_t s);
 cudaError_t launch_bin_scatter(const BinArgs &a, cudaStream_t s);
-cudaError_t launch_result_index(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx, cudaStream_t s);
+cudaError_t launch_result_index(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx, unsigned long long *n_ok,
+                                cudaStream_t s);
 cudaError_t launch_fill(int R, const KernelArgs &a, cudaStream_t s);
 cudaError_t launch_trace(int R, const KernelArgs &a, cudaStream_t s, int sm_count, int *launches);
 cudaError_t launch_generic(const GenericArgs &a, int n_slots, cudaStream_t s);

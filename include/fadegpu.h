@@ -68,6 +68,8 @@ typedef struct fadegpu_params {
                                       (A/B switch; results are identical) */
 #define FADEGPU_F_HOST_BINNING 16u  /* fadegpu_submit: bin the reads on the host (as fadegpu_submit_inputs
                                       does) instead of uploading the pinned view and binning on the device */
+#define FADEGPU_F_SYNC_SUBMIT 32u   /* fadegpu_submit: plan and launch on the calling thread (errors of the batch
+                                      are then returned by fadegpu_submit itself instead of fadegpu_wait) */
 #define FADEGPU_F_NO_SCATTER 2u    /* fadegpu_wait fills only flags[] and the compact results
                                       (fadegpu_get_results), not the other per-read output arrays */
 
@@ -144,10 +146,12 @@ int fadegpu_alloc_batch(fadegpu_ctx *ctx, int64_t max_reads, int64_t max_seq_byt
 int fadegpu_get_batch_view(fadegpu_batch *b, fadegpu_batch_view *view);
 void fadegpu_free_batch(fadegpu_batch *b);
 
-/* Asynchronous.  The per-read arrays of the pinned view are DMA'd to the device as they are and the
- * binning (length floor, windows, sort by window length) runs on the GPU; the host only turns a
- * small histogram into the launch plan.  Uploads and binning of one batch overlap with the kernels
- * of the previous one. */
+/* Asynchronous: returns at once.  The per-read arrays of the pinned view are DMA'd to the device as
+ * they are and the binning (length floor, windows, sort by window length) runs on the GPU; a thread
+ * owned by the ctx turns the small histogram into the launch plan and queues the kernels.  Uploads
+ * and binning of one batch overlap with the kernels of the previous one and with the result copies
+ * of the one before.  The view's input arrays must stay untouched until fadegpu_wait, which also
+ * reports any error of the batch (inconsistent seq_off, window too large, CUDA failure). */
 int fadegpu_submit(fadegpu_ctx *ctx, fadegpu_batch *b, int64_t n_reads);
 
 /* Same, reading the inputs from caller-owned host arrays (pageable is fine: the library gathers

@@ -315,10 +315,11 @@ def test_long_windows_use_generic_kernel_and_absurd_ones_are_refused():
         b.close()
 
 
-@pytest.mark.parametrize("flags", [0, api.F_HOST_BINNING])
+@pytest.mark.parametrize("flags", [0, api.F_HOST_BINNING, api.F_SYNC_SUBMIT])
 def test_device_and_host_binning_agree(flags):
-    """fadegpu_submit bins the pinned view on the device by default; FADEGPU_F_HOST_BINNING and
-    fadegpu_submit_inputs bin on the host.  Same records either way (ragged lengths, several contigs)."""
+    """By default the host only gathers the reads past the length floor and the device bins them, queued
+    on the ctx thread; FADEGPU_F_SYNC_SUBMIT does that on the calling thread, FADEGPU_F_HOST_BINNING bins
+    on the host.  Same records every way (ragged lengths, several contigs), from the view and from arrays."""
     rng = random.Random(41)
     contigs = [readsets.random_ref(rng, n) for n in (9000, 2500, 600)]
     rd = readsets.build(readsets.ragged_reads(rng, contigs, 4000, max_len=320))
@@ -331,7 +332,7 @@ def test_device_and_host_binning_agree(flags):
         rec1 = b.results()[0]
         rec1 = rec1[np.argsort(rec1["read"])].copy()
         b.submit_arrays(rd.n, rd.seq4, rd.seq_off, rd.l_qseq, rd.tid, rd.pos, rd.aligned_len, rd.clip_left, rd.clip_right)
-        b.wait()                                   # fadegpu_submit_inputs (host binning)
+        b.wait()                                   # fadegpu_submit_inputs (caller-owned arrays)
         rec2 = b.results()[0]
         assert np.array_equal(rec1, rec2[np.argsort(rec2["read"])])
         b.run(0)                                   # empty batch through the device path
