@@ -132,7 +132,11 @@ struct fadegpu_batch {
     int32_t *h_c_lq = nullptr, *h_c_tid = nullptr, *h_c_alen = nullptr, *h_c_cl = nullptr, *h_c_cr = nullptr, *h_c_read = nullptr;
     int32_t *d_in_read = nullptr;
     int64_t n_c = 0, seq_c = 0;                        // gathered reads / their sequence bytes
-    bool job_gather = false;                           // the queued submit still has to gather from the view
+    bool job_pull = false;                             // the queued submit reads the batch's own pinned view
+    bool pulled = false;
+    int64_t *d_src_off = nullptr;
+    const uint8_t *d_view_seq4 = nullptr;              // device address of the pinned view's seq4
+    std::vector<int32_t> idx;                          // gather scratch
     cudaEvent_t ev_prep = nullptr, ev_ready = nullptr, ev_done = nullptr;
     // asynchronous submit (guarded by ctx->q_mu)
     bool queued = false;
@@ -673,7 +677,7 @@ void fadegpu_free_batch(fadegpu_batch *b)
     free_dev(b->d_rflags); free_dev(b->d_stats);
     free_host(b->h_hist); free_host(b->h_keybase); free_host(b->h_stats); free_host(b->h_aln_start);
     free_host(b->h_c_seq4); free_host(b->h_c_seq_off); free_host(b->h_c_pos); free_host(b->h_c_lq); free_host(b->h_c_tid);
-    free_host(b->h_c_alen); free_host(b->h_c_cl); free_host(b->h_c_cr); free_host(b->h_c_read); free_dev(b->d_in_read);
+    free_host(b->h_c_alen); free_host(b->h_c_cl); free_host(b->h_c_cr); free_host(b->h_c_read); free_dev(b->d_in_read); free_dev(b->d_src_off);
     if (b->ev_prep) cudaEventDestroy(b->ev_prep);
     if (b->ev_ready) cudaEventDestroy(b->ev_ready);
     if (b->ev_done) cudaEventDestroy(b->ev_done);
@@ -699,7 +703,7 @@ int fadegpu_alloc_batch(fadegpu_ctx *c, int64_t max_reads, int64_t max_seq_bytes
     cudaError_t e = cudaSuccess;
     auto H = [&](auto **p, size_t bytes) { if (e == cudaSuccess) e = cudaHostAlloc((void **)p, std::max<size_t>(bytes, 16), cudaHostAllocDefault); };
     auto D = [&](auto **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc((void **)p, std::max<size_t>(bytes, 16)); };
-    H(&v.seq4, (size_t)max_seq_bytes); H(&v.seq_off, (n + 1) * 8); H(&v.l_qseq, n * 4); H(&v.tid, n * 4);
+    H(&v.seq4, (size_t)max_seq_bytes + 16); H(&v.seq_off, (n + 1) * 8); H(&v.l_qseq, n * 4); H(&v.tid, n * 4);
     H(&v.pos, n * 8); H(&v.aligned_len, n * 4); H(&v.clip_left, n * 4); H(&v.clip_right, n * 4);
     H(&v.flags, n);
     if (!(c->p.flags & FADEGPU_F_NO_SCATTER)) {   // the per-read output arrays are only filled without NO_SCATTER
@@ -713,13 +717,15 @@ int fadegpu_alloc_batch(fadegpu_ctx *c, int64_t max_reads, int64_t max_seq_bytes
     D(&b->d_out, n * sizeof(AlnOut)); D(&b->d_flags, n * 4);
     D(&b->d_fillres, (size_t)b->cap_items * 32 * sizeof(uint2));
     // device-side binning: mirrors of the inputs, keys, histogram, per-read result index
-    D(&b->d_in_seq4, (size_t)max_seq_bytes + 16); D(&b->d_in_seq_off, (n + 1) * 8); D(&b->d_in_pos, n * 8);
+    // d_in_seq4: 16-byte slots that keep the source's alignment phase
+    D(&b->d_in_seq4, (size_t)max_seq_bytes + 32 * n + 16); D(&b->d_in_seq_off, (n + 1) * 8); D(&b->d_in_pos, n * 8);
     D(&b->d_in_read, n * 4);
     D(&b->d_in_lq, n * 4); D(&b->d_in_tid, n * 4); D(&b->d_in_alen, n * 4); D(&b->d_in_cl, n * 4); D(&b->d_in_cr, n * 4);
     D(&b->d_key, n * 4); D(&b->d_tlen, n * 4); D(&b->d_start, n * 8); D(&b->d_aln_start, n * 8);
     D(&b->d_hist, (size_t)BIN_KEYS * 4); D(&b->d_keybase, (size_t)BIN_KEYS * 4); D(&b->d_cursor, (size_t)BIN_KEYS * 4);
-    D(&b->d_ridx, n * 4); D(&b->d_rflags, n); D(&b->d_stats, 64);
-    H(&b->h_hist, (size_t)BIN_KEYS * 4); H(&b->h_keybase, (size_t)BIN_KEYS * 4); H(&b->h_stats, 64); H(&b->h_aln_start, n * 8);
+    D(&b->d_ridx, n * 4); D(&b->d_rflags, n); D(&b->d_stats, 128); D(&b->d_src_off, n * 8);
+    H(&b->h_hist, (size_t)BIN_KEYS * 4); H(&b->h_keybase, (size_t)BIN_KEYS * 4); H(&b->h_stats, 128); H(&b->h_aln_start, n * 8);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&b->d_view_seq4, v.seq4, 0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_prep);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_ready);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
@@ -993,42 +999,56 @@ static int gather_reads(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, const fadeg
     const uint32_t floor_u = (uint32_t)c->p.min_length;
     const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(c->host_threads, 64), n / 4096));
     std::vector<int64_t> cnt((size_t)T + 1, 0), bytes((size_t)T + 1, 0);
-    int bad = 0;
-    auto need = [&](int64_t r) {
-        const uint32_t cl = (uint32_t)in.clip_left[r], cr = (uint32_t)in.clip_right[r];
-        return (cl != 0 && !(cl <= floor_u)) || (cr != 0 && !(cr <= floor_u));
-    };
-#pragma omp parallel for schedule(static, 1) reduction(| : bad) num_threads(T)
-    for (int t = 0; t < T; ++t) {
-        const int64_t r0 = n * t / T, r1 = n * (t + 1) / T;
-        int64_t k = 0, by = 0;
-        for (int64_t r = r0; r < r1; ++r) {
-            if (!need(r)) continue;
-            const int ql = in.l_qseq[r];
-            const int64_t nb = ql > 0 ? (ql + 1) / 2 : 0;
-            if (in.seq_off[r] < 0 || (ql > 0 && in.seq_off[r + 1] - in.seq_off[r] < nb)) { bad = 1; continue; }
-            ++k; by += nb;
-        }
-        cnt[(size_t)t + 1] = k; bytes[(size_t)t + 1] = by;
-    }
-    if (bad) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
-    for (int t = 0; t < T; ++t) { cnt[(size_t)t + 1] += cnt[(size_t)t]; bytes[(size_t)t + 1] += bytes[(size_t)t]; }
-    if (bytes[(size_t)T] > b->cap_seq) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: sequence bytes exceed max_seq_bytes");
+    b->idx.resize((size_t)std::max<int64_t>(n, 1));
+    int32_t *const idx = b->idx.data();
+    // pass 1, branch-free: indices of the reads that need SW (compacted per thread range) and their bytes
 #pragma omp parallel for schedule(static, 1) num_threads(T)
     for (int t = 0; t < T; ++t) {
         const int64_t r0 = n * t / T, r1 = n * (t + 1) / T;
-        int64_t k = cnt[(size_t)t], by = bytes[(size_t)t];
+        int64_t k = 0, by = 0;
+        int32_t *out = idx + r0;
         for (int64_t r = r0; r < r1; ++r) {
-            if (!need(r)) continue;
+            const uint32_t cl = (uint32_t)in.clip_left[r], cr = (uint32_t)in.clip_right[r];
+            const int nd = (int)(cl > floor_u) | (int)(cr > floor_u);     // == (cl != 0 && !(cl <= floor)) || ...
+            const int ql = in.l_qseq[r];
+            out[k] = (int32_t)r;
+            k += nd;
+            by += nd ? (int64_t)((ql > 0 ? ql + 1 : 0) >> 1) : 0;
+        }
+        cnt[(size_t)t + 1] = k; bytes[(size_t)t + 1] = by;
+    }
+    for (int t = 0; t < T; ++t) { cnt[(size_t)t + 1] += cnt[(size_t)t]; bytes[(size_t)t + 1] += bytes[(size_t)t]; }
+    if (bytes[(size_t)T] > b->cap_seq) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: sequence bytes exceed max_seq_bytes");
+    // pass 2: copy the kept reads; the loads are scattered over seven arrays, so prefetch ahead
+    int bad = 0;
+#pragma omp parallel for schedule(static, 1) reduction(| : bad) num_threads(T)
+    for (int t = 0; t < T; ++t) {
+        const int32_t *ix = idx + n * t / T;
+        const int64_t m = cnt[(size_t)t + 1] - cnt[(size_t)t];
+        int64_t k = cnt[(size_t)t], by = bytes[(size_t)t];
+        constexpr int D = 12;
+        for (int64_t i = 0; i < m; ++i) {
+            if (i + 2 * D < m) {
+                const int64_t rr = ix[i + 2 * D];
+                __builtin_prefetch(&in.seq_off[rr]); __builtin_prefetch(&in.pos[rr]); __builtin_prefetch(&in.tid[rr]);
+                __builtin_prefetch(&in.aligned_len[rr]); __builtin_prefetch(&in.l_qseq[rr]);
+            }
+            if (i + D < m) {
+                const uint8_t *p = in.seq4 + in.seq_off[ix[i + D]];
+                __builtin_prefetch(p); __builtin_prefetch(p + 64);
+            }
+            const int64_t r = ix[i];
             const int ql = in.l_qseq[r];
             const int64_t nb = ql > 0 ? (ql + 1) / 2 : 0;
-            memcpy(b->h_c_seq4 + by, in.seq4 + in.seq_off[r], (size_t)nb);
+            if (in.seq_off[r] < 0 || (nb > 0 && in.seq_off[r + 1] - in.seq_off[r] < nb)) bad = 1;
+            else memcpy(b->h_c_seq4 + by, in.seq4 + in.seq_off[r], (size_t)nb);
             b->h_c_seq_off[k] = by; b->h_c_pos[k] = in.pos[r];
             b->h_c_lq[k] = ql; b->h_c_tid[k] = in.tid[r]; b->h_c_alen[k] = in.aligned_len[r];
             b->h_c_cl[k] = in.clip_left[r]; b->h_c_cr[k] = in.clip_right[r]; b->h_c_read[k] = (int32_t)r;
             ++k; by += nb;
         }
     }
+    if (bad) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
     b->n_c = cnt[(size_t)T]; b->seq_c = bytes[(size_t)T];
     b->h_c_seq_off[b->n_c] = b->seq_c;
     b->n_reads = n;
@@ -1042,7 +1062,7 @@ static int gather_reads(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, const fadeg
 // histogram into the launch plan, a scatter kernel writes the sorted descriptors, the SW kernels
 // follow on the compute stream and the results come back on a third stream.  Uploads and binning of
 // batch k+1 overlap the kernels of batch k.
-static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
+static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, bool pull)
 {
     const auto t_begin = std::chrono::steady_clock::now();
     auto ms_since = [](std::chrono::steady_clock::time_point t0) {
@@ -1052,7 +1072,7 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
     b->plan.clear();
     b->dev_binning = true;
     {
-        const float g = b->st.host_gather_ms; const int32_t th = b->st.host_threads;
+        const float g = pull ? 0.f : b->st.host_gather_ms; const int32_t th = pull ? 1 : b->st.host_threads;
         memset(&b->st, 0, sizeof(b->st));
         b->st.host_gather_ms = g; b->st.host_threads = th;
     }
@@ -1060,24 +1080,29 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
     b->n_aln = 0; b->n_items = 0;
     cudaStream_t s2 = c->stream2;
     CU(c, cudaEventRecord(b->ev[0], s2));
-    const int64_t n = b->n_c;                 // reads past the length floor, in read order
-    const int64_t seq_total = b->seq_c;
+    // pull: every read's fields are DMA'd from the pinned view (36 B/read), the bases stay there until
+    // seq_pull_kernel fetches those of the reads that get aligned.  Otherwise: what gather_reads staged.
+    b->pulled = pull;
+    const fadegpu_batch_view &v = b->v;
+    const int64_t n = pull ? n_reads : b->n_c;
+    const int64_t seq_total = pull ? (n > 0 ? v.seq_off[n] : 0) : b->seq_c;
     int64_t n_aln = 0;
     if (n > 0) {
         auto up = [&](void *d, const void *h, size_t bytes) { return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s2); };
-        CU(c, up(b->d_in_seq4, b->h_c_seq4, (size_t)seq_total));
-        CU(c, up(b->d_in_seq_off, b->h_c_seq_off, (size_t)(n + 1) * 8));
-        CU(c, up(b->d_in_lq, b->h_c_lq, (size_t)n * 4)); CU(c, up(b->d_in_tid, b->h_c_tid, (size_t)n * 4));
-        CU(c, up(b->d_in_pos, b->h_c_pos, (size_t)n * 8)); CU(c, up(b->d_in_alen, b->h_c_alen, (size_t)n * 4));
-        CU(c, up(b->d_in_cl, b->h_c_cl, (size_t)n * 4)); CU(c, up(b->d_in_cr, b->h_c_cr, (size_t)n * 4));
-        CU(c, up(b->d_in_read, b->h_c_read, (size_t)n * 4));
+        if (!pull) CU(c, up(b->d_in_seq4, b->h_c_seq4, (size_t)seq_total));
+        CU(c, up(b->d_in_seq_off, pull ? v.seq_off : b->h_c_seq_off, (size_t)(n + 1) * 8));
+        CU(c, up(b->d_in_lq, pull ? v.l_qseq : b->h_c_lq, (size_t)n * 4)); CU(c, up(b->d_in_tid, pull ? v.tid : b->h_c_tid, (size_t)n * 4));
+        CU(c, up(b->d_in_pos, pull ? v.pos : b->h_c_pos, (size_t)n * 8)); CU(c, up(b->d_in_alen, pull ? v.aligned_len : b->h_c_alen, (size_t)n * 4));
+        CU(c, up(b->d_in_cl, pull ? v.clip_left : b->h_c_cl, (size_t)n * 4)); CU(c, up(b->d_in_cr, pull ? v.clip_right : b->h_c_cr, (size_t)n * 4));
+        if (!pull) CU(c, up(b->d_in_read, b->h_c_read, (size_t)n * 4));
     CU(c, cudaMemsetAsync(b->d_hist, 0, (size_t)BIN_KEYS * 4, s2));
         CU(c, cudaMemsetAsync(b->d_cursor, 0, (size_t)BIN_KEYS * 4, s2));
-        CU(c, cudaMemsetAsync(b->d_stats, 0, 64, s2));
+        CU(c, cudaMemsetAsync(b->d_stats, 0, 128, s2));
         BinArgs ba{};
         ba.seq4 = b->d_in_seq4; ba.seq_off = b->d_in_seq_off; ba.l_qseq = b->d_in_lq; ba.tid = b->d_in_tid; ba.pos = b->d_in_pos;
         ba.aligned_len = b->d_in_alen; ba.clip_left = b->d_in_cl; ba.clip_right = b->d_in_cr;
-        ba.read = b->d_in_read;
+        ba.read = pull ? nullptr : b->d_in_read;
+        ba.seq_cursor = pull ? b->d_stats + 8 : nullptr; ba.src_off = b->d_src_off;
         ba.n = n; ba.seq_total = seq_total; ba.clen = c->d_clen; ba.coff = c->d_coff; ba.n_contigs = c->n_contigs;
         ba.window = c->p.window_size; ba.min_length = c->p.min_length; ba.flags = c->p.flags;
         ba.key = b->d_key; ba.tlen = b->d_tlen; ba.start = b->d_start; ba.hist = b->d_hist; ba.stats = b->d_stats;
@@ -1124,6 +1149,7 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
             if (b->n_items > 0)
                 CU(c, cudaMemcpyAsync(b->d_items, b->h_items, (size_t)b->n_items * sizeof(WarpItem), cudaMemcpyHostToDevice, s2));
             CU(c, launch_bin_scatter(ba, s2));
+            if (pull) CU(c, launch_seq_pull(b->d_view_seq4, b->d_aln, b->d_src_off, (int)n_aln, b->d_in_seq4, s2));
         }
     }
     if (n_reads > 0) {
@@ -1136,7 +1162,7 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
     CU(c, cudaEventRecord(b->ev[1], c->stream));
     int nl = 0;
     { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl); if (rc) return rc; }
-    b->st.kernel_launches = nl + (n > 0 ? 1 : 0) + (n_aln > 0 ? 2 : 0);
+    b->st.kernel_launches = nl + (n > 0 ? 1 : 0) + (n_aln > 0 ? (pull ? 3 : 2) : 0);
     CU(c, cudaEventRecord(b->ev[2], c->stream));
     if (n_aln > 0) CU(c, launch_result_index(b->d_out, (int)n_aln, n_reads, b->d_rflags, b->d_ridx, b->d_stats + 7, c->stream));
     CU(c, cudaEventRecord(b->ev_done, c->stream));
@@ -1146,12 +1172,13 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
         CU(c, cudaMemcpyAsync(b->v.flags, b->d_rflags, (size_t)n_reads, cudaMemcpyDeviceToHost, s3));
         CU(c, cudaMemcpyAsync(b->h_ridx, b->d_ridx, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, s3));
     }
-    if (n_aln > 0) CU(c, cudaMemcpyAsync(b->h_stats + 7, b->d_stats + 7, 8, cudaMemcpyDeviceToHost, s3));
+    if (n_aln > 0) CU(c, cudaMemcpyAsync(b->h_stats + 7, b->d_stats + 7, 16, cudaMemcpyDeviceToHost, s3));
     if (n_aln > 0) {
         CU(c, cudaMemcpyAsync(b->h_out, b->d_out, (size_t)n_aln * sizeof(AlnOut), cudaMemcpyDeviceToHost, s3));
         CU(c, cudaMemcpyAsync(b->h_aln_start, b->d_aln_start, (size_t)n_aln * 8, cudaMemcpyDeviceToHost, s3));
     }
-    b->st.h2d_bytes = seq_total + (n + 1) * 8 + n * 32 + (int64_t)BIN_KEYS * 4 + b->n_items * (int64_t)sizeof(WarpItem);
+    // (pull: the bytes seq_pull_kernel fetched are added by fadegpu_wait, from the device's cursor)
+    b->st.h2d_bytes = (pull ? 0 : seq_total + n * 4) + (n + 1) * 8 + n * 28 + (int64_t)BIN_KEYS * 4 + b->n_items * (int64_t)sizeof(WarpItem);
     b->st.d2h_bytes = n_aln * (int64_t)(sizeof(AlnOut) + 8) + n_reads * 5 + (int64_t)BIN_KEYS * 4 + 72;
     CU(c, cudaEventRecord(b->ev[3], s3));
     b->in_flight = true;
@@ -1169,11 +1196,11 @@ static fadegpu_inputs view_inputs(const fadegpu_batch_view &v)
     return in;
 }
 
+// gather = the inputs are the batch's own pinned view: nothing was gathered, the GPU pulls what it needs
 static int submit_stages(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, bool gather)
 {
     if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, FADEGPU_E_CUDA, "fadegpu_submit: cudaSetDevice failed");
-    if (gather) { int rc = gather_reads(c, b, n, view_inputs(b->v)); if (rc) return rc; }
-    return submit_device_binning(c, b, n);
+    return submit_device_binning(c, b, n, gather);
 }
 
 // queue stage B (and stage A when the inputs are the batch's own view) for the ctx thread
@@ -1185,7 +1212,7 @@ static int queue_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, bool gather
     }
     std::lock_guard<std::mutex> lk(c->q_mu);
     if (!c->worker.joinable()) c->worker = std::thread(worker_main, c);
-    b->queued = true; b->submit_rc = 0; b->job_gather = gather;
+    b->queued = true; b->submit_rc = 0; b->job_pull = gather;
     b->in_flight = true;
     c->jobs.emplace_back(b, n);
     c->q_cv.notify_one();
@@ -1207,7 +1234,7 @@ static void worker_main(fadegpu_ctx *c)
         std::string err;
         {
             std::lock_guard<std::mutex> g(c->submit_mu);
-            rc = submit_stages(c, job.first, job.second, job.first->job_gather);
+            rc = submit_stages(c, job.first, job.second, job.first->job_pull);
             if (rc) { std::lock_guard<std::mutex> ge(g_err_mu); err = c->err; }
         }
         lk.lock();
@@ -1272,6 +1299,7 @@ int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
         // flags[] and the result index were produced on the device; only validate (and, unless
         // FADEGPU_F_NO_SCATTER, fill the per-read arrays)
         if (b->n_aln > 0 && (int64_t)b->h_stats[7] != b->n_aln) bad = 1;   // result records counted on the device
+        if (b->n_aln > 0 && b->pulled) { b->st.h2d_bytes += (int64_t)b->h_stats[8]; b->pulled = false; }
 #pragma omp parallel for schedule(static) reduction(| : bad) num_threads(nthr) if (scatter)
         for (int64_t k = 0; k < (scatter ? b->n_aln : 0); ++k) {
             const AlnOut &o = b->h_out[k];

@@ -766,6 +766,14 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const BinArgs a)
         AlnDesc d;
         d.gstart = a.coff[a.tid[r]] + a.start[r];
         d.seq_off = a.seq_off[r];
+        if (a.seq_cursor) {
+            // a 16-byte aligned slot that keeps the source's alignment phase, so that seq_pull_kernel copies whole uint4s
+            const int64_t so = d.seq_off;
+            const int ph = (int)(so & 15);
+            const unsigned long long bytes = (unsigned long long)((ph + (a.l_qseq[r] + 1) / 2 + 15) & ~15);
+            d.seq_off = (int64_t)atomicAdd(a.seq_cursor, bytes) + ph;
+            a.src_off[slot] = so;
+        }
         d.tlen = a.tlen[r];
         d.qlen = a.l_qseq[r];
         d.clip_left = (uint32_t)a.clip_left[r];
@@ -774,6 +782,24 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const BinArgs a)
         d.pad = 0;
         a.aln[slot] = d;
         a.aln_start[slot] = a.start[r];
+    }
+}
+
+// The GPU fetches the bases of the reads it aligns straight from the caller's pinned (mapped) view:
+// 8 lanes per alignment, one aligned uint4 each per pass, i.e. one 128-byte PCIe read per pass.
+// Only ~20 % of a batch's bases are ever needed, so the other 80 % never cross PCIe
+// and no host core touches any of them.
+__global__ void __launch_bounds__(256) seq_pull_kernel(const uint8_t *__restrict__ host_seq4, const AlnDesc *__restrict__ aln,
+                                                       const int64_t *__restrict__ src_off, int n_aln, uint8_t *__restrict__ dst)
+{
+    const int lane = threadIdx.x & 7;
+    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; k < n_aln; k += (gridDim.x * blockDim.x) >> 3) {
+        const int64_t so = src_off[k];
+        const int ph = (int)(so & 15);
+        const int chunks = (ph + (aln[k].qlen + 1) / 2 + 15) >> 4;
+        const uint4 *s = reinterpret_cast<const uint4 *>(host_seq4 + (so - ph));
+        uint4 *d = reinterpret_cast<uint4 *>(dst + (aln[k].seq_off - ph));
+        for (int i = lane; i < chunks; i += 8) d[i] = s[i];
     }
 }
 
@@ -923,6 +949,14 @@ cudaError_t launch_bin_scatter(const BinArgs &a, cudaStream_t s)
     if (a.n <= 0) return cudaSuccess;
     const int grid = (int)std::min<int64_t>((a.n + 255) / 256, 148 * 16);
     bin_scatter_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_seq_pull(const uint8_t *host_seq4, const AlnDesc *aln, const int64_t *src_off, int n_aln, uint8_t *dst, cudaStream_t s)
+{
+    if (n_aln <= 0) return cudaSuccess;
+    const int grid = std::min((n_aln * 8 + 255) / 256, 148 * 16);
+    seq_pull_kernel<<<grid, 256, 0, s>>>(host_seq4, aln, src_off, n_aln, dst);
     return cudaGetLastError();
 }
 

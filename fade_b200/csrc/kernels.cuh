@@ -107,6 +107,9 @@ struct BinArgs {
     int32_t *cursor;                // [BIN_KEYS]
     AlnDesc *aln;
     int64_t *aln_start;
+    // pull mode (the bases stay in the caller's pinned view until the GPU fetches the ones it needs)
+    unsigned long long *seq_cursor; // device byte cursor into the compact sequence buffer; nullptr = seq_off is final
+    int64_t *src_off;               // [n_aln] offset of each alignment's bases in the pinned view
 };
 
 constexpr int FILL_THREADS = 128;
@@ -132,6 +135,7 @@ __host__ __device__ inline int bin_rank(int qlen, int tlen, bool force_generic)
 }
 cudaError_t launch_bin_classify(const BinArgs &a, cudaStream_t s);
 cudaError_t launch_bin_scatter(const BinArgs &a, cudaStream_t s);
+cudaError_t launch_seq_pull(const uint8_t *host_seq4, const AlnDesc *aln, const int64_t *src_off, int n_aln, uint8_t *dst, cudaStream_t s);
 cudaError_t launch_result_index(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx, unsigned long long *n_ok,
                                 cudaStream_t s);
 cudaError_t launch_fill(int R, const KernelArgs &a, cudaStream_t s);
