@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "fadegpu_abi_version", "fadegpu_device_count", "fadegpu_default_params", "fadegpu_create",
     "fadegpu_destroy", "fadegpu_last_error", "fadegpu_load_reference", "fadegpu_share_reference",
     "fadegpu_reference_info", "fadegpu_alloc_batch", "fadegpu_get_batch_view", "fadegpu_free_batch",
-    "fadegpu_submit", "fadegpu_submit_inputs", "fadegpu_wait", "fadegpu_get_results", "fadegpu_get_stats", "fadegpu_replay_kernels",
+    "fadegpu_submit", "fadegpu_submit_inputs", "fadegpu_wait", "fadegpu_get_results", "fadegpu_get_stats", "fadegpu_replay_kernels", "fadegpu_replay_batches",
     "fadegpu_measure_alu_peak",
     "fadehost_parse_clips", "fadehost_aligned_length", "fadehost_prepare", "fadehost_finish",
 ]
@@ -123,6 +123,7 @@ def lib():
     L.fadegpu_get_results.argtypes = [vp, C.POINTER(ResultsView)]
     L.fadegpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.fadegpu_replay_kernels.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]
+    L.fadegpu_replay_batches.argtypes = [vp, C.POINTER(vp), i32, i32, C.POINTER(C.c_float)]
     L.fadegpu_measure_alu_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.fadehost_parse_clips.argtypes = [C.POINTER(C.c_uint32), i32, C.POINTER(C.c_uint32)]
     L.fadehost_parse_clips.restype = None

@@ -87,6 +87,14 @@ class Context:
         self._check(lib().fadegpu_measure_alu_peak(self._h, C.byref(ops), C.byref(mhz)))
         return ops.value, mhz.value
 
+    def replay_batches(self, batches, iters: int = 1) -> float:
+        """fadegpu_replay_batches: device ms of `iters` passes of only the kernels over resident batches,
+        queued back to back as consecutive submits queue them."""
+        arr = (C.c_void_p * len(batches))(*[b._h.value for b in batches])
+        ms = C.c_float()
+        self._check(lib().fadegpu_replay_batches(self._h, arr, len(batches), iters, C.byref(ms)))
+        return ms.value
+
     def alloc_batch(self, max_reads: int, max_seq_bytes: int) -> "Batch":
         return Batch(self, max_reads, max_seq_bytes)
 

@@ -47,17 +47,27 @@ struct fadegpu_ctx {
     uint8_t *d_xchr = nullptr;
     int64_t n_x = 0;
     size_t ref_bytes = 0;
-    // scratch shared by all batches of the ctx (one stream -> serialised)
-    uint32_t *d_ck = nullptr;
-    size_t ck_bytes = 0;
-    uint8_t *d_gen = nullptr;
-    size_t gen_bytes = 0;
-    unsigned int *d_cursor = nullptr;
+    // Fills run back to back on `stream`; the traceback rounds (and the generic kernel) of a launch
+    // run on `tstream`, at higher priority, under the fill of the NEXT launch (of this batch or of
+    // the following one): their many small, latency-bound grids take SM slots as fill blocks retire.
+    // Two scratch sets alternate between consecutive launches, ordered by events.
+    cudaStream_t tstream = nullptr;
+    unsigned next_lane = 0;
+    struct Lane {
+        cudaEvent_t ev_fill = nullptr, ev_trace = nullptr;   // last fill / last traceback that used this scratch set
+        bool used = false;
+        uint32_t *d_ck = nullptr;        // fill checkpoints
+        size_t ck_bytes = 0;
+        uint8_t *d_gen = nullptr;        // generic kernel slots
+        size_t gen_bytes = 0;
+        unsigned int *d_cursor = nullptr;
+        // traceback rounds: per-alignment state, request queues, trace tiles (sized per launch)
+        uint8_t *d_trace = nullptr;
+        size_t trace_bytes = 0;
+        unsigned int *d_qcount = nullptr;
+    } lane[2];
+    int n_lanes = 2;
     uint32_t *d_alu = nullptr;
-    // traceback rounds: per-alignment state, request queues, trace tiles (sized per launch)
-    uint8_t *d_trace = nullptr;
-    size_t trace_bytes = 0;
-    unsigned int *d_qcount = nullptr;
     int sm_count = 148;
     int host_threads = 1;
     cudaStream_t stream2 = nullptr;      // uploads + binning of the next batch while the previous one computes
@@ -138,6 +148,8 @@ struct fadegpu_batch {
     const uint8_t *d_view_seq4 = nullptr;              // device address of the pinned view's seq4
     std::vector<int32_t> idx;                          // gather scratch
     cudaEvent_t ev_prep = nullptr, ev_ready = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_lane[2] = { nullptr, nullptr };    // end of the batch's work on each kernel lane
+    int lanes_used = 1;
     // asynchronous submit (guarded by ctx->q_mu)
     bool queued = false;
     int submit_rc = 0;
@@ -219,13 +231,13 @@ int class_of(const fadegpu_ctx *c, int qlen, int tlen)
 
 size_t ck_words_of(int R) { return (size_t)(2 * R + 2); }
 
-int ensure_ck(fadegpu_ctx *c, size_t bytes)
+int ensure_dev(fadegpu_ctx *c, void **p, size_t *have, size_t bytes)
 {
-    if (bytes <= c->ck_bytes) return 0;
-    free_dev(c->d_ck);
-    c->ck_bytes = 0;
-    CU(c, cudaMalloc(&c->d_ck, bytes));
-    c->ck_bytes = bytes;
+    if (bytes <= *have) return 0;
+    if (*p) cudaFree(*p);               // (synchronises with whatever still uses it)
+    *p = nullptr; *have = 0;
+    CU(c, cudaMalloc(p, bytes));
+    *have = bytes;
     return 0;
 }
 
@@ -238,27 +250,9 @@ size_t trace_scratch_bytes(int R, int64_t n)
            align256((size_t)((n + 1) / 2) * trace_tile_bytes(R));
 }
 
-int ensure_trace(fadegpu_ctx *c, size_t bytes)
-{
-    if (bytes <= c->trace_bytes) return 0;
-    free_dev(c->d_trace);
-    c->trace_bytes = 0;
-    CU(c, cudaMalloc(&c->d_trace, bytes));
-    c->trace_bytes = bytes;
-    return 0;
-}
-
-int ensure_gen(fadegpu_ctx *c, size_t bytes)
-{
-    if (bytes <= c->gen_bytes) return 0;
-    free_dev(c->d_gen);
-    c->gen_bytes = 0;
-    CU(c, cudaMalloc(&c->d_gen, bytes));
-    c->gen_bytes = bytes;
-    return 0;
-}
-
 constexpr int GEN_SLOTS_MAX = 8192;
+constexpr int SPLIT_MAX = 1;     // (splitting costs more fill tails and traceback rounds than the overlap returns)
+constexpr int64_t SPLIT_MIN_ITEMS = 2048;
 constexpr size_t GEN_BUDGET = (size_t)4 << 30;
 
 size_t gen_slot_bytes(int qmax, int tmax)
@@ -292,6 +286,10 @@ int build_plan(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_aln, const int64_t *c
         // warp items of 8 alignments; split into launches that fit the checkpoint scratch
         const size_t cw = ck_words_of(R);
         int64_t a0 = first_aln;
+        // up to SPLIT_MAX launches per class (>= SPLIT_MIN_ITEMS warp items each) to alternate between the lanes
+        const int64_t class_items = (last_aln - first_aln + 7) / 8;
+        const int64_t n_split = c->n_lanes > 1 ? std::max<int64_t>(1, std::min<int64_t>(SPLIT_MAX, class_items / SPLIT_MIN_ITEMS)) : 1;
+        const int64_t items_per_launch = (class_items + n_split - 1) / n_split;
         while (a0 < last_aln) {
             Launch L{};
             L.R = R; L.aln_first = (int)a0; L.item_first = (int)n_items; L.qmax = qmax_all; L.tmax = tmax_all;
@@ -302,6 +300,7 @@ int build_plan(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_aln, const int64_t *c
                 const int nblk = num_blocks(sorted_tlen[a1]);  // longest of the 8 (sorted descending)
                 const size_t wds = (size_t)(nblk - 1) * cw * 32;
                 if (a1 > a0 && (words + wds) * 4 > (size_t)c->p.scratch_bytes) break;
+                if (n_items - L.item_first >= items_per_launch) break;
                 if (n_items >= b->cap_items) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: internal error (item capacity)");
                 WarpItem &it = b->h_items[n_items++];
                 it.ck_off = (int64_t)words;
@@ -329,18 +328,24 @@ int build_plan(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_aln, const int64_t *c
     b->st.scratch_bytes = (int64_t)ck_needed;
     // a slot for wildcard alignments discovered on the device, sized for the largest problem
     if (n_aln > 0) gen_needed = std::max(gen_needed, gen_slot_bytes(qmax_all, tmax_all));
-    if (ck_needed) { int rc = ensure_ck(c, ck_needed); if (rc) return rc; }
-    if (trace_needed) { int rc = ensure_trace(c, trace_needed); if (rc) return rc; }
-    if (gen_needed) {
-        const size_t want = std::min<size_t>(GEN_BUDGET, gen_needed * 1024);
-        int rc = ensure_gen(c, std::max(want, gen_needed));
-        if (rc) return rc;
+    for (int l = 0; l < (b->plan.empty() ? 0 : c->n_lanes); ++l) {
+        fadegpu_ctx::Lane &ln = c->lane[l];
+        if (ck_needed) { int rc = ensure_dev(c, (void **)&ln.d_ck, &ln.ck_bytes, ck_needed); if (rc) return rc; }
+        if (trace_needed) { int rc = ensure_dev(c, (void **)&ln.d_trace, &ln.trace_bytes, trace_needed); if (rc) return rc; }
+        if (gen_needed) {
+            const size_t want = std::min<size_t>(GEN_BUDGET, gen_needed * 1024);
+            int rc = ensure_dev(c, (void **)&ln.d_gen, &ln.gen_bytes, std::max(want, gen_needed));
+            if (rc) return rc;
+        }
     }
     return 0;
 }
 
-// queue every kernel of the batch's plan on the ctx stream; stage times via optional events
-int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, float *gen_ms, int *launches)
+// Queue every kernel of the batch's plan: fills on c->stream (after `dep`: the batch's inputs, or the
+// start of a timed replay), traceback + generic on c->tstream, consecutive launches on alternating
+// scratch sets.  On return b->ev_lane[0] marks the end of the batch's kernels; the caller joins it.
+// With stage timers every launch is synchronised.
+int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, float *gen_ms, int *launches, cudaEvent_t dep)
 {
     const bool timed = fill_ms != nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
@@ -349,17 +354,23 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
         *fill_ms = *trace_ms = *gen_ms = 0.f;
     }
     int nl = 0;
-    if (b->n_aln > 0) CU(c, cudaMemsetAsync(b->d_flags, 0, (size_t)b->n_aln * sizeof(uint32_t), c->stream));
+    cudaStream_t sf = c->stream, st = c->tstream;
+    if (dep) CU(c, cudaStreamWaitEvent(sf, dep, 0));
     for (const Launch &L : b->plan) {
+        fadegpu_ctx::Lane &ln = c->lane[c->next_lane++ % (unsigned)c->n_lanes];
+        // the lane's scratch is free again once its previous traceback is through
+        if (ln.used) CU(c, cudaStreamWaitEvent(sf, ln.ev_trace, 0));
+        ln.used = true;
+        const uint8_t *seq = b->dev_binning ? b->d_in_seq4 : b->d_seq;
         if (L.R != 0) {
             KernelArgs a;
             a.aln = b->d_aln + L.aln_first;
             a.n_aln = L.n_aln;
             a.items = b->d_items + L.item_first;
             a.n_items = L.n_items;
-            a.seq = b->dev_binning ? b->d_in_seq4 : b->d_seq;
+            a.seq = seq;
             a.ref = ref_dev(c);
-            a.ck = c->d_ck;
+            a.ck = ln.d_ck;
             a.fillres = b->d_fillres + (size_t)L.item_first * 32;
             a.aln_flags = b->d_flags + L.aln_first;
             a.out = b->d_out + L.aln_first;
@@ -367,39 +378,42 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
             a.min_length = c->p.min_length;
             a.tw_stride = L.tw_stride;
             {
-                uint8_t *p = c->d_trace;
+                uint8_t *p = ln.d_trace;
                 a.state = reinterpret_cast<LaneCtl *>(p); p += align256((size_t)L.n_aln * sizeof(LaneCtl));
                 a.queue[0] = reinterpret_cast<unsigned long long *>(p); p += align256((size_t)L.n_aln * 8);
                 a.queue[1] = reinterpret_cast<unsigned long long *>(p); p += align256((size_t)L.n_aln * 8);
                 a.tiles = reinterpret_cast<uint32_t *>(p);
-                a.qcount = c->d_qcount;
+                a.qcount = ln.d_qcount;
                 a.round = 0;
                 a.max_rounds = L.nblk_max + FG;   // each round scans one candidate block or walks one block
             }
-            if (timed) CU(c, cudaEventRecord(e0, c->stream));
-            CU(c, launch_fill(L.R, a, c->stream));
-            if (timed) CU(c, cudaEventRecord(e1, c->stream));
-            CU(c, cudaMemsetAsync(c->d_qcount, 0, 2 * sizeof(unsigned int), c->stream));
+            CU(c, cudaMemsetAsync(a.aln_flags, 0, (size_t)L.n_aln * sizeof(uint32_t), sf));
+            CU(c, cudaMemsetAsync(ln.d_qcount, 0, 2 * sizeof(unsigned int), sf));
+            if (timed) CU(c, cudaEventRecord(e0, sf));
+            CU(c, launch_fill(L.R, a, sf));
+            if (timed) CU(c, cudaEventRecord(e1, sf));
+            CU(c, cudaEventRecord(ln.ev_fill, sf));
+            CU(c, cudaStreamWaitEvent(st, ln.ev_fill, 0));
             nl += 1;   // the fill kernel; launch_trace adds its own launches
-            CU(c, launch_trace(L.R, a, c->stream, c->sm_count, &nl));
+            CU(c, launch_trace(L.R, a, st, c->sm_count, &nl));
             // wildcard letters found by the packed kernels -> generic kernel over the flagged ones
             GenericArgs ga;
             ga.aln = a.aln; ga.n_aln = L.n_aln; ga.aln_flags = a.aln_flags; ga.seq = a.seq; ga.ref = a.ref;
-            ga.out = a.out; ga.cursor = c->d_cursor; ga.scratch = c->d_gen;
+            ga.out = a.out; ga.cursor = ln.d_cursor; ga.scratch = ln.d_gen;
             ga.qmax = L.qmax; ga.tmax = L.tmax;
             ga.slot_bytes = (int64_t)gen_slot_bytes(L.qmax, L.tmax);
-            ga.n_slots = (int)std::max<size_t>(1, std::min<size_t>(GEN_SLOTS_MAX, c->gen_bytes / (size_t)ga.slot_bytes));
+            ga.n_slots = (int)std::max<size_t>(1, std::min<size_t>(GEN_SLOTS_MAX, ln.gen_bytes / (size_t)ga.slot_bytes));
             ga.chunk = 64;
             ga.open = c->p.gap_open; ga.extend = c->p.gap_extend; ga.match = c->p.match; ga.mismatch = c->p.mismatch;
             ga.min_length = c->p.min_length;
-            if (timed) CU(c, cudaEventRecord(e2, c->stream));
-            CU(c, cudaMemsetAsync(c->d_cursor, 0, sizeof(unsigned int), c->stream));
-            CU(c, launch_generic(ga, ga.n_slots, c->stream));
+            if (timed) CU(c, cudaEventRecord(e2, st));
+            CU(c, cudaMemsetAsync(ln.d_cursor, 0, sizeof(unsigned int), st));
+            CU(c, launch_generic(ga, ga.n_slots, st));
             nl += 1;
             if (timed) {
                 cudaEvent_t e3;
                 CU(c, cudaEventCreate(&e3));
-                CU(c, cudaEventRecord(e3, c->stream));
+                CU(c, cudaEventRecord(e3, st));
                 CU(c, cudaEventSynchronize(e3));
                 float t;
                 cudaEventElapsedTime(&t, e0, e1); *fill_ms += t;
@@ -407,31 +421,45 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
                 cudaEventElapsedTime(&t, e2, e3); *gen_ms += t;
                 cudaEventDestroy(e3);
             }
+            CU(c, cudaEventRecord(ln.ev_trace, st));
         } else {
             GenericArgs ga;
-            ga.aln = b->d_aln + L.aln_first; ga.n_aln = L.n_aln; ga.aln_flags = nullptr; ga.seq = b->dev_binning ? b->d_in_seq4 : b->d_seq;
-            ga.ref = ref_dev(c); ga.out = b->d_out + L.aln_first; ga.cursor = c->d_cursor; ga.scratch = c->d_gen;
+            ga.aln = b->d_aln + L.aln_first; ga.n_aln = L.n_aln; ga.aln_flags = nullptr; ga.seq = seq;
+            ga.ref = ref_dev(c); ga.out = b->d_out + L.aln_first; ga.cursor = ln.d_cursor; ga.scratch = ln.d_gen;
             ga.qmax = L.qmax; ga.tmax = L.tmax;
             ga.slot_bytes = (int64_t)gen_slot_bytes(L.qmax, L.tmax);
-            ga.n_slots = (int)std::max<size_t>(1, std::min<size_t>(GEN_SLOTS_MAX, c->gen_bytes / (size_t)ga.slot_bytes));
+            ga.n_slots = (int)std::max<size_t>(1, std::min<size_t>(GEN_SLOTS_MAX, ln.gen_bytes / (size_t)ga.slot_bytes));
             ga.n_slots = std::min(ga.n_slots, std::max(L.n_aln, 1));
             ga.chunk = 1;
             ga.open = c->p.gap_open; ga.extend = c->p.gap_extend; ga.match = c->p.match; ga.mismatch = c->p.mismatch;
             ga.min_length = c->p.min_length;
-            if (timed) CU(c, cudaEventRecord(e0, c->stream));
-            CU(c, cudaMemsetAsync(c->d_cursor, 0, sizeof(unsigned int), c->stream));
-            CU(c, launch_generic(ga, ga.n_slots, c->stream));
+            CU(c, cudaEventRecord(ln.ev_fill, sf));        // (orders the lane: dep and the previous traceback)
+            CU(c, cudaStreamWaitEvent(st, ln.ev_fill, 0));
+            if (timed) CU(c, cudaEventRecord(e0, st));
+            CU(c, cudaMemsetAsync(ln.d_cursor, 0, sizeof(unsigned int), st));
+            CU(c, launch_generic(ga, ga.n_slots, st));
             nl += 1;
             if (timed) {
-                CU(c, cudaEventRecord(e1, c->stream));
+                CU(c, cudaEventRecord(e1, st));
                 CU(c, cudaEventSynchronize(e1));
                 float t;
                 cudaEventElapsedTime(&t, e0, e1); *gen_ms += t;
             }
+            CU(c, cudaEventRecord(ln.ev_trace, st));
         }
     }
     if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
+    b->lanes_used = 1;
+    // every launch ends on tstream, in launch order: its tail is the batch's
+    CU(c, cudaEventRecord(b->ev_lane[0], b->plan.empty() ? sf : st));
     if (launches) *launches = nl;
+    return 0;
+}
+
+// the stream `s` continues after every lane the batch used
+int join_lanes(fadegpu_ctx *c, fadegpu_batch *b, cudaStream_t s)
+{
+    for (int l = 0; l < b->lanes_used; ++l) CU(c, cudaStreamWaitEvent(s, b->ev_lane[l], 0));
     return 0;
 }
 
@@ -500,10 +528,18 @@ int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
     c->k = make_consts(pp.gap_open, pp.gap_extend, pp.match, pp.mismatch);
     if (pp.flags & FADEGPU_F_NO_SHORTCUT) c->k.shortcut = 0;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc(&c->d_cursor, sizeof(unsigned int))) != cudaSuccess || (e = cudaMalloc(&c->d_alu, 64)) != cudaSuccess ||
-        (e = cudaMalloc(&c->d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, -1)) != cudaSuccess ||
-        (e = cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, -1)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_alu, 64)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&c->tstream, cudaStreamNonBlocking, -1)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->lane[0].ev_fill, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->lane[1].ev_fill, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->lane[0].ev_trace, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->lane[1].ev_trace, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaMalloc(&c->lane[0].d_cursor, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(&c->lane[1].d_cursor, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(&c->lane[0].d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(&c->lane[1].d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, -2)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, -2)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "fadegpu_create");
         delete c;
@@ -526,7 +562,13 @@ void fadegpu_destroy(fadegpu_ctx *c)
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
     free_reference(c);
-    free_dev(c->d_ck); free_dev(c->d_gen); free_dev(c->d_cursor); free_dev(c->d_alu); free_dev(c->d_trace); free_dev(c->d_qcount);
+    if (c->tstream) { cudaStreamSynchronize(c->tstream); cudaStreamDestroy(c->tstream); }
+    for (auto &ln : c->lane) {
+        if (ln.ev_fill) cudaEventDestroy(ln.ev_fill);
+        if (ln.ev_trace) cudaEventDestroy(ln.ev_trace);
+    }
+    for (auto &ln : c->lane) { free_dev(ln.d_ck); free_dev(ln.d_gen); free_dev(ln.d_cursor); free_dev(ln.d_trace); free_dev(ln.d_qcount); }
+    free_dev(c->d_alu);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -539,7 +581,7 @@ int fadegpu_load_reference(fadegpu_ctx *c, int32_t n_contigs, const char *const 
     drain_submits(c);
     std::lock_guard<std::mutex> submit_guard(c->submit_mu);
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->stream));
+    { CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaStreamSynchronize(c->tstream)); }
     free_reference(c);
     c->n_contigs = n_contigs;
     int64_t off = 0, total = 0;
@@ -628,7 +670,7 @@ int fadegpu_share_reference(fadegpu_ctx *dst, const fadegpu_ctx *src)
     drain_submits(dst);
     std::lock_guard<std::mutex> submit_guard(dst->submit_mu);
     CU(dst, cudaSetDevice(dst->device));
-    CU(dst, cudaStreamSynchronize(dst->stream));
+    { CU(dst, cudaStreamSynchronize(dst->stream)); CU(dst, cudaStreamSynchronize(dst->tstream)); }
     free_reference(dst);
     dst->n_contigs = src->n_contigs; dst->names = src->names; dst->clen = src->clen; dst->coff = src->coff;
     dst->total_bases = src->total_bases; dst->padded_bases = src->padded_bases; dst->n_x = src->n_x;
@@ -662,7 +704,7 @@ void fadegpu_free_batch(fadegpu_batch *b)
     if (!b) return;
     fadegpu_ctx *c = b->ctx;
     if (c) { std::unique_lock<std::mutex> lk(c->q_mu); c->done_cv.wait(lk, [&] { return !b->queued; }); }
-    if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); if (c->stream2) cudaStreamSynchronize(c->stream2); if (c->stream3) cudaStreamSynchronize(c->stream3); }
+    if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); if (c->tstream) cudaStreamSynchronize(c->tstream); if (c->stream2) cudaStreamSynchronize(c->stream2); if (c->stream3) cudaStreamSynchronize(c->stream3); }
     fadegpu_batch_view &v = b->v;
     free_host(v.seq4); free_host(v.seq_off); free_host(v.l_qseq); free_host(v.tid); free_host(v.pos);
     free_host(v.aligned_len); free_host(v.clip_left); free_host(v.clip_right);
@@ -681,6 +723,7 @@ void fadegpu_free_batch(fadegpu_batch *b)
     if (b->ev_prep) cudaEventDestroy(b->ev_prep);
     if (b->ev_ready) cudaEventDestroy(b->ev_ready);
     if (b->ev_done) cudaEventDestroy(b->ev_done);
+    for (auto &e : b->ev_lane) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto &e : b->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     delete b;
 }
@@ -729,6 +772,7 @@ int fadegpu_alloc_batch(fadegpu_ctx *c, int64_t max_reads, int64_t max_seq_bytes
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_prep);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_ready);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
+    for (auto &ev : b->ev_lane) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto &ev : b->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e != cudaSuccess) {
         int rc = cuda_fail(c, e, "fadegpu_alloc_batch");
@@ -968,11 +1012,10 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     CU(c, cudaStreamWaitEvent(c->stream, b->ev_ready, 0));
     CU(c, cudaEventRecord(b->ev[1], c->stream));
     int nl = 0;
-    { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl); if (rc) return rc; }
+    { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl, b->ev_ready); if (rc) return rc; }
     b->st.kernel_launches = nl;
-    CU(c, cudaEventRecord(b->ev[2], c->stream));
-    CU(c, cudaEventRecord(b->ev_done, c->stream));
-    CU(c, cudaStreamWaitEvent(c->stream3, b->ev_done, 0));
+    { int rc = join_lanes(c, b, c->stream3); if (rc) return rc; }
+    CU(c, cudaEventRecord(b->ev[2], c->stream3));
     if (n_aln > 0)
         CU(c, cudaMemcpyAsync(b->h_out, b->d_out, (size_t)n_aln * sizeof(AlnOut), cudaMemcpyDeviceToHost, c->stream3));
     b->st.d2h_bytes = n_aln * (int64_t)sizeof(AlnOut);
@@ -1161,13 +1204,12 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
     CU(c, cudaStreamWaitEvent(c->stream, b->ev_ready, 0));
     CU(c, cudaEventRecord(b->ev[1], c->stream));
     int nl = 0;
-    { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl); if (rc) return rc; }
+    { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl, b->ev_ready); if (rc) return rc; }
     b->st.kernel_launches = nl + (n > 0 ? 1 : 0) + (n_aln > 0 ? (pull ? 3 : 2) : 0);
-    CU(c, cudaEventRecord(b->ev[2], c->stream));
-    if (n_aln > 0) CU(c, launch_result_index(b->d_out, (int)n_aln, n_reads, b->d_rflags, b->d_ridx, b->d_stats + 7, c->stream));
-    CU(c, cudaEventRecord(b->ev_done, c->stream));
     cudaStream_t s3 = c->stream3;                    // results go home while the next batch computes
-    CU(c, cudaStreamWaitEvent(s3, b->ev_done, 0));
+    { int rc = join_lanes(c, b, s3); if (rc) return rc; }
+    CU(c, cudaEventRecord(b->ev[2], s3));
+    if (n_aln > 0) CU(c, launch_result_index(b->d_out, (int)n_aln, n_reads, b->d_rflags, b->d_ridx, b->d_stats + 7, s3));
     if (n_reads > 0) {
         CU(c, cudaMemcpyAsync(b->v.flags, b->d_rflags, (size_t)n_reads, cudaMemcpyDeviceToHost, s3));
         CU(c, cudaMemcpyAsync(b->h_ridx, b->d_ridx, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, s3));
@@ -1363,13 +1405,47 @@ int fadegpu_replay_kernels(fadegpu_ctx *c, fadegpu_batch *b, int32_t iters, floa
     CU(c, cudaSetDevice(c->device));
     // one pass with per-stage events (serialising), then `iters` untouched passes for the total
     float f = 0, t = 0, g = 0;
-    { int rc = run_plan(c, b, &f, &t, &g, nullptr); if (rc) return rc; }
+    { int rc = run_plan(c, b, &f, &t, &g, nullptr, nullptr); if (rc) return rc; }
     b->st.fill_ms = f; b->st.trace_ms = t; b->st.generic_ms = g;
     cudaEvent_t e0, e1;
     CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
-    CU(c, cudaStreamSynchronize(c->stream));
+    { CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaStreamSynchronize(c->tstream)); }
     CU(c, cudaEventRecord(e0, c->stream));
-    for (int i = 0; i < iters; ++i) { int rc = run_plan(c, b, nullptr, nullptr, nullptr, nullptr); if (rc) return rc; }
+    for (int i = 0; i < iters; ++i) { int rc = run_plan(c, b, nullptr, nullptr, nullptr, nullptr, nullptr); if (rc) return rc; }
+    { int rc = join_lanes(c, b, c->stream); if (rc) return rc; }
+    CU(c, cudaEventRecord(e1, c->stream));
+    CU(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(c, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms;
+    return FADEGPU_OK;
+}
+
+int fadegpu_replay_batches(fadegpu_ctx *c, fadegpu_batch *const *batches, int32_t n_batches, int32_t iters, float *ms_out)
+{
+    if (!c || !batches || n_batches <= 0 || iters <= 0) return fail(c, FADEGPU_E_ARG, "fadegpu_replay_batches: bad arguments");
+    for (int32_t i = 0; i < n_batches; ++i) {
+        fadegpu_batch *b = batches[i];
+        if (!b || b->ctx != c) return fail(c, FADEGPU_E_ARG, "fadegpu_replay_batches: bad batch");
+        if (b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_replay_batches: batch in flight");
+        if (b->plan.empty() && b->n_aln > 0) return fail(c, FADEGPU_E_STATE, "fadegpu_replay_batches: nothing submitted");
+    }
+    drain_submits(c);
+    std::lock_guard<std::mutex> submit_guard(c->submit_mu);
+    CU(c, cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
+    { CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaStreamSynchronize(c->tstream)); }
+    CU(c, cudaEventRecord(e0, c->stream));
+    fadegpu_batch *last = nullptr;
+    for (int32_t it = 0; it < iters; ++it)
+        for (int32_t i = 0; i < n_batches; ++i) {
+            int rc = run_plan(c, batches[i], nullptr, nullptr, nullptr, nullptr, nullptr);
+            if (rc) return rc;
+            last = batches[i];
+        }
+    { int rc = join_lanes(c, last, c->stream); if (rc) return rc; }
     CU(c, cudaEventRecord(e1, c->stream));
     CU(c, cudaEventSynchronize(e1));
     float ms = 0;

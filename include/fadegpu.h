@@ -193,6 +193,11 @@ int fadegpu_get_results(const fadegpu_batch *b, fadegpu_results_view *r);
  * stream.  ms_out receives the device milliseconds of `iters` passes. */
 int fadegpu_get_stats(const fadegpu_batch *b, fadegpu_stats *s);
 int fadegpu_replay_kernels(fadegpu_ctx *ctx, fadegpu_batch *b, int32_t iters, float *ms_out);
+/* The same over several resident batches of the ctx, queued back to back the way consecutive submits
+ * queue them (the traceback rounds of one batch run under the fill of the next): device
+ * milliseconds of `iters` passes over all of them, first fill to last traceback. */
+int fadegpu_replay_batches(fadegpu_ctx *ctx, fadegpu_batch *const *batches, int32_t n_batches, int32_t iters,
+                           float *ms_out);
 
 /* INT16x2 ALU roofline denominator: measures packed VIMNMX/VIADDMNMX issue rate.
  * ops_per_sec_out = packed (2-lane) instructions * 32 threads per second over the whole GPU. */
