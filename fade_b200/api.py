@@ -3,6 +3,7 @@ mirrors source/anno.d:44-50 + annotateTask (source/anno.d:55-110) in batched for
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -60,6 +61,7 @@ class Context:
             raise FadeGpuError(rc, lib().fadegpu_last_error(None).decode())
         self.device = device
         self.contig_names: list[str] = []
+        self._batches = weakref.WeakSet()      # freed before the ctx: a batch must not outlive it
 
     def _check(self, rc: int):
         if rc:
@@ -100,6 +102,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for b in list(self._batches):
+                b.close()
             lib().fadegpu_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -123,6 +127,7 @@ class Batch:
         self.ctx = ctx
         self._h = C.c_void_p()
         ctx._check(lib().fadegpu_alloc_batch(ctx._h, max_reads, max_seq_bytes, C.byref(self._h)))
+        ctx._batches.add(self)
         v = BatchView()
         ctx._check(lib().fadegpu_get_batch_view(self._h, C.byref(v)))
         self.max_reads, self.max_seq_bytes = max_reads, max_seq_bytes

@@ -169,7 +169,9 @@ int fadegpu_submit_inputs(fadegpu_ctx *ctx, fadegpu_batch *b, int64_t n_reads, c
 int fadegpu_wait(fadegpu_ctx *ctx, fadegpu_batch *b);
 
 /* Compact results of the last fadegpu_wait: one record per read for which SW ran, in the
- * library's processing order, plus a per-read index into them.  Always filled (cheaper for the
+ * library's processing order (by window length; unspecified among equal lengths, so it may differ
+ * between two runs on the same input -- address records through result_index), plus a per-read
+ * index into them.  Always filled (cheaper for the
  * host than the per-read arrays of the view: nothing is scattered but flags[] and the index). */
 typedef struct fadegpu_result {
     int32_t score;                 /* res.score */

@@ -338,3 +338,62 @@ def test_device_and_host_binning_agree(flags):
         b.run(0)                                   # empty batch through the device path
         assert b.stats().n_aligned == 0
         b.close()
+
+
+def test_many_batches_in_flight_and_replay_batches():
+    """Asynchronous submits: six batches queued before the first wait (uploads, binning, fills and the
+    traceback rounds of neighbouring batches overlap on the ctx's streams and its two scratch sets);
+    every one equals the oracle.  fadegpu_replay_batches then re-runs only the kernels of all of them and
+    leaves the results untouched."""
+    rng = random.Random(77)
+    contigs = [readsets.random_ref(rng, n) for n in (20000, 3000)]
+    rds = [readsets.build(readsets.ragged_reads(random.Random(300 + k), contigs, 1500 + 200 * k, max_len=300)) for k in range(6)]
+    with _ctx() as ctx:
+        ctx.load_reference(["a", "b"], contigs)
+        bs = [ctx.alloc_batch(r.n, int(r.seq_off[r.n])) for r in rds]
+        for b, r in zip(bs, rds):
+            b.fill(r.seq4, r.seq_off, r.l_qseq, r.tid, r.pos, r.aligned_len, r.clip_left, r.clip_right)
+            b.submit()
+        for b in bs:
+            b.wait()
+        for b, r in zip(bs, rds):
+            compare(b, r, contigs, oracle_params(ctx.params))
+        def by_read(b):                                      # the order of the records within a window length is unspecified
+            rec = b.results()[0]
+            return rec[np.argsort(rec["read"])].copy()
+        before = [by_read(b) for b in bs]
+        ms = ctx.replay_batches(bs, 2)
+        assert ms > 0
+        ms1 = sum(b.replay_kernels(1) for b in bs)
+        assert ms1 > 0
+        for b, r, rec in zip(bs, rds, before):
+            b.run()                                          # fresh D2H of what the kernels left in HBM
+            assert np.array_equal(by_read(b), rec)
+        for b in bs:
+            b.close()
+
+
+def test_errors_of_a_queued_submit_surface_at_wait():
+    """inconsistent seq_off: FADEGPU_E_ARG from fadegpu_wait (queued submit) or from fadegpu_submit itself
+    (FADEGPU_F_SYNC_SUBMIT); the batch and the ctx stay usable afterwards."""
+    rng = random.Random(5)
+    contigs = [readsets.random_ref(rng, 4000)]
+    rd = readsets.build(readsets.ragged_reads(rng, contigs, 200, max_len=150))
+    for flags in (0, api.F_SYNC_SUBMIT):
+        with _ctx(flags=flags) as ctx:
+            ctx.load_reference(["a"], contigs)
+            b = ctx.alloc_batch(rd.n, int(rd.seq_off[rd.n]))
+            b.fill(rd.seq4, rd.seq_off, rd.l_qseq, rd.tid, rd.pos, rd.aligned_len, rd.clip_left, rd.clip_right)
+            k = int(np.flatnonzero(rd.clip_left > 10)[0])
+            b.seq_off[k] = int(rd.seq_off[rd.n]) + 5        # points past the end of seq4
+            if flags:
+                with pytest.raises(api.FadeGpuError) as e:
+                    b.submit()
+            else:
+                b.submit()
+                with pytest.raises(api.FadeGpuError) as e:
+                    b.wait()
+            assert "seq_off" in str(e.value)
+            b.fill(rd.seq4, rd.seq_off, rd.l_qseq, rd.tid, rd.pos, rd.aligned_len, rd.clip_left, rd.clip_right).run()
+            compare(b, rd, contigs, oracle_params(ctx.params))
+            b.close()
