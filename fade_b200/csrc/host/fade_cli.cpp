@@ -1,10 +1,10 @@
 // fade_cli.cpp -- C++ host driver `fade-b200 annotate`: the batched mirror of fade's annotate()
 // (source/anno.d:16-52) on top of the C ABI (include/fadegpu.h, include/fadehost.h).
 //
-// The reference host is D + dhtslib/htslib; neither is available here, so this harness speaks SAM
-// text only (the reference's default output container, util.d:65-76 case 0) and a plain FASTA.
-// It keeps the reference's flags and tag schema:
-//     fade-b200 annotate [-t N] [--min-length N] [-w N | --window-size N] <in.sam|-> <ref.fa>  > out.sam
+// The reference host is D + dhtslib/htslib; neither is available here, so record I/O is samio.hpp:
+// SAM text or BAM in (recognised by content), SAM text (default), BAM (-b) or uncompressed BAM (-u)
+// out, as util.d:65-76; the reference is a plain FASTA.  Flags and tag schema are the reference's:
+//     fade-b200 annotate [-t N] [--min-length N] [-w N | --window-size N] [-b|-u] <in.sam|in.bam|-> <ref.fa>  > out
 // Every record gets rs:i (anno.d:94); artifact records get am/as/ar/ab:Z (anno.d:98-107); a
 // @PG ID:fade-annotate line is appended to the header (anno.d:25-32).  Records are written in
 // input order (the reference's order is unspecified, anno.d:19).
@@ -21,10 +21,34 @@
 #include <vector>
 #include "../../../include/fadegpu.h"
 #include "../../../include/fadehost.h"
+#include "samio.hpp"
 
 namespace {
 
 const char *kVersion = "fade-b200-0.1";
+
+samio::LineSink *g_out = nullptr;   // stdout as SAM text, uBAM or BAM (util.d:65-76)
+
+bool out_line(const std::string &l)
+{
+    if (g_out->put(l)) return true;
+    fprintf(stderr, "fade-b200: cannot encode record for BAM output: %s\n", l.c_str());
+    return false;
+}
+
+// -b / --bam, -u / --ubam as in app.d:82-83,94 (con = bam << 1 | ubam)
+bool output_flag(const std::string &a, int &con)
+{
+    if (a == "-b" || a == "--bam") { con |= 2; return true; }
+    if (a == "-u" || a == "--ubam") { con |= 1; return true; }
+    return false;
+}
+
+void open_output(int con)
+{
+    static samio::LineSink sink(stdout, con == 0 ? samio::LineSink::SAM : con == 1 ? samio::LineSink::UBAM : samio::LineSink::BAM);
+    g_out = &sink;
+}
 
 struct Rec {
     std::string line;            // the record without trailing newline (tags rs/am/as/ar/ab stripped)
@@ -100,7 +124,9 @@ int usage()
             "fade-b200 out [-c] <annotated SAM or ->      removes (or with -c hard-clips) artifact reads\n"
             "fade-b200 extract <annotated SAM or ->       emits the artifacts in their re-mapped state\n"
             "fade-b200 annotate: marks artifact reads in bam tags (B200 implementation of `fade annotate`)\n"
-            "usage: fade-b200 annotate [options] <SAM or -> <FASTA>   (SAM text in, SAM text out)\n"
+            "fade-b200 view <SAM/BAM or ->                 copies the records (format conversion)\n"
+            "every command: -b / --bam writes BAM, -u / --ubam uncompressed BAM, default SAM text; input may be SAM or BAM\n"
+            "usage: fade-b200 annotate [options] <SAM/BAM or -> <FASTA>\n"
             "  -t, --threads N      host threads (default: all cores)\n"
             "      --min-length N   minimum soft-clip length considered (default 5)\n"
             "  -w, --window-size N  bases considered outside of the read region (default 300)\n"
@@ -116,7 +142,7 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
     fadegpu_params prm;
     fadegpu_default_params(&prm);
     int64_t batch_n = 1 << 20;
-    int device = 0;
+    int device = 0, con = 0;
     std::vector<std::string> pos_args;
     for (int i = 2; i < argc; ++i) {
         const std::string a = argv[i];
@@ -130,28 +156,24 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
         else if (a == "--batch") batch_n = atoll(need("--batch"));
         else if (a == "--device") device = atoi(need("--device"));
         else if (a == "-h" || a == "--help") return usage();
-        else if (a == "-b" || a == "--bam" || a == "-u" || a == "--ubam") {
-            fprintf(stderr, "fade-b200: BAM output needs htslib, which this harness does not link; SAM text only\n");
-            return 1;
-        } else pos_args.push_back(a);
+        else if (output_flag(a, con)) {}
+        else pos_args.push_back(a);
     }
     if (pos_args.size() < 2) { usage(); return 0; }
+    if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    open_output(con);
     fprintf(stderr, "[W::fade annotate] Output SAM will keep the input order\n");
 
     // ---- header ----
-    std::istream *in = &std::cin;
-    std::ifstream fin;
-    if (pos_args[0] != "-") {
-        fin.open(pos_args[0]);
-        if (!fin) { fprintf(stderr, "fade-b200: cannot open %s\n", pos_args[0].c_str()); return 1; }
-        in = &fin;
-    }
+    samio::LineSource src;
+    if (!src.open(pos_args[0])) { fprintf(stderr, "fade-b200: cannot open %s\n", pos_args[0].c_str()); return 1; }
+    samio::LineSource *in = &src;
     std::vector<std::string> header;
     std::vector<std::string> sq_names;
     std::vector<int64_t> sq_len;
     std::string last_pg_id, line;
     bool have_line = false;
-    while (std::getline(*in, line)) {
+    while (in->getline(line)) {
         if (line.empty() || line[0] != '@') { have_line = true; break; }
         header.push_back(line);
         const auto f = split_tab(line);
@@ -168,7 +190,7 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
     if (!last_pg_id.empty()) pg += "\tPP:" + last_pg_id;
     pg += "\tCL:" + cl;
     header.push_back(pg);
-    for (const auto &h : header) { fputs(h.c_str(), stdout); fputc('\n', stdout); }
+    for (const auto &h : header) out_line(h);
 
     // ---- reference: anno.d:23; contigs in @SQ order so that tid indexes them ----
     std::map<std::string, std::string> fasta;
@@ -237,11 +259,13 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
                                            v.n_ops[k], v.ops + (size_t)k * FADEGPU_MAX_OPS, &rs, &am[0], &as_[0], &ar[0],
                                            &ab[0], cap);
             if (rc < 0) { fprintf(stderr, "fade-b200: tag buffer too small\n"); return 1; }
-            fputs(r.line.c_str(), stdout);
-            fprintf(stdout, "\trs:i:%u", (unsigned)rs);                                   // anno.d:94
-            if (rc == 1)                                                                  // anno.d:98-107
-                fprintf(stdout, "\tam:Z:%s\tas:Z:%s\tar:Z:%s\tab:Z:%s", am.c_str(), as_.c_str(), ar.c_str(), ab.c_str());
-            fputc('\n', stdout);
+            std::string o = r.line;
+            o += "\trs:i:" + std::to_string((unsigned)rs);                                // anno.d:94
+            if (rc == 1) {                                                                // anno.d:98-107
+                o += "\tam:Z:"; o += am.c_str(); o += "\tas:Z:"; o += as_.c_str();
+                o += "\tar:Z:"; o += ar.c_str(); o += "\tab:Z:"; o += ab.c_str();
+            }
+            if (!out_line(o)) return 1;
             n_art += rc == 1;
             n_sc += rs & 1;
         }
@@ -288,9 +312,11 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
             recs.push_back(std::move(r));
             if ((int64_t)recs.size() == batch_n || seq_bytes + 1024 > max_seq) { if (flush()) return 1; seq_bytes = 0; }
         }
-        have_line = (bool)std::getline(*in, line);
+        have_line = in->getline(line);
     }
+    if (src.failed()) { fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
     if (flush()) return 1;
+    g_out->close();
     fprintf(stderr, "[fade-b200 annotate] %lld records, %lld soft-clipped, %lld with artifact tags\n", (long long)n_total,
             (long long)n_sc, (long long)n_art);
     fadegpu_free_batch(bt);
@@ -330,11 +356,10 @@ struct Sam {
 
 bool read_sam(const std::string &path, Sam &sam)
 {
-    std::istream *in = &std::cin;
-    std::ifstream fin;
-    if (path != "-") { fin.open(path); if (!fin) return false; in = &fin; }
+    samio::LineSource in;
+    if (!in.open(path)) return false;
     std::string line;
-    while (std::getline(*in, line)) {
+    while (in.getline(line)) {
         if (!line.empty() && line.back() == '\r') line.pop_back();
         if (line.empty()) continue;
         if (line[0] == '@') {
@@ -351,16 +376,16 @@ bool read_sam(const std::string &path, Sam &sam)
         r.tags.assign(f.begin() + 11, f.end());
         sam.recs.push_back(std::move(r));
     }
-    return true;
+    return !in.failed();
 }
 
 void write_header(const Sam &sam, const char *id, const std::string &cl)
 {
-    for (auto &h : sam.header) { fputs(h.c_str(), stdout); fputc('\n', stdout); }
+    for (auto &h : sam.header) out_line(h);
     std::string pg = std::string("@PG\tID:") + id + "\tPN:fade\tVN:" + kVersion;   // filter.d:171-178, remap.d:19-26
     if (!sam.last_pg.empty()) pg += "\tPP:" + sam.last_pg;
     pg += "\tCL:" + cl;
-    fputs(pg.c_str(), stdout); fputc('\n', stdout);
+    out_line(pg);
 }
 
 typedef std::vector<std::pair<long, char>> Cig;
@@ -485,20 +510,23 @@ int rs_of(const SamRec &r, bool &have)
 int cmd_out(int argc, char **argv, const std::string &cl)
 {
     bool clip = false;
+    int con = 0;
     std::string path;
     for (int i = 2; i < argc; ++i) {
         const std::string a = argv[i];
         if (a == "-c" || a == "--clip") clip = true;
         else if (a == "-t" || a == "--threads") ++i;
-        else if (a == "-b" || a == "-u" || a == "--bam" || a == "--ubam") { fprintf(stderr, "fade-b200: SAM text only\n"); return 1; }
+        else if (output_flag(a, con)) {}
         else path = a;
     }
     if (path.empty()) return usage();
+    if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    open_output(con);
     Sam sam;
     if (!read_sam(path, sam)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
     write_header(sam, "fade-extract", cl);   // sic: filter.d:173 uses the ID of extract
     OutStats st;
-    auto put = [](const SamRec &r) { fputs(r.line().c_str(), stdout); fputc('\n', stdout); };
+    auto put = [](const SamRec &r) { out_line(r.line()); };
     if (clip) {   // filter.d:182-208
         for (auto &r : sam.recs) {
             ++st.read_count;
@@ -543,14 +571,25 @@ int cmd_out(int argc, char **argv, const std::string &cl)
         }
     }
     st.print();
+    g_out->close();
     return 0;
 }
 
 int cmd_extract(int argc, char **argv, const std::string &cl)
 {
-    if (argc < 3) return usage();
+    int con = 0;
+    std::string path;
+    for (int i = 2; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a == "-t" || a == "--threads") ++i;
+        else if (output_flag(a, con)) {}
+        else path = a;
+    }
+    if (path.empty()) return usage();
+    if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    open_output(con);
     Sam sam;
-    if (!read_sam(argv[argc - 1], sam)) { fprintf(stderr, "fade-b200: cannot read %s\n", argv[argc - 1]); return 1; }
+    if (!read_sam(path, sam)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
     write_header(sam, "fade-extract", cl);
     static const char comp[] = "=TGKCYSBAWRDMHVN";   // complement of "=ACMGRSVTWYHKDBN" (util.d:18-21)
     static const char nt16[] = "=ACMGRSVTWYHKDBN";
@@ -569,11 +608,39 @@ int cmd_extract(int argc, char **argv, const std::string &cl)
             const std::string qual(r.f[10].rbegin(), r.f[10].rend());
             const int flag = (atoi(r.f[1].c_str()) & 16) ? 0 : 16;
             const bool hc = !sam.contigs.empty();
-            fprintf(stdout, "%s\t%d\t%s\t%ld\t0\t%s\t%s\t%s\t0\t%s\t%s\n", r.f[0].c_str(), flag, tid >= 0 ? chrom.c_str() : "*",
-                    atol(pos0.c_str()) + 1, cig.c_str(), tid == 0 ? "=" : (hc ? sam.contigs[0].c_str() : "*"), hc ? "1" : "0",
-                    seq.c_str(), qual.c_str());
+            std::string o = r.f[0] + "\t" + std::to_string(flag) + "\t" + (tid >= 0 ? chrom : std::string("*")) + "\t" +
+                            std::to_string(atol(pos0.c_str()) + 1) + "\t0\t" + cig + "\t" +
+                            (tid == 0 ? std::string("=") : (hc ? sam.contigs[0] : std::string("*"))) + "\t" + (hc ? "1" : "0") +
+                            "\t0\t" + seq + "\t" + qual;
+            if (!out_line(o)) return 1;
         }
     }
+    g_out->close();
+    return 0;
+}
+
+// format conversion only: every header line and record, unchanged (SAM <-> BAM)
+int cmd_view(int argc, char **argv)
+{
+    int con = 0;
+    std::string path;
+    for (int i = 2; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (output_flag(a, con)) {}
+        else path = a;
+    }
+    if (path.empty()) return usage();
+    if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    open_output(con);
+    samio::LineSource in;
+    if (!in.open(path)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
+    std::string line;
+    while (in.getline(line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!line.empty() && !out_line(line)) return 1;
+    }
+    if (in.failed()) { fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
+    g_out->close();
     return 0;
 }
 
@@ -587,6 +654,7 @@ int main(int argc, char **argv)
     if (strcmp(argv[1], "annotate") == 0) return cmd_annotate(argc, argv, cl);
     if (strcmp(argv[1], "out") == 0) return cmd_out(argc, argv, cl);
     if (strcmp(argv[1], "extract") == 0) return cmd_extract(argc, argv, cl);
+    if (strcmp(argv[1], "view") == 0) return cmd_view(argc, argv);
     usage();
     return 1;
 }

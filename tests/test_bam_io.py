@@ -1,0 +1,115 @@
+"""Record I/O of the C++ driver without htslib (fade_b200/csrc/host/samio.hpp): SAM text
+and BGZF/BAM both ways, against the independent codec tests/bamcodec.py.  Pure host code, no GPU.
+The reference gets this from dhtslib/htslib (anno.d:22, util.d:65-76); PARITY UNPINNED with respect to
+htslib's exact bytes -- what is checked is the SAM/BAM specification and htslib's text conventions."""
+import os
+import random
+import subprocess
+
+import bamcodec
+from test_cli_consumers import BIN, annotated_sam
+
+HEADER = ["@HD\tVN:1.6\tSO:unsorted", "@SQ\tSN:chrA\tLN:100000", "@SQ\tSN:chrB\tLN:5000", "@RG\tID:g1\tSM:s",
+          "@PG\tID:bwa\tPN:bwa\tCL:bwa mem ref.fa r.fq"]
+
+
+def rich_lines(n=400, seed=9):
+    """records exercising every field shape: unmapped, '*' SEQ/QUAL/CIGAR, RNEXT '=', long reads, every aux type"""
+    rng = random.Random(seed)
+    out = list(HEADER)
+    for k in range(n):
+        L = rng.choice([0, 1, 2, 7, 50, 151, 600])
+        seq = "".join(rng.choice("ACGTNRYKM") for _ in range(L)) or "*"
+        qual = "*" if L == 0 or k % 7 == 0 else "".join(chr(33 + rng.randrange(42)) for _ in range(L))
+        unmapped = k % 11 == 0
+        cig = "*" if unmapped or L == 0 else (f"{L}M" if k % 3 else f"3S{max(L - 5, 1)}M2S" if L > 6 else f"{L}M")
+        rname = "*" if unmapped else rng.choice(["chrA", "chrB"])
+        pos = 0 if unmapped else rng.randrange(1, 4000)
+        rnext = rng.choice(["*", "=", "chrB"]) if not unmapped else "*"
+        if rnext == rname and rname != "*":
+            rnext = "="                      # what htslib prints when the mate is on the same contig
+        f = [f"read{k}/x", str(rng.choice([0, 4, 16, 99, 147, 2048, 2064])), rname, str(pos), str(rng.randrange(61)), cig, rnext,
+             str(0 if rnext == "*" else rng.randrange(1, 5000)), str(rng.randrange(-900, 900)), seq, qual]
+        f += [f"NM:i:{rng.choice([0, 3, 200, 255, 256, 65535, 65536, -1, -128, -129, -32768, -32769, 2000000000])}",
+              f"XA:A:{rng.choice('abXY+')}", f"XF:f:{rng.choice(['0.5', '3', '-1.25', '1e+10', '0.001'])}",
+              f"SA:Z:chrA,{k + 1},+,50M100S,60,0;", f"XH:H:{rng.choice(['1AE301', '', 'FF'])}",
+              f"XB:B:{rng.choice(['c,-1,2,127', 'C,0,255', 's,-300,300', 'S,65535', 'i,-70000,70000', 'I,4000000000', 'f,0.5,-2'])}"]
+        if k % 5 == 0:
+            f += ["rs:i:3", "am:Z:chrA,100,50S100=;", "ab:Z:III;II"]
+        out.append("\t".join(f))
+    return out
+
+
+def cli(args, data=None, path=None):
+    p = subprocess.run([BIN, *args, str(path) if path else "-"], input=data, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    return p.stdout
+
+
+def test_sam_to_bam_matches_independent_codec():
+    lines = rich_lines()
+    sam = ("\n".join(lines) + "\n").encode()
+    for flag, level in (("-b", 6), ("-u", 0)):
+        bam = cli(["view", flag], sam)
+        assert bamcodec.decode(bam) == lines                                     # our writer, their reader
+        assert bgzf_payload(bam) == bgzf_payload(bamcodec.encode(lines, level))  # same uncompressed BAM stream, byte for byte
+    assert bam[-28:] == bamcodec.EOF_BLOCK
+
+
+def bgzf_payload(b):
+    return bamcodec.bgzf_decode(b)
+
+
+def test_bam_to_sam_matches_independent_codec():
+    lines = rich_lines(seed=10)
+    bam = bamcodec.encode(lines)
+    assert cli(["view"], bam).decode().splitlines() == lines                     # their writer, our reader
+    again = cli(["view", "-b"], bam)
+    assert cli(["view"], again).decode().splitlines() == lines
+
+
+def test_many_blocks_and_stdin_detection(tmp_path):
+    lines = rich_lines(6000, seed=11)                                            # several MB: hundreds of BGZF blocks
+    sam = ("\n".join(lines) + "\n").encode()
+    p = tmp_path / "x.bam"
+    p.write_bytes(cli(["view", "-b"], sam))
+    assert cli(["view"], path=p).decode().splitlines() == lines
+    assert cli(["view"], p.read_bytes()).decode().splitlines() == lines          # BAM on stdin is recognised by content
+
+
+def test_bam_without_sq_text_uses_binary_reference_list():
+    lines = [HEADER[0]] + [ln for ln in rich_lines(50, seed=12) if not ln.startswith("@")]
+    full = bamcodec.encode(HEADER[:3] + lines[1:])
+    # rebuild the header block with a text that lacks the @SQ lines but keep the binary reference list
+    import struct
+    d = bamcodec.bgzf_decode(full)
+    l_text = struct.unpack_from("<I", d, 4)[0]
+    text = (HEADER[0] + "\n").encode()
+    d2 = b"BAM\1" + struct.pack("<I", len(text)) + text + d[8 + l_text:]
+    got = cli(["view"], bamcodec.bgzf_blocks(d2)).decode().splitlines()
+    assert got[0] == HEADER[0] and got[1:3] == HEADER[1:3]
+    assert [ln for ln in got if not ln.startswith("@")] == lines[1:]
+
+
+def test_damaged_bam_fails_loudly():
+    bam = bytearray(cli(["view", "-b"], ("\n".join(rich_lines(300)) + "\n").encode()))
+    bam[len(bam) // 2] ^= 0x55
+    p = subprocess.run([BIN, "view", "-"], input=bytes(bam), capture_output=True)
+    assert p.returncode != 0 and b"damaged" in p.stderr
+
+
+def test_consumers_read_and_write_bam(tmp_path):
+    """`out -c`, `out` and `extract` give the same records whether they read SAM or BAM and write SAM or BAM."""
+    path, _ = annotated_sam(tmp_path, n=1500)
+    sam = path.read_bytes()
+    bam_in = tmp_path / "anno.bam"
+    bam_in.write_bytes(bamcodec.encode(sam.decode().splitlines()))
+    for args in (["out", "-c"], ["out"], ["extract"]):
+        ref = cli(args, path=path).decode().splitlines()
+        body = lambda ls: [ln for ln in ls if not ln.startswith("@PG\tID:fade-extract")]
+        from_bam = cli(args, path=bam_in).decode().splitlines()
+        assert body(from_bam) == body(ref)
+        to_bam = bamcodec.decode(cli(args + ["-b"], path=path))
+        assert body(to_bam) == body(ref)
+        to_ubam = bamcodec.decode(cli(args + ["-u"], path=bam_in))
+        assert body(to_ubam) == body(ref)

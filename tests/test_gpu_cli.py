@@ -84,3 +84,37 @@ def test_end_to_end_chain_annotate_out_extract(tmp_path):
         body = [ln for ln in p.stdout.splitlines() if not ln.startswith("@")]
         assert body == [cons.format_sam_line(r) for r in exp], args
         assert len(body) > 50
+
+
+def test_cli_annotate_reads_and_writes_bam(tmp_path):
+    """the same annotation whether the records arrive as SAM text or BAM and leave as SAM,
+    uncompressed BAM (-u) or BAM (-b), as util.d:65-76; checked with the independent codec tests/bamcodec.py.
+    The rs tag travels as a uint8 (`rs:C`, anno.d:94 assigns a ubyte)."""
+    import bamcodec
+    names, contigs, cfg, _ = sim.config_c1()
+    contigs = [contigs[0][:300_000]]
+    rd = sim.make_reads(cfg, 0, 2500, contigs)
+    fa, sam, bam = tmp_path / "ref.fa", tmp_path / "in.sam", tmp_path / "in.bam"
+    samio.write_fasta(fa, names, contigs)
+    samio.write_sam(sam, names, contigs, rd)
+    bam.write_bytes(bamcodec.encode(open(sam).read().splitlines()))
+
+    def run(src, *flags):
+        p = subprocess.run([BIN, "annotate", *flags, str(src), str(fa)], capture_output=True)
+        assert p.returncode == 0, p.stderr.decode()
+        return p.stdout
+
+    body = lambda ls: [ln for ln in ls if not ln.startswith("@PG\tID:fade-annotate")]
+    ref = body(run(sam).decode().splitlines())
+    assert sum("\tam:Z:" in ln for ln in ref) > 50
+    assert body(run(bam).decode().splitlines()) == ref
+    out_b = run(bam, "-b")
+    assert body(bamcodec.decode(out_b)) == ref
+    assert body(bamcodec.decode(run(sam, "-u"))) == ref
+    assert b"rsC" in bamcodec.bgzf_decode(out_b)
+    # and the chain stays in BAM: annotate -b | out -c -b | view
+    p1 = subprocess.run([BIN, "out", "-c", "-b", "-"], input=out_b, capture_output=True)
+    p2 = subprocess.run([BIN, "out", "-c", "-"], input=run(sam), capture_output=True)
+    assert p1.returncode == 0 and p2.returncode == 0
+    strip = lambda ls: [ln for ln in ls if not ln.startswith("@PG")]
+    assert strip(bamcodec.decode(p1.stdout)) == strip(p2.stdout.decode().splitlines())
