@@ -1,0 +1,461 @@
+// bamfast.hpp -- `fade-b200 annotate` on BAM input without a text detour (SURVEY 8f row 3:
+// "required for real-file end-to-end runs and for feeding 8 GPUs; the likely end-to-end bottleneck").
+//
+// The batched mirror of anno.d:36-52 on binary records: BGZF blocks are inflated in parallel, the
+// records of a batch are parsed in parallel (parse_clips / alignedLength / sc / sup through
+// fadehost_prepare, anno.d:61-74), their 4-bit bases are copied as they are into the pinned view of
+// a batch (the memcpy of INTEGRATION.md section 2), fadegpu_submit returns at once and the next
+// batch is read while the GPU works; after fadegpu_wait the tags are written into the binary records
+// (rs as a uint8 `C`, am/as/ar/ab as `Z`, anno.d:94-107) and the output is deflated in parallel (BAM, -b),
+// stored (uncompressed BAM, -u) or formatted as SAM text.  Records keep their input order.
+#pragma once
+#include <omp.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "../../../include/fadegpu.h"
+#include "../../../include/fadehost.h"
+#include "samio.hpp"
+
+namespace bamfast {
+
+using samio::get_i32;
+using samio::get_u16;
+using samio::get_u32;
+
+// parallel BGZF inflate: raw blocks are read sequentially, decompressed side by side
+class BulkReader {
+public:
+    BulkReader(FILE *f, const std::string &pre, int threads) : f_(f), pre_(pre), threads_(std::max(1, threads)) {}
+    // appends the payload of up to max_blocks further blocks to out; false when the file is exhausted
+    bool more(std::vector<uint8_t> &out, int max_blocks)
+    {
+        struct Blk { std::vector<uint8_t> c; uint32_t isize, crc; size_t off; };
+        std::vector<Blk> blks;
+        size_t total = 0;
+        while ((int)blks.size() < max_blocks) {
+            uint8_t h[12];
+            const size_t got = raw(h, 12);
+            if (got == 0) break;
+            if (got != 12 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { bad_ = true; return false; }
+            const uint32_t xlen = get_u16(h + 10);
+            std::vector<uint8_t> extra(xlen);
+            if (raw(extra.data(), xlen) != xlen) { bad_ = true; return false; }
+            int64_t bsize = -1;
+            for (size_t i = 0; i + 4 <= xlen;) {
+                const uint32_t sl = get_u16(&extra[i + 2]);
+                if (extra[i] == 'B' && extra[i + 1] == 'C' && sl == 2 && i + 6 <= xlen) bsize = get_u16(&extra[i + 4]);
+                i += 4 + sl;
+            }
+            const int64_t clen = bsize - xlen - 19;
+            if (bsize < 0 || clen < 0) { bad_ = true; return false; }
+            Blk b;
+            b.c.resize((size_t)clen + 8);
+            if (raw(b.c.data(), b.c.size()) != b.c.size()) { bad_ = true; return false; }
+            b.crc = get_u32(&b.c[(size_t)clen]);
+            b.isize = get_u32(&b.c[(size_t)clen + 4]);
+            b.off = total;
+            total += b.isize;
+            blks.push_back(std::move(b));
+        }
+        if (blks.empty()) return false;
+        const size_t base = out.size();
+        out.resize(base + total);
+        int bad = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(| : bad) num_threads(threads_)
+        for (long k = 0; k < (long)blks.size(); ++k) {
+            const Blk &b = blks[(size_t)k];
+            if (!b.isize) continue;
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; continue; }
+            zs.next_in = const_cast<uint8_t *>(b.c.data()); zs.avail_in = (uInt)(b.c.size() - 8);
+            zs.next_out = out.data() + base + b.off; zs.avail_out = b.isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+                crc32(crc32(0, nullptr, 0), out.data() + base + b.off, b.isize) != b.crc) bad = 1;
+        }
+        if (bad) bad_ = true;
+        return !bad;
+    }
+    bool bad() const { return bad_; }
+
+private:
+    size_t raw(uint8_t *d, size_t n)
+    {
+        size_t got = 0;
+        if (pre_pos_ < pre_.size()) {
+            got = std::min(n, pre_.size() - pre_pos_);
+            memcpy(d, pre_.data() + pre_pos_, got);
+            pre_pos_ += got;
+        }
+        if (got < n) got += fread(d + got, 1, n - got, f_);
+        return got;
+    }
+    FILE *f_;
+    std::string pre_;
+    size_t pre_pos_ = 0;
+    int threads_;
+    bool bad_ = false;
+};
+
+// BGZF blocks of `data`, compressed side by side, written in order (no EOF marker)
+inline void write_blocks(FILE *f, const uint8_t *data, size_t n, int level, int threads)
+{
+    constexpr size_t kBlock = 0xff00;
+    const long nb = (long)((n + kBlock - 1) / kBlock);
+    std::vector<std::string> out((size_t)nb);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(std::max(1, threads))
+    for (long k = 0; k < nb; ++k) {
+        const uint8_t *src = data + (size_t)k * kBlock;
+        const size_t len = std::min(kBlock, n - (size_t)k * kBlock);
+        std::string &o = out[(size_t)k];
+        o.resize(0x10000 + 64);
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+        zs.next_in = const_cast<uint8_t *>(src); zs.avail_in = (uInt)len;
+        zs.next_out = reinterpret_cast<uint8_t *>(&o[18]); zs.avail_out = (uInt)(o.size() - 26);
+        deflate(&zs, Z_FINISH);
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        static const uint8_t head[16] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0 };
+        memcpy(&o[0], head, 16);
+        const uint32_t bsize = (uint32_t)(clen + 25);
+        o[16] = (char)(bsize & 0xff); o[17] = (char)(bsize >> 8);
+        const uint32_t crc = (uint32_t)crc32(crc32(0, nullptr, 0), src, (uInt)len);
+        for (int i = 0; i < 4; ++i) { o[18 + clen + (size_t)i] = (char)(crc >> (8 * i)); o[22 + clen + (size_t)i] = (char)((uint32_t)len >> (8 * i)); }
+        o.resize(26 + clen);
+    }
+    for (const auto &o : out) fwrite(o.data(), 1, o.size(), f);
+}
+
+// bytes of one aux field starting at its 2-letter tag; 0 = damaged
+inline size_t aux_field_size(const uint8_t *p, const uint8_t *end)
+{
+    if (p + 3 > end) return 0;
+    const char ty = (char)p[2];
+    size_t v;
+    switch (ty) {
+    case 'A': case 'c': case 'C': v = 1; break;
+    case 's': case 'S': v = 2; break;
+    case 'i': case 'I': case 'f': v = 4; break;
+    case 'd': v = 8; break;
+    case 'Z': case 'H': {
+        const void *z = memchr(p + 3, 0, (size_t)(end - (p + 3)));
+        if (!z) return 0;
+        v = (size_t)(static_cast<const uint8_t *>(z) - (p + 3)) + 1;
+        break;
+    }
+    case 'B': {
+        if (p + 8 > end) return 0;
+        const char st = (char)p[3];
+        const size_t w = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : (st == 'i' || st == 'I' || st == 'f') ? 4 : 0;
+        if (!w) return 0;
+        v = 5 + w * (size_t)get_u32(p + 4);
+        break;
+    }
+    default: return 0;
+    }
+    return (p + 3 + v <= end) ? 3 + v : 0;
+}
+
+struct RecMeta {
+    size_t off;                 // of the record's block_size field inside the slot buffer
+    uint32_t size;              // block_size
+    int32_t aligned_len, clip_left, clip_right;
+    uint8_t rs_base;
+};
+
+struct Slot {
+    std::vector<uint8_t> buf;   // the batch's records, as in the file
+    std::vector<RecMeta> rec;
+    fadegpu_batch *bt = nullptr;
+    fadegpu_batch_view v{};
+    bool in_flight = false;
+};
+
+struct Job {
+    fadegpu_params prm;
+    int device = 0;
+    int64_t batch_n = 1 << 20;
+    int con = 0;                // util.d:65-76: 0 SAM, 1 uBAM, 2 BAM
+    std::string cl, version;
+    std::string fasta_path;
+};
+
+// the whole command; returns the process exit code
+inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
+                        bool (*read_fasta)(const std::string &, std::map<std::string, std::string> &))
+{
+    const int threads = job.prm.host_threads > 0 ? job.prm.host_threads : omp_get_max_threads();
+    BulkReader rd(fin, pre, threads);
+    std::vector<uint8_t> stream;
+    size_t spos = 0;
+    auto need = [&](size_t bytes) {   // make stream[spos, spos + bytes) available
+        while (stream.size() - spos < bytes) if (!rd.more(stream, 64)) return false;
+        return true;
+    };
+    // ---- header (SAMv1 4.2) ----
+    samio::Header hdr;
+    {
+        if (!need(12) || memcmp(&stream[spos], "BAM\1", 4) != 0) { fprintf(stderr, "fade-b200: not a BAM file\n"); return 1; }
+        const uint32_t l_text = get_u32(&stream[spos + 4]);
+        if (!need(12 + (size_t)l_text)) { fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
+        std::string text(reinterpret_cast<const char *>(&stream[spos + 8]), l_text);
+        text.resize(strnlen(text.c_str(), text.size()));
+        bool has_sq = false;
+        for (size_t a = 0; a < text.size();) {
+            size_t e = text.find('\n', a);
+            if (e == std::string::npos) e = text.size();
+            if (e > a) { hdr.add_line(text.substr(a, e - a)); has_sq |= text.compare(a, 3, "@SQ") == 0; }
+            a = e + 1;
+        }
+        spos += 8 + l_text;
+        const uint32_t n_ref = get_u32(&stream[spos]);
+        spos += 4;
+        for (uint32_t r = 0; r < n_ref; ++r) {
+            if (!need(4)) { fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
+            const uint32_t l = get_u32(&stream[spos]);
+            if (!need(8 + (size_t)l)) { fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
+            std::string nm(reinterpret_cast<const char *>(&stream[spos + 4]), l);
+            nm.resize(strnlen(nm.c_str(), nm.size()));
+            if (!has_sq) hdr.add_line("@SQ\tSN:" + nm + "\tLN:" + std::to_string(get_u32(&stream[spos + 4 + l])));
+            spos += 8 + l;
+        }
+    }
+    std::string last_pg;
+    for (const auto &l : hdr.lines)
+        if (l.compare(0, 3, "@PG") == 0) {
+            const size_t a = l.find("\tID:");
+            if (a != std::string::npos) last_pg = l.substr(a + 4, l.find('\t', a + 4) - a - 4);
+        }
+    std::string pg = "@PG\tID:fade-annotate\tPN:fade\tVN:" + job.version;   // anno.d:25-32
+    if (!last_pg.empty()) pg += "\tPP:" + last_pg;
+    pg += "\tCL:" + job.cl;
+    hdr.add_line(pg);
+    const int level = job.con == 1 ? 0 : 6;
+    if (job.con == 0) {
+        for (const auto &l : hdr.lines) { fwrite(l.data(), 1, l.size(), stdout); fputc('\n', stdout); }
+    } else {
+        std::string text, o("BAM\1", 4);
+        for (const auto &l : hdr.lines) { text += l; text += '\n'; }
+        samio::put_u32(o, (uint32_t)text.size());
+        o += text;
+        samio::put_u32(o, (uint32_t)hdr.names.size());
+        for (size_t r = 0; r < hdr.names.size(); ++r) {
+            samio::put_u32(o, (uint32_t)hdr.names[r].size() + 1);
+            o += hdr.names[r]; o.push_back('\0');
+            samio::put_u32(o, (uint32_t)hdr.lens[r]);
+        }
+        write_blocks(stdout, reinterpret_cast<const uint8_t *>(o.data()), o.size(), level, threads);
+    }
+
+    // ---- reference (anno.d:23) ----
+    std::map<std::string, std::string> fasta;
+    if (!read_fasta(job.fasta_path, fasta)) { fprintf(stderr, "fade-b200: cannot read %s\n", job.fasta_path.c_str()); return 1; }
+    std::vector<const char *> cnames, cseqs;
+    for (size_t t = 0; t < hdr.names.size(); ++t) {
+        auto it = fasta.find(hdr.names[t]);
+        if (it == fasta.end() || (int64_t)it->second.size() < hdr.lens[t]) {
+            fprintf(stderr, "fade-b200: contig %s missing or shorter than @SQ LN in the FASTA\n", hdr.names[t].c_str());
+            return 1;
+        }
+        cnames.push_back(hdr.names[t].c_str());
+        cseqs.push_back(it->second.data());
+    }
+    fadegpu_params prm = job.prm;
+    prm.flags |= FADEGPU_F_NO_SCATTER;
+    fadegpu_ctx *ctx = nullptr;
+    if (fadegpu_create(job.device, &prm, &ctx) != 0) { fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(nullptr)); return 1; }
+    if (!hdr.names.empty() &&
+        fadegpu_load_reference(ctx, (int32_t)hdr.names.size(), cnames.data(), hdr.lens.data(), cseqs.data()) != 0) {
+        fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(ctx));
+        return 1;
+    }
+    fasta.clear();
+
+    const int64_t max_seq = job.batch_n * 160;
+    Slot slot[2];
+    for (auto &s : slot)
+        if (fadegpu_alloc_batch(ctx, job.batch_n, max_seq, &s.bt) != 0 || fadegpu_get_batch_view(s.bt, &s.v) != 0) {
+            fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(ctx));
+            return 1;
+        }
+    long long n_total = 0, n_art = 0, n_sc = 0;
+    int rc_all = 0;
+
+    // records of the next batch -> slot (parse + fill the pinned view); false when there are none
+    auto load = [&](Slot &s) -> bool {
+        s.rec.clear();
+        const size_t start = spos;
+        int64_t seq_bytes = 0;
+        while ((int64_t)s.rec.size() < job.batch_n) {
+            if (!need(4)) break;
+            const uint32_t bs = get_u32(&stream[spos]);
+            if (bs < 32 || !need(4 + (size_t)bs)) { if (!rd.bad()) fprintf(stderr, "fade-b200: truncated BAM record\n"); rc_all = 1; break; }
+            const int32_t l_seq = get_i32(&stream[spos + 4 + 16]);
+            if (l_seq < 0) { fprintf(stderr, "fade-b200: damaged BAM record\n"); rc_all = 1; break; }
+            if (seq_bytes + (l_seq + 1) / 2 + 1024 > max_seq) {
+                if (s.rec.empty()) { fprintf(stderr, "fade-b200: a read of %d bases does not fit a batch (raise --batch)\n", l_seq); rc_all = 1; }
+                break;
+            }
+            seq_bytes += (l_seq + 1) / 2;
+            RecMeta m{};
+            m.off = spos - start; m.size = bs;
+            s.rec.push_back(m);
+            spos += 4 + (size_t)bs;
+        }
+        if (rd.bad()) { fprintf(stderr, "fade-b200: damaged BAM input\n"); rc_all = 1; }
+        if (s.rec.empty()) return false;
+        s.buf.assign(stream.begin() + (long)start, stream.begin() + (long)spos);
+        stream.erase(stream.begin(), stream.begin() + (long)spos);
+        spos = 0;
+        const long n = (long)s.rec.size();
+        fadegpu_batch_view &v = s.v;
+        int64_t off = 0;
+        for (long k = 0; k < n; ++k) {   // offsets of the bases inside the view
+            v.seq_off[k] = off;
+            off += (get_i32(&s.buf[s.rec[(size_t)k].off + 4 + 16]) + 1) / 2;
+        }
+        v.seq_off[n] = off;
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad) num_threads(threads)
+        for (long k = 0; k < n; ++k) {
+            RecMeta &m = s.rec[(size_t)k];
+            const uint8_t *p = &s.buf[m.off + 4], *end = p + m.size;
+            const uint32_t l_name = p[8], n_cig = get_u16(p + 12), flag = get_u16(p + 14);
+            const int32_t l_seq = get_i32(p + 16);
+            const uint8_t *cig = p + 32 + l_name, *seq = cig + 4ull * n_cig, *qual = seq + (size_t)(l_seq + 1) / 2, *aux = qual + (size_t)l_seq;
+            if (aux > end) { bad = 1; continue; }
+            uint32_t cigar[64];
+            std::vector<uint32_t> big;
+            uint32_t *cg = cigar;
+            if (n_cig > 64) { big.resize(n_cig); cg = big.data(); }
+            memcpy(cg, cig, 4ull * n_cig);
+            bool has_sa = false;
+            for (const uint8_t *a = aux; a < end;) {
+                const size_t sz = aux_field_size(a, end);
+                if (!sz) { bad = 1; break; }
+                if (a[0] == 'S' && a[1] == 'A') has_sa = true;
+                a += sz;
+            }
+            fadehost_record hr;
+            hr.flag = (int32_t)flag; hr.has_sa = has_sa; hr.cigar = cg; hr.n_cigar = (int32_t)n_cig;
+            hr.seq4 = seq; hr.qual = qual; hr.l_qseq = l_seq; hr.tid = get_i32(p); hr.pos = get_i32(p + 4);
+            fadehost_prepare(&hr, &m.aligned_len, &m.clip_left, &m.clip_right, &m.rs_base);   // anno.d:61-74
+            memcpy(v.seq4 + v.seq_off[k], seq, (size_t)(l_seq + 1) / 2);
+            v.l_qseq[k] = l_seq; v.tid[k] = hr.tid; v.pos[k] = hr.pos;
+            v.aligned_len[k] = m.aligned_len; v.clip_left[k] = m.clip_left; v.clip_right[k] = m.clip_right;
+        }
+        if (bad) { fprintf(stderr, "fade-b200: damaged BAM record\n"); rc_all = 1; return false; }
+        if (fadegpu_submit(ctx, s.bt, n) != 0) { fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(ctx)); rc_all = 1; return false; }
+        s.in_flight = true;
+        return true;
+    };
+
+    // results of the slot -> tagged records -> stdout
+    auto emit = [&](Slot &s) -> bool {
+        s.in_flight = false;
+        fadegpu_results_view rv;
+        if (fadegpu_wait(ctx, s.bt) != 0 || fadegpu_get_results(s.bt, &rv) != 0) {
+            fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(ctx));
+            return false;
+        }
+        const long n = (long)s.rec.size();
+        const int T = (int)std::max<long>(1, std::min<long>(threads, n / 256));
+        std::vector<std::string> part((size_t)T);
+        std::vector<long long> art((size_t)T, 0), sc((size_t)T, 0);
+        int bad = 0;
+#pragma omp parallel for schedule(static, 1) reduction(| : bad) num_threads(T)
+        for (int t = 0; t < T; ++t) {
+            std::string &o = part[(size_t)t];
+            std::string am, as_, ar, ab, rec, line;
+            std::vector<uint32_t> big;
+            for (long k = n * t / T; k < n * (t + 1) / T; ++k) {
+                const RecMeta &m = s.rec[(size_t)k];
+                const uint8_t *p = &s.buf[m.off + 4], *end = p + m.size;
+                const uint32_t l_name = p[8], n_cig = get_u16(p + 12);
+                const int32_t l_seq = get_i32(p + 16), tid = get_i32(p);
+                const uint8_t *cig = p + 32 + l_name, *seq = cig + 4ull * n_cig, *qual = seq + (size_t)(l_seq + 1) / 2, *aux = qual + (size_t)l_seq;
+                big.resize(n_cig);
+                memcpy(big.data(), cig, 4ull * n_cig);
+                fadehost_record hr;
+                hr.flag = (int32_t)get_u16(p + 14); hr.has_sa = (m.rs_base & FADE_RS_SUP) != 0; hr.cigar = big.data(); hr.n_cigar = (int32_t)n_cig;
+                hr.seq4 = seq; hr.qual = qual; hr.l_qseq = l_seq; hr.tid = tid; hr.pos = get_i32(p + 4);
+                const char *cname = (tid >= 0 && (size_t)tid < hdr.names.size()) ? hdr.names[(size_t)tid].c_str() : "";
+                const size_t cap = (size_t)4 * (size_t)std::max(l_seq, 0) + 512 + strlen(cname);
+                am.resize(cap); as_.resize(cap); ar.resize(cap); ab.resize(cap);
+                const int32_t ri = rv.result_index[k];
+                static const uint32_t no_ops[1] = { 0 };
+                const fadegpu_result *res = ri >= 0 ? &rv.results[ri] : nullptr;
+                uint8_t rs = 0;
+                const int rc = fadehost_finish(&hr, cname, m.rs_base, m.clip_left, m.clip_right, m.aligned_len, s.v.flags[k],
+                                               res ? rv.win_start[ri] : 0, res ? res->beg_ref : 0, res ? res->n_ops : 0,
+                                               res ? res->ops : no_ops, &rs, &am[0], &as_[0], &ar[0], &ab[0], cap);
+                if (rc < 0) { bad = 1; continue; }
+                // the record without the tags annotate (re)writes, then rs / am / as / ar / ab (anno.d:94-106)
+                rec.assign(reinterpret_cast<const char *>(p), (size_t)(aux - p));
+                for (const uint8_t *a = aux; a < end;) {
+                    const size_t sz = aux_field_size(a, end);
+                    if (!sz) { bad = 1; break; }
+                    const bool ours = (a[0] == 'r' && a[1] == 's') || (a[0] == 'a' && (a[1] == 'm' || a[1] == 's' || a[1] == 'r' || a[1] == 'b'));
+                    if (!ours) rec.append(reinterpret_cast<const char *>(a), sz);
+                    a += sz;
+                }
+                rec += "rsC"; rec.push_back((char)rs);
+                if (rc == 1) {
+                    rec += "amZ"; rec += am.c_str(); rec.push_back('\0');
+                    rec += "asZ"; rec += as_.c_str(); rec.push_back('\0');
+                    rec += "arZ"; rec += ar.c_str(); rec.push_back('\0');
+                    rec += "abZ"; rec += ab.c_str(); rec.push_back('\0');
+                    ++art[(size_t)t];
+                }
+                sc[(size_t)t] += rs & 1;
+                if (job.con == 0) {
+                    if (!samio::bam_to_sam(reinterpret_cast<const uint8_t *>(rec.data()), rec.size(), hdr, line)) { bad = 1; continue; }
+                    o += line; o += '\n';
+                } else {
+                    samio::put_u32(o, (uint32_t)rec.size());
+                    o += rec;
+                }
+            }
+        }
+        if (bad) { fprintf(stderr, "fade-b200: damaged BAM record\n"); return false; }
+        for (int t = 0; t < T; ++t) { n_art += art[(size_t)t]; n_sc += sc[(size_t)t]; }
+        n_total += n;
+        if (job.con == 0) for (const auto &o : part) fwrite(o.data(), 1, o.size(), stdout);
+        else {
+            std::string all;
+            size_t tot = 0;
+            for (const auto &o : part) tot += o.size();
+            all.reserve(tot);
+            for (const auto &o : part) all += o;
+            write_blocks(stdout, reinterpret_cast<const uint8_t *>(all.data()), all.size(), level, threads);
+        }
+        return true;
+    };
+
+    // anno.d:44-50, batched and double-buffered: the GPU works on one slot while the host reads the other
+    int cur = 0;
+    for (;;) {
+        const bool got = load(slot[cur]);
+        Slot &prev = slot[cur ^ 1];
+        if (prev.in_flight && !emit(prev)) { rc_all = 1; break; }
+        if (!got) break;
+        cur ^= 1;
+    }
+    for (auto &s : slot) if (s.in_flight && rc_all == 0 && !emit(s)) rc_all = 1;
+    if (job.con != 0 && rc_all == 0) {
+        static const uint8_t eof[28] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+        fwrite(eof, 1, sizeof(eof), stdout);
+    }
+    fflush(stdout);
+    fprintf(stderr, "[fade-b200 annotate] %lld records, %lld soft-clipped, %lld with artifact tags\n", n_total, n_sc, n_art);
+    for (auto &s : slot) { if (s.in_flight) fadegpu_wait(ctx, s.bt); fadegpu_free_batch(s.bt); }
+    fadegpu_destroy(ctx);
+    return rc_all;
+}
+
+}  // namespace bamfast

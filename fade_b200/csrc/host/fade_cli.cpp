@@ -22,6 +22,7 @@
 #include "../../../include/fadegpu.h"
 #include "../../../include/fadehost.h"
 #include "samio.hpp"
+#include "bamfast.hpp"
 
 namespace {
 
@@ -143,6 +144,7 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
     fadegpu_default_params(&prm);
     int64_t batch_n = 1 << 20;
     int device = 0, con = 0;
+    bool text_path = false;
     std::vector<std::string> pos_args;
     for (int i = 2; i < argc; ++i) {
         const std::string a = argv[i];
@@ -155,18 +157,31 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
         else if (a == "-w" || a == "--window-size") prm.window_size = atoi(need("--window-size"));
         else if (a == "--batch") batch_n = atoll(need("--batch"));
         else if (a == "--device") device = atoi(need("--device"));
+        else if (a == "--text-path") text_path = true;   // BAM input through the SAM text loop (A/B check of bamfast.hpp)
         else if (a == "-h" || a == "--help") return usage();
         else if (output_flag(a, con)) {}
         else pos_args.push_back(a);
     }
     if (pos_args.size() < 2) { usage(); return 0; }
     if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    fprintf(stderr, "[W::fade annotate] Output will keep the input order\n");
+
+    FILE *fin_raw = pos_args[0] == "-" ? stdin : fopen(pos_args[0].c_str(), "rb");
+    if (!fin_raw) { fprintf(stderr, "fade-b200: cannot open %s\n", pos_args[0].c_str()); return 1; }
+    std::string pre(2, '\0');
+    pre.resize(fread(&pre[0], 1, 2, fin_raw));
+    if (pre.size() == 2 && (uint8_t)pre[0] == 0x1f && (uint8_t)pre[1] == 0x8b && !text_path) {
+        // BAM input: binary records end to end (bamfast.hpp); SAM text input continues below
+        bamfast::Job job;
+        job.prm = prm; job.device = device; job.batch_n = batch_n; job.con = con; job.cl = cl; job.version = kVersion;
+        job.fasta_path = pos_args[1];
+        return bamfast::annotate_bam(fin_raw, pre, job, read_fasta);
+    }
     open_output(con);
-    fprintf(stderr, "[W::fade annotate] Output SAM will keep the input order\n");
 
     // ---- header ----
     samio::LineSource src;
-    if (!src.open(pos_args[0])) { fprintf(stderr, "fade-b200: cannot open %s\n", pos_args[0].c_str()); return 1; }
+    if (!src.open(fin_raw, pre)) { fprintf(stderr, "fade-b200: cannot read %s\n", pos_args[0].c_str()); return 1; }
     samio::LineSource *in = &src;
     std::vector<std::string> header;
     std::vector<std::string> sq_names;

@@ -412,12 +412,19 @@ public:
     // path "-" = stdin.  BAM is recognised by the gzip magic.
     bool open(const std::string &path)
     {
-        f_ = path == "-" ? stdin : fopen(path.c_str(), "rb");
-        if (!f_) return false;
+        FILE *f = path == "-" ? stdin : fopen(path.c_str(), "rb");
+        if (!f) return false;
         uint8_t m[2];
-        const size_t got = fread(m, 1, 2, f_);
-        std::string pre(reinterpret_cast<char *>(m), got);
-        if (got == 2 && m[0] == 0x1f && m[1] == 0x8b) {
+        const size_t got = fread(m, 1, 2, f);
+        return open(f, std::string(reinterpret_cast<char *>(m), got));
+    }
+    // an already opened file whose first bytes (`pre`, at least 2 unless the file is shorter) were read
+    bool open(FILE *f, const std::string &pre)
+    {
+        f_ = f;
+        const size_t got = pre.size();
+        const uint8_t *m = reinterpret_cast<const uint8_t *>(pre.data());
+        if (got >= 2 && m[0] == 0x1f && m[1] == 0x8b) {
             bam_ = true;
             bz_ = new BgzfReader(f_, pre);
             return read_bam_header();

@@ -107,11 +107,17 @@ def test_cli_annotate_reads_and_writes_bam(tmp_path):
     body = lambda ls: [ln for ln in ls if not ln.startswith("@PG\tID:fade-annotate")]
     ref = body(run(sam).decode().splitlines())
     assert sum("\tam:Z:" in ln for ln in ref) > 50
-    assert body(run(bam).decode().splitlines()) == ref
+    assert body(run(bam).decode().splitlines()) == ref                   # binary records end to end (bamfast.hpp)
+    assert body(run(bam, "--text-path").decode().splitlines()) == ref    # BAM through the SAM text loop
+    assert body(run(bam, "--batch", "700", "-t", "3").decode().splitlines()) == ref   # several double-buffered batches
     out_b = run(bam, "-b")
     assert body(bamcodec.decode(out_b)) == ref
     assert body(bamcodec.decode(run(sam, "-u"))) == ref
     assert b"rsC" in bamcodec.bgzf_decode(out_b)
+    # re-annotating the annotated BAM replaces the five tags, nothing else (PP chain aside)
+    again = tmp_path / "again.bam"
+    again.write_bytes(out_b)
+    assert body(bamcodec.decode(run(again, "-b"))) == ref
     # and the chain stays in BAM: annotate -b | out -c -b | view
     p1 = subprocess.run([BIN, "out", "-c", "-b", "-"], input=out_b, capture_output=True)
     p2 = subprocess.run([BIN, "out", "-c", "-"], input=run(sam), capture_output=True)
