@@ -51,13 +51,14 @@ CHUNK = 1_000_000
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fade_b200", choices=["fade_b200", "reference"])
     ap.add_argument("--reads", type=int, default=N_READS, help="reads per GPU per step")
     ap.add_argument("--ref-len", type=int, default=REF_LEN)
     ap.add_argument("--chunk", type=int, default=CHUNK)
-    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="reads in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=4_000_000,
+                    help="reads in the cpu_baseline sample (4 M reads = about 30 core-seconds of the AVX2 port)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
     ap.add_argument("--depth", type=int, default=3, help="chunks in flight in the e2e loop (view path)")
     ap.add_argument("--e2e-path", default="view", choices=["view", "arrays"],

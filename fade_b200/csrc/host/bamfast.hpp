@@ -194,7 +194,7 @@ inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
     std::vector<uint8_t> stream;
     size_t spos = 0;
     auto need = [&](size_t bytes) {   // make stream[spos, spos + bytes) available
-        while (stream.size() - spos < bytes) if (!rd.more(stream, 64)) return false;
+        while (stream.size() - spos < bytes) if (!rd.more(stream, 512)) return false;
         return true;
     };
     // ---- header (SAMv1 4.2) ----
@@ -285,11 +285,13 @@ inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
         }
     long long n_total = 0, n_art = 0, n_sc = 0;
     int rc_all = 0;
+    double t_read = 0, t_parse = 0, t_wait = 0, t_tag = 0, t_write = 0;   // FADE_TIMING=1 prints them
+    const double t_start = omp_get_wtime();
 
     // records of the next batch -> slot (parse + fill the pinned view); false when there are none
     auto load = [&](Slot &s) -> bool {
         s.rec.clear();
-        const size_t start = spos;
+        double t0 = omp_get_wtime();
         int64_t seq_bytes = 0;
         while ((int64_t)s.rec.size() < job.batch_n) {
             if (!need(4)) break;
@@ -303,14 +305,16 @@ inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
             }
             seq_bytes += (l_seq + 1) / 2;
             RecMeta m{};
-            m.off = spos - start; m.size = bs;
+            m.off = spos; m.size = bs;
             s.rec.push_back(m);
             spos += 4 + (size_t)bs;
         }
         if (rd.bad()) { fprintf(stderr, "fade-b200: damaged BAM input\n"); rc_all = 1; }
         if (s.rec.empty()) return false;
-        s.buf.assign(stream.begin() + (long)start, stream.begin() + (long)spos);
-        stream.erase(stream.begin(), stream.begin() + (long)spos);
+        t_read += omp_get_wtime() - t0; t0 = omp_get_wtime();
+        // the slot takes the buffer (no copy, its capacity is reused two batches later); the unread tail moves on
+        s.buf.swap(stream);
+        stream.assign(s.buf.begin() + (long)spos, s.buf.end());
         spos = 0;
         const long n = (long)s.rec.size();
         fadegpu_batch_view &v = s.v;
@@ -351,6 +355,7 @@ inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
         }
         if (bad) { fprintf(stderr, "fade-b200: damaged BAM record\n"); rc_all = 1; return false; }
         if (fadegpu_submit(ctx, s.bt, n) != 0) { fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(ctx)); rc_all = 1; return false; }
+        t_parse += omp_get_wtime() - t0;
         s.in_flight = true;
         return true;
     };
@@ -359,10 +364,12 @@ inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
     auto emit = [&](Slot &s) -> bool {
         s.in_flight = false;
         fadegpu_results_view rv;
+        double t0 = omp_get_wtime();
         if (fadegpu_wait(ctx, s.bt) != 0 || fadegpu_get_results(s.bt, &rv) != 0) {
             fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(ctx));
             return false;
         }
+        t_wait += omp_get_wtime() - t0; t0 = omp_get_wtime();
         const long n = (long)s.rec.size();
         const int T = (int)std::max<long>(1, std::min<long>(threads, n / 256));
         std::vector<std::string> part((size_t)T);
@@ -425,6 +432,7 @@ inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
         if (bad) { fprintf(stderr, "fade-b200: damaged BAM record\n"); return false; }
         for (int t = 0; t < T; ++t) { n_art += art[(size_t)t]; n_sc += sc[(size_t)t]; }
         n_total += n;
+        t_tag += omp_get_wtime() - t0; t0 = omp_get_wtime();
         if (job.con == 0) for (const auto &o : part) fwrite(o.data(), 1, o.size(), stdout);
         else {
             std::string all;
@@ -434,6 +442,7 @@ inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
             for (const auto &o : part) all += o;
             write_blocks(stdout, reinterpret_cast<const uint8_t *>(all.data()), all.size(), level, threads);
         }
+        t_write += omp_get_wtime() - t0;
         return true;
     };
 
@@ -453,6 +462,9 @@ inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
     }
     fflush(stdout);
     fprintf(stderr, "[fade-b200 annotate] %lld records, %lld soft-clipped, %lld with artifact tags\n", n_total, n_sc, n_art);
+    if (getenv("FADE_TIMING"))
+        fprintf(stderr, "[fade-b200 annotate] %d threads; record loop %.3f s: inflate+split %.3f, parse+fill+submit %.3f, wait for GPU %.3f, "
+                        "tag %.3f, deflate+write %.3f\n", threads, omp_get_wtime() - t_start, t_read, t_parse, t_wait, t_tag, t_write);
     for (auto &s : slot) { if (s.in_flight) fadegpu_wait(ctx, s.bt); fadegpu_free_batch(s.bt); }
     fadegpu_destroy(ctx);
     return rc_all;
