@@ -14,6 +14,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <exception>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -251,8 +252,6 @@ size_t trace_scratch_bytes(int R, int64_t n)
 }
 
 constexpr int GEN_SLOTS_MAX = 8192;
-constexpr int SPLIT_MAX = 1;     // (splitting costs more fill tails and traceback rounds than the overlap returns)
-constexpr int64_t SPLIT_MIN_ITEMS = 2048;
 constexpr size_t GEN_BUDGET = (size_t)4 << 30;
 
 size_t gen_slot_bytes(int qmax, int tmax)
@@ -286,10 +285,6 @@ int build_plan(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_aln, const int64_t *c
         // warp items of 8 alignments; split into launches that fit the checkpoint scratch
         const size_t cw = ck_words_of(R);
         int64_t a0 = first_aln;
-        // up to SPLIT_MAX launches per class (>= SPLIT_MIN_ITEMS warp items each) to alternate between the lanes
-        const int64_t class_items = (last_aln - first_aln + 7) / 8;
-        const int64_t n_split = c->n_lanes > 1 ? std::max<int64_t>(1, std::min<int64_t>(SPLIT_MAX, class_items / SPLIT_MIN_ITEMS)) : 1;
-        const int64_t items_per_launch = (class_items + n_split - 1) / n_split;
         while (a0 < last_aln) {
             Launch L{};
             L.R = R; L.aln_first = (int)a0; L.item_first = (int)n_items; L.qmax = qmax_all; L.tmax = tmax_all;
@@ -300,7 +295,6 @@ int build_plan(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_aln, const int64_t *c
                 const int nblk = num_blocks(sorted_tlen[a1]);  // longest of the 8 (sorted descending)
                 const size_t wds = (size_t)(nblk - 1) * cw * 32;
                 if (a1 > a0 && (words + wds) * 4 > (size_t)c->p.scratch_bytes) break;
-                if (n_items - L.item_first >= items_per_launch) break;
                 if (n_items >= b->cap_items) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: internal error (item capacity)");
                 WarpItem &it = b->h_items[n_items++];
                 it.ck_off = (int64_t)words;
@@ -1253,7 +1247,10 @@ static int queue_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, bool gather
         return submit_stages(c, b, n, gather);
     }
     std::lock_guard<std::mutex> lk(c->q_mu);
-    if (!c->worker.joinable()) c->worker = std::thread(worker_main, c);
+    if (!c->worker.joinable()) {
+        try { c->worker = std::thread(worker_main, c); }
+        catch (const std::exception &e) { return fail(c, FADEGPU_E_STATE, std::string("fadegpu_submit: cannot start the submit thread: ") + e.what()); }
+    }
     b->queued = true; b->submit_rc = 0; b->job_pull = gather;
     b->in_flight = true;
     c->jobs.emplace_back(b, n);

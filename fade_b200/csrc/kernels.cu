@@ -12,8 +12,6 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
-
 // Stage one pair: target selector words (window gather from the packed reference,
 // source/analysis.d:45-64) into shared memory, query selector words (reverse complement of the
 // BAM 4-bit bases, source/util.d:18-34) into registers.  `wild` gets bit0/bit1 when alignment
