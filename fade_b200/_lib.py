@@ -58,7 +58,7 @@ class Inputs(C.Structure):
 class Result(C.Structure):
     _fields_ = [("score", C.c_int32), ("end_query", C.c_int32), ("end_ref", C.c_int32), ("beg_query", C.c_int32),
                 ("beg_ref", C.c_int32), ("n_ops", C.c_int32), ("flags", C.c_uint32), ("read", C.c_int32),
-                ("ops", C.c_uint32 * 32)]
+                ("ops", C.c_uint32 * 16)]   # FADEGPU_MAX_OPS
 
 
 class ResultsView(C.Structure):

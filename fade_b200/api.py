@@ -10,7 +10,7 @@ import numpy as np
 
 from ._lib import BatchView, FadeGpuError, HostRecord, Inputs, Params, Result, ResultsView, Stats, lib
 
-MAX_OPS = 32
+MAX_OPS = 16
 R_ALIGNED, R_ART_LEFT, R_ART_RIGHT, R_OPS_TRUNC, R_GENERIC = 1, 2, 4, 8, 16
 F_FORCE_GENERIC = 1
 F_NO_SCATTER = 2
@@ -19,7 +19,7 @@ F_HOST_BINNING = 16
 F_SYNC_SUBMIT = 32
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_query", "<i4"), ("end_ref", "<i4"), ("beg_query", "<i4"),
                          ("beg_ref", "<i4"), ("n_ops", "<i4"), ("flags", "<u4"), ("read", "<i4"),
-                         ("ops", "<u4", (32,))])
+                         ("ops", "<u4", (MAX_OPS,))])
 OPCHARS = "MIDNSHP=XB"
 
 

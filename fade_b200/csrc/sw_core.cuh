@@ -27,7 +27,7 @@ namespace fade {
 
 constexpr int FG = 8;     // threads per group
 constexpr int FBLK = 32;  // steps per checkpoint block
-constexpr int OPS_CAP = 32;  // == FADEGPU_MAX_OPS
+constexpr int OPS_CAP = 16;  // == FADEGPU_MAX_OPS
 
 // symbol codes (P1: parasail_matrix_create("ACTGN",...) order), plus padding codes
 enum : int { C_A = 0, C_C = 1, C_T = 2, C_G = 3, C_N = 4, C_WILD = 5, C_TPAD = 6, C_QPAD = 7 };

@@ -35,7 +35,7 @@ extern "C" {
 #endif
 
 #define FADEGPU_ABI_VERSION 1
-#define FADEGPU_MAX_OPS 32 /* CIGAR ops materialised per read (fade rejects > 10, analysis.d:69) */
+#define FADEGPU_MAX_OPS 16 /* CIGAR ops materialised per read (fade rejects > 10, analysis.d:69) */
 
 typedef enum {
     FADEGPU_OK = 0,

@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from fade_b200.api import MAX_OPS
 from oracle import oracle as orc
 
 FIELDS = ("score", "beg_query", "end_query", "beg_ref", "end_ref", "n_ops")
@@ -29,7 +30,7 @@ def compare(batch, rd, contigs, params, max_report=5):
     n = rd.n
     res, ops = orc.align_batch(rd.seq4, rd.seq_off, rd.l_qseq, rd.tid, rd.pos, rd.aligned_len, rd.clip_left,
                                rd.clip_right, [c.tobytes() if hasattr(c, "tobytes") else c for c in contigs],
-                               params=params, ops_cap=32)
+                               params=params, ops_cap=MAX_OPS)
     flags = batch.flags[:n]
     errs = []
     g_al = (flags & 1).astype(np.int32)
@@ -53,8 +54,8 @@ def compare(batch, rd, contigs, params, max_report=5):
         bad = np.where(g != o)[0]
         if len(bad):
             errs.append(f"{name} differs at reads {bad[:max_report].tolist()} ({len(bad)} total)")
-    k = np.minimum(res["n_ops"], 32)
-    mask = np.arange(32)[None, :] < k[:, None]
+    k = np.minimum(res["n_ops"], MAX_OPS)
+    mask = np.arange(MAX_OPS)[None, :] < k[:, None]
     gops = np.where(mask, batch.ops[:n], 0)
     oops = np.where(mask, ops, 0)
     bad = np.where(al & (gops != oops).any(axis=1))[0]

@@ -35,6 +35,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Params) == 48
     assert C.sizeof(_lib.Inputs) == 8 * 8
     assert C.sizeof(_lib.BatchView) == 8 * 19
+    assert C.sizeof(_lib.Result) == 32 + 4 * 16                      # fadegpu_result, FADEGPU_MAX_OPS == 16
     p = api.default_params()
     assert (p.window_size, p.min_length, p.gap_open, p.gap_extend, p.match, p.mismatch) == (300, 5, 10, 2, 2, -3)
 

@@ -50,12 +50,12 @@ def expect(q, t, params=None):
     r = orc.sw_trace(q, t, params)
     if r.score == 0:
         return (0, 0, 0, 0, 0, 0, [])
-    return (r.score, r.end_query, r.end_ref, r.beg_query, r.beg_ref, r.n_ops, r.ops[:32])
+    return (r.score, r.end_query, r.end_ref, r.beg_query, r.beg_ref, r.n_ops, r.ops[:E.OPS_CAP])
 
 
 def got(x):
     return (x.score, x.end_query, x.end_ref, x.beg_query, x.beg_ref, x.n_ops,
-            [x.ops[k] for k in range(min(x.n_ops, 32))])
+            [x.ops[k] for k in range(min(x.n_ops, E.OPS_CAP))])
 
 
 @pytest.mark.parametrize("tagged", [1, 0, 3, 2, 5])   # bit 0: tagged trace, 1: no diagonal shortcut, 2: scan-only first replay

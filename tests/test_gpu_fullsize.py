@@ -7,6 +7,8 @@ from fade_b200 import Context, api, default_params, sim
 from oracle import oracle as orc
 from parity_util import compare, oracle_params
 
+MAX_OPS = api.MAX_OPS
+
 pytestmark = pytest.mark.gpu
 
 N16 = "=ACMGRSVTWYHKDBN"
@@ -30,11 +32,11 @@ def _check_properties(b, rd, ref, params, rng, n_score_checks=3000):
     assert len(rec) == len(al)
     ops = rec["ops"]
     nops = rec["n_ops"]
-    assert (nops <= 32).mean() > 0.999
-    ok = nops <= 32
+    assert (nops <= MAX_OPS).mean() > 0.99
+    ok = nops <= MAX_OPS
     ln = (ops >> 4).astype(np.int64)
     op = ops & 0xf
-    valid = np.arange(32)[None, :] < nops[:, None]
+    valid = np.arange(MAX_OPS)[None, :] < nops[:, None]
     qcons = np.where(valid & np.isin(op, (1, 4, 7, 8)), ln, 0).sum(1)
     rcons = np.where(valid & np.isin(op, (2, 7, 8)), ln, 0).sum(1)
     acons = np.where(valid & np.isin(op, (1, 7, 8)), ln, 0).sum(1)
@@ -50,7 +52,7 @@ def _check_properties(b, rd, ref, params, rng, n_score_checks=3000):
     # accept flags imply the predicates of analysis.d:69-80 / :98-104
     fl = rec["flags"]
     first = op[:, 0]
-    last = op[np.arange(len(rec)), np.maximum(nops - 1, 0) % 32]
+    last = op[np.arange(len(rec)), np.maximum(nops - 1, 0) % MAX_OPS]
     cl, cr = rd.clip_left[rec["read"]], rd.clip_right[rec["read"]]
     left = (fl & 2) != 0
     right = (fl & 4) != 0
