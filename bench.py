@@ -7,8 +7,10 @@ One "step" = one pass of the hot path over the whole workload (BASELINE.json con
 simulated 2x150 paired reads against a synthetic 100 Mbp chromosome, default window-size /
 min-length), processed as chunks of --chunk reads through the C ABI (libfadegpu.so).
 
-  value  reads/s with the chunk's inputs already resident in HBM: CUDA-event time of ALL kernel
-         launches of the chunk (fadegpu_replay_kernels), summed over the chunks of a step.
+  value  reads/s with every chunk's inputs already resident in HBM: one CUDA-event interval around
+         ALL kernel launches of the step's chunks (binning, fill, traceback rounds, generic kernel,
+         result index), queued back to back as consecutive submits queue them
+         (fadegpu_replay_batches); no host work, no copies.
   e2e    reads/s through the public C ABI with HOST buffers.  --e2e-path view (default): every
          chunk's records sit in the pinned host view of its batch (where the caller's BAM reader
          writes them); per chunk fadegpu_submit copies them to the device,
@@ -426,7 +428,7 @@ def main():
                          # (profiles/r01_prof_fill_final_raw.csv); only meaningful for the default configuration
                          "traffic": 2.398e9 if (args.workload == "c2" and chunk == 1_000_000) else None,
                          "kernel": "dominant: sw_fill_kernel<19> (80 % of the path); achieved = cells / time of ALL "
-                                   "kernels of the path (fill + traceback rounds + generic)",
+                                   "kernels of the path (binning + fill + traceback rounds + generic + result index)",
                          "fill_only_gcups": fill_gcups,
                          "fill_ms": k_fill / args.steps, "trace_ms": k_trace / args.steps,
                          "generic_ms": k_gen / args.steps,

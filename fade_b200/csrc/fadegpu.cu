@@ -148,6 +148,10 @@ struct fadegpu_batch {
     int64_t *d_src_off = nullptr;
     const uint8_t *d_view_seq4 = nullptr;              // device address of the pinned view's seq4
     std::vector<int32_t> idx;                          // gather scratch
+    BinArgs ba{};                                      // the binning of the last submit (for replays)
+    bool ba_valid = false;
+    AlnDesc *d_aln_scratch = nullptr;                  // replays scatter into these instead of the live descriptors
+    int64_t *d_i64_scratch = nullptr;
     cudaEvent_t ev_prep = nullptr, ev_ready = nullptr, ev_done = nullptr;
     cudaEvent_t ev_lane[2] = { nullptr, nullptr };    // end of the batch's work on each kernel lane
     int lanes_used = 1;
@@ -714,6 +718,7 @@ void fadegpu_free_batch(fadegpu_batch *b)
     free_host(b->h_hist); free_host(b->h_keybase); free_host(b->h_stats); free_host(b->h_aln_start);
     free_host(b->h_c_seq4); free_host(b->h_c_seq_off); free_host(b->h_c_pos); free_host(b->h_c_lq); free_host(b->h_c_tid);
     free_host(b->h_c_alen); free_host(b->h_c_cl); free_host(b->h_c_cr); free_host(b->h_c_read); free_dev(b->d_in_read); free_dev(b->d_src_off);
+    free_dev(b->d_aln_scratch); free_dev(b->d_i64_scratch);
     if (b->ev_prep) cudaEventDestroy(b->ev_prep);
     if (b->ev_ready) cudaEventDestroy(b->ev_ready);
     if (b->ev_done) cudaEventDestroy(b->ev_done);
@@ -1115,6 +1120,7 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
     }
     b->st.n_reads = n_reads;
     b->n_aln = 0; b->n_items = 0;
+    b->ba_valid = false;
     cudaStream_t s2 = c->stream2;
     CU(c, cudaEventRecord(b->ev[0], s2));
     // pull: every read's fields are DMA'd from the pinned view (36 B/read), the bases stay there until
@@ -1144,6 +1150,7 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
         ba.window = c->p.window_size; ba.min_length = c->p.min_length; ba.flags = c->p.flags;
         ba.key = b->d_key; ba.tlen = b->d_tlen; ba.start = b->d_start; ba.hist = b->d_hist; ba.stats = b->d_stats;
         ba.keybase = b->d_keybase; ba.cursor = b->d_cursor; ba.aln = b->d_aln; ba.aln_start = b->d_aln_start;
+        b->ba = ba; b->ba_valid = true;
         CU(c, launch_bin_classify(ba, s2));
         CU(c, cudaMemcpyAsync(b->h_hist, b->d_hist, (size_t)BIN_KEYS * 4, cudaMemcpyDeviceToHost, s2));
         CU(c, cudaMemcpyAsync(b->h_stats, b->d_stats, 64, cudaMemcpyDeviceToHost, s2));
@@ -1392,31 +1399,54 @@ int fadegpu_get_stats(const fadegpu_batch *b, fadegpu_stats *s)
     return FADEGPU_OK;
 }
 
-int fadegpu_replay_kernels(fadegpu_ctx *c, fadegpu_batch *b, int32_t iters, float *ms_out)
+// Replays re-run the device side of a submit on what it left resident in HBM: the binning kernels
+// (length floor, window arithmetic, histogram, scatter of the descriptors -- into scratch, because the
+// order among equal window lengths is not reproducible and the live descriptors point at the bases
+// already fetched), then fills / traceback / generic, then the result index.  No host work, no copies.
+static int replay_binning(fadegpu_ctx *c, fadegpu_batch *b, cudaEvent_t *dep)
 {
-    if (!c || !b || b->ctx != c || iters <= 0) return fail(c, FADEGPU_E_ARG, "fadegpu_replay_kernels: bad arguments");
-    if (b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_replay_kernels: batch in flight");
-    if (b->plan.empty() && b->n_aln > 0) return fail(c, FADEGPU_E_STATE, "fadegpu_replay_kernels: nothing submitted");
-    drain_submits(c);
-    std::lock_guard<std::mutex> submit_guard(c->submit_mu);
-    CU(c, cudaSetDevice(c->device));
-    // one pass with per-stage events (serialising), then `iters` untouched passes for the total
-    float f = 0, t = 0, g = 0;
-    { int rc = run_plan(c, b, &f, &t, &g, nullptr, nullptr); if (rc) return rc; }
-    b->st.fill_ms = f; b->st.trace_ms = t; b->st.generic_ms = g;
-    cudaEvent_t e0, e1;
-    CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
-    { CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaStreamSynchronize(c->tstream)); }
-    CU(c, cudaEventRecord(e0, c->stream));
-    for (int i = 0; i < iters; ++i) { int rc = run_plan(c, b, nullptr, nullptr, nullptr, nullptr, nullptr); if (rc) return rc; }
+    *dep = nullptr;
+    if (!b->dev_binning || !b->ba_valid) return 0;
+    const size_t n = (size_t)b->v.max_reads;
+    if (!b->d_aln_scratch) {
+        CU(c, cudaMalloc((void **)&b->d_aln_scratch, n * sizeof(AlnDesc)));
+        CU(c, cudaMalloc((void **)&b->d_i64_scratch, 2 * n * sizeof(int64_t)));
+    }
+    cudaStream_t s2 = c->stream2;
+    CU(c, cudaMemsetAsync(b->d_hist, 0, (size_t)BIN_KEYS * 4, s2));
+    CU(c, cudaMemsetAsync(b->d_cursor, 0, (size_t)BIN_KEYS * 4, s2));
+    CU(c, cudaMemsetAsync(b->d_stats, 0, 128, s2));
+    BinArgs ba = b->ba;
+    CU(c, launch_bin_classify(ba, s2));
+    if (b->n_aln > 0) {
+        ba.aln = b->d_aln_scratch; ba.aln_start = b->d_i64_scratch; ba.src_off = b->d_i64_scratch + n;
+        if (ba.seq_cursor) ba.seq_cursor = b->d_stats + 9;
+        CU(c, launch_bin_scatter(ba, s2));
+    }
+    CU(c, cudaEventRecord(b->ev_ready, s2));
+    *dep = b->ev_ready;
+    return 0;
+}
+
+static int replay_pass(fadegpu_ctx *c, fadegpu_batch *b)
+{
+    cudaEvent_t dep = nullptr;
+    { int rc = replay_binning(c, b, &dep); if (rc) return rc; }
+    { int rc = run_plan(c, b, nullptr, nullptr, nullptr, nullptr, dep); if (rc) return rc; }
+    if (b->dev_binning && b->n_aln > 0) {
+        { int rc = join_lanes(c, b, c->stream3); if (rc) return rc; }
+        CU(c, launch_result_index(b->d_out, (int)b->n_aln, b->n_reads, b->d_rflags, b->d_ridx, b->d_stats + 7, c->stream3));
+        CU(c, cudaEventRecord(b->ev_done, c->stream3));
+    }
+    return 0;
+}
+
+// the ctx stream continues after everything a replay pass of b queued
+static int replay_join(fadegpu_ctx *c, fadegpu_batch *b)
+{
     { int rc = join_lanes(c, b, c->stream); if (rc) return rc; }
-    CU(c, cudaEventRecord(e1, c->stream));
-    CU(c, cudaEventSynchronize(e1));
-    float ms = 0;
-    CU(c, cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (ms_out) *ms_out = ms;
-    return FADEGPU_OK;
+    if (b->dev_binning && b->n_aln > 0) CU(c, cudaStreamWaitEvent(c->stream, b->ev_done, 0));
+    return 0;
 }
 
 int fadegpu_replay_batches(fadegpu_ctx *c, fadegpu_batch *const *batches, int32_t n_batches, int32_t iters, float *ms_out)
@@ -1433,16 +1463,13 @@ int fadegpu_replay_batches(fadegpu_ctx *c, fadegpu_batch *const *batches, int32_
     CU(c, cudaSetDevice(c->device));
     cudaEvent_t e0, e1;
     CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
-    { CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaStreamSynchronize(c->tstream)); }
+    CU(c, cudaDeviceSynchronize());
     CU(c, cudaEventRecord(e0, c->stream));
-    fadegpu_batch *last = nullptr;
+    CU(c, cudaStreamWaitEvent(c->stream2, e0, 0));
     for (int32_t it = 0; it < iters; ++it)
-        for (int32_t i = 0; i < n_batches; ++i) {
-            int rc = run_plan(c, batches[i], nullptr, nullptr, nullptr, nullptr, nullptr);
-            if (rc) return rc;
-            last = batches[i];
-        }
-    { int rc = join_lanes(c, last, c->stream); if (rc) return rc; }
+        for (int32_t i = 0; i < n_batches; ++i) { int rc = replay_pass(c, batches[i]); if (rc) return rc; }
+    // the streams are in order, so the last pass of every batch covers the earlier ones
+    for (int32_t i = 0; i < n_batches; ++i) { int rc = replay_join(c, batches[i]); if (rc) return rc; }
     CU(c, cudaEventRecord(e1, c->stream));
     CU(c, cudaEventSynchronize(e1));
     float ms = 0;
@@ -1450,6 +1477,24 @@ int fadegpu_replay_batches(fadegpu_ctx *c, fadegpu_batch *const *batches, int32_
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (ms_out) *ms_out = ms;
     return FADEGPU_OK;
+}
+
+int fadegpu_replay_kernels(fadegpu_ctx *c, fadegpu_batch *b, int32_t iters, float *ms_out)
+{
+    if (!c || !b || b->ctx != c || iters <= 0) return fail(c, FADEGPU_E_ARG, "fadegpu_replay_kernels: bad arguments");
+    if (b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_replay_kernels: batch in flight");
+    if (b->plan.empty() && b->n_aln > 0) return fail(c, FADEGPU_E_STATE, "fadegpu_replay_kernels: nothing submitted");
+    drain_submits(c);
+    {   // one pass with per-stage events (serialising: fill / traceback / generic), then the timed passes
+        std::lock_guard<std::mutex> submit_guard(c->submit_mu);
+        CU(c, cudaSetDevice(c->device));
+        float f = 0, t = 0, g = 0;
+        int rc = run_plan(c, b, &f, &t, &g, nullptr, nullptr);
+        if (rc) return rc;
+        b->st.fill_ms = f; b->st.trace_ms = t; b->st.generic_ms = g;
+    }
+    fadegpu_batch *one[1] = { b };
+    return fadegpu_replay_batches(c, one, 1, iters, ms_out);
 }
 
 int fadegpu_measure_alu_peak(fadegpu_ctx *c, double *ops_per_sec_out, double *sm_clock_mhz_out)

@@ -25,7 +25,8 @@
  * never throws or aborts.  There is NO CPU fallback: without a CUDA device (or with the kernels
  * failing to launch) calls fail with FADEGPU_E_CUDA / FADEGPU_E_NODEV.
  * Threading: a ctx (and its batches) is driven by one host thread at a time; distinct ctxs may be
- * driven concurrently.  All buffers handed out are owned by the library.
+ * driven concurrently.  A ctx owns one helper thread (started by the first fadegpu_submit) that
+ * plans and launches queued batches.  All buffers handed out are owned by the library.
  */
 #ifndef FADEGPU_H
 #define FADEGPU_H
@@ -58,7 +59,8 @@ typedef struct fadegpu_params {
     int32_t mismatch;      /* -3  */
     uint32_t flags;        /* FADEGPU_F_* */
     int64_t scratch_bytes; /* cap on the device checkpoint scratch per launch; 0 = default */
-    int32_t host_threads;  /* host threads used by submit/wait (binning, gather, scatter); 0 = all cores */
+    int32_t host_threads;  /* host threads of the library's per-read loops (gather of fadegpu_submit_inputs,
+                              scatter of fadegpu_wait, FADEGPU_F_HOST_BINNING); 0 = all cores */
     int32_t reserved;
 } fadegpu_params;
 
@@ -66,8 +68,8 @@ typedef struct fadegpu_params {
 #define FADEGPU_F_FORCE_GENERIC 1u /* route every alignment through the generic (slow) kernel */
 #define FADEGPU_F_NO_SHORTCUT 8u   /* traceback: always replay blocks, never use the ungapped-diagonal proof
                                       (A/B switch; results are identical) */
-#define FADEGPU_F_HOST_BINNING 16u  /* fadegpu_submit: bin the reads on the host (as fadegpu_submit_inputs
-                                      does) instead of uploading the pinned view and binning on the device */
+#define FADEGPU_F_HOST_BINNING 16u  /* both submit calls: classify, sort and gather the reads on the host (the first
+                                      implementation, kept as an A/B switch) instead of binning them on the device */
 #define FADEGPU_F_SYNC_SUBMIT 32u   /* fadegpu_submit: plan and launch on the calling thread (errors of the batch
                                       are then returned by fadegpu_submit itself instead of fadegpu_wait) */
 #define FADEGPU_F_NO_SCATTER 2u    /* fadegpu_wait fills only flags[] and the compact results
