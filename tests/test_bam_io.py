@@ -22,7 +22,13 @@ def rich_lines(n=400, seed=9):
         seq = "".join(rng.choice("ACGTNRYKM") for _ in range(L)) or "*"
         qual = "*" if L == 0 or k % 7 == 0 else "".join(chr(33 + rng.randrange(42)) for _ in range(L))
         unmapped = k % 11 == 0
-        cig = "*" if unmapped or L == 0 else (f"{L}M" if k % 3 else f"3S{max(L - 5, 1)}M2S" if L > 6 else f"{L}M")
+        if unmapped or L == 0:
+            cig = "*"
+        elif L > 100 and k % 3 == 0:
+            a, b = rng.randrange(1, 40), rng.randrange(0, 40)          # clips long enough to be realigned
+            cig = f"{a}S{L - a - b}M" + (f"{b}S" if b else "")
+        else:
+            cig = f"3S{L - 5}M2S" if (L > 6 and k % 3 == 1) else f"{L}M"
         rname = "*" if unmapped else rng.choice(["chrA", "chrB"])
         pos = 0 if unmapped else rng.randrange(1, 4000)
         rnext = rng.choice(["*", "=", "chrB"]) if not unmapped else "*"

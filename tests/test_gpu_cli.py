@@ -124,3 +124,31 @@ def test_cli_annotate_reads_and_writes_bam(tmp_path):
     assert p1.returncode == 0 and p2.returncode == 0
     strip = lambda ls: [ln for ln in ls if not ln.startswith("@PG")]
     assert strip(bamcodec.decode(p1.stdout)) == strip(p2.stdout.decode().splitlines())
+
+
+def test_binary_bam_path_equals_text_path_on_rich_records(tmp_path):
+    """bamfast.hpp (binary records end to end) against the SAM text loop on records of every shape: unmapped,
+    '*' SEQ / QUAL / CIGAR, all aux types incl. B arrays, pre-existing rs / am / ab tags, several contigs."""
+    import random
+
+    import bamcodec
+    from test_bam_io import rich_lines
+    rng = random.Random(21)
+    fa = tmp_path / "ref.fa"
+    with open(fa, "w") as f:
+        for name, ln in (("chrA", 100000), ("chrB", 5000)):
+            f.write(f">{name}\n" + "".join(rng.choice("ACGT") for _ in range(ln)) + "\n")
+    lines = rich_lines(3000, seed=22)
+    bam = tmp_path / "rich.bam"
+    bam.write_bytes(bamcodec.encode(lines))
+    outs = {}
+    for tag, flags in (("fast", []), ("text", ["--text-path"]), ("fast_b", ["-b", "--batch", "512"]), ("text_u", ["-u", "--text-path"])):
+        p = subprocess.run([BIN, "annotate", *flags, str(bam), str(fa)], capture_output=True)
+        assert p.returncode == 0, p.stderr.decode()
+        ls = p.stdout.decode().splitlines() if not flags or flags == ["--text-path"] else bamcodec.decode(p.stdout)
+        outs[tag] = [ln for ln in ls if not ln.startswith("@PG\tID:fade-annotate")]
+    assert outs["fast"] == outs["text"] == outs["fast_b"] == outs["text_u"]
+    recs = [ln for ln in outs["fast"] if not ln.startswith("@")]
+    assert len(recs) == 3000 and all("\trs:i:" in ln for ln in recs)
+    assert sum("\trs:i:1" in ln or "\trs:i:33" in ln for ln in recs) > 300          # soft-clipped reads went to the GPU
+    assert not any(ln.count("\tam:Z:") > 1 or ln.count("\trs:i:") > 1 for ln in recs)   # old tags were replaced
