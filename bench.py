@@ -425,8 +425,8 @@ def main():
                          "frac": achieved / peak if peak > 0 else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (sw_fill_kernel<19>)
                          # per launch, from the ncu --set full capture of a 1 M-read chunk of this workload
-                         # (profiles/r01_prof_fill_final_raw.csv); only meaningful for the default configuration
-                         "traffic": 2.398e9 if (args.workload == "c2" and chunk == 1_000_000) else None,
+                         # (profiles/r01_prof_fill_5blk_raw.csv: 0.173 GB read + 2.293 GB written); only meaningful for the default configuration
+                         "traffic": 2.466e9 if (args.workload == "c2" and chunk == 1_000_000) else None,
                          "kernel": "dominant: sw_fill_kernel<19> (80 % of the path); achieved = cells / time of ALL "
                                    "kernels of the path (binning + fill + traceback rounds + generic + result index)",
                          "fill_only_gcups": fill_gcups,
