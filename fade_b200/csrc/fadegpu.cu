@@ -1,9 +1,13 @@
 // fadegpu.cu -- C ABI (include/fadegpu.h) and host runtime of libfadegpu: contexts, packed
-// reference upload, pinned batch buffers, length binning, launch planning, result scatter.
+// reference upload, pinned batch buffers, queued submits, launch planning, streams, results.
 //
-// Host-side work that mirrors the reference: the length floor of source/analysis.d:34 and the
-// window arithmetic of source/analysis.d:45-59 (both trivially cheap) are evaluated here while
-// building the alignment descriptors; everything else of align_clip runs in kernels.cu.
+// A submit is: (fadegpu_submit_inputs only: gather of the reads past the length floor, on the
+// caller's thread) -> on the ctx thread: upload, bin_classify_kernel (length floor of
+// source/analysis.d:34, window arithmetic of source/analysis.d:45-59, histogram), launch plan from the
+// histogram, bin_scatter_kernel (sorted descriptors), seq_pull_kernel (bases fetched from the pinned
+// view), then fills on `stream` and traceback rounds on `tstream` over two alternating scratch sets,
+// result_index_kernel and the copies home on `stream3`.  FADEGPU_F_HOST_BINNING keeps the first
+// implementation, which evaluates the floor and the windows and sorts on the host.
 // There is no CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -53,8 +57,8 @@ struct fadegpu_ctx {
     // the following one): their many small, latency-bound grids take SM slots as fill blocks retire.
     // Two scratch sets alternate between consecutive launches, ordered by events.
     cudaStream_t tstream = nullptr;
-    unsigned next_lane = 0;
-    struct Lane {
+    unsigned next_set = 0;
+    struct ScratchSet {
         cudaEvent_t ev_fill = nullptr, ev_trace = nullptr;   // last fill / last traceback that used this scratch set
         bool used = false;
         uint32_t *d_ck = nullptr;        // fill checkpoints
@@ -66,8 +70,8 @@ struct fadegpu_ctx {
         uint8_t *d_trace = nullptr;
         size_t trace_bytes = 0;
         unsigned int *d_qcount = nullptr;
-    } lane[2];
-    int n_lanes = 2;
+    } scratch[2];
+    int n_sets = 2;
     uint32_t *d_alu = nullptr;
     int sm_count = 148;
     int host_threads = 1;
@@ -153,8 +157,7 @@ struct fadegpu_batch {
     AlnDesc *d_aln_scratch = nullptr;                  // replays scatter into these instead of the live descriptors
     int64_t *d_i64_scratch = nullptr;
     cudaEvent_t ev_prep = nullptr, ev_ready = nullptr, ev_done = nullptr;
-    cudaEvent_t ev_lane[2] = { nullptr, nullptr };    // end of the batch's work on each kernel lane
-    int lanes_used = 1;
+    cudaEvent_t ev_kernels = nullptr;                  // end of the batch's kernels (recorded on tstream)
     // asynchronous submit (guarded by ctx->q_mu)
     bool queued = false;
     int submit_rc = 0;
@@ -326,8 +329,8 @@ int build_plan(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_aln, const int64_t *c
     b->st.scratch_bytes = (int64_t)ck_needed;
     // a slot for wildcard alignments discovered on the device, sized for the largest problem
     if (n_aln > 0) gen_needed = std::max(gen_needed, gen_slot_bytes(qmax_all, tmax_all));
-    for (int l = 0; l < (b->plan.empty() ? 0 : c->n_lanes); ++l) {
-        fadegpu_ctx::Lane &ln = c->lane[l];
+    for (int l = 0; l < (b->plan.empty() ? 0 : c->n_sets); ++l) {
+        fadegpu_ctx::ScratchSet &ln = c->scratch[l];
         if (ck_needed) { int rc = ensure_dev(c, (void **)&ln.d_ck, &ln.ck_bytes, ck_needed); if (rc) return rc; }
         if (trace_needed) { int rc = ensure_dev(c, (void **)&ln.d_trace, &ln.trace_bytes, trace_needed); if (rc) return rc; }
         if (gen_needed) {
@@ -341,7 +344,7 @@ int build_plan(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_aln, const int64_t *c
 
 // Queue every kernel of the batch's plan: fills on c->stream (after `dep`: the batch's inputs, or the
 // start of a timed replay), traceback + generic on c->tstream, consecutive launches on alternating
-// scratch sets.  On return b->ev_lane[0] marks the end of the batch's kernels; the caller joins it.
+// scratch sets.  On return b->ev_kernels marks the end of the batch's kernels; the caller joins it.
 // With stage timers every launch is synchronised.
 int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, float *gen_ms, int *launches, cudaEvent_t dep)
 {
@@ -355,8 +358,8 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
     cudaStream_t sf = c->stream, st = c->tstream;
     if (dep) CU(c, cudaStreamWaitEvent(sf, dep, 0));
     for (const Launch &L : b->plan) {
-        fadegpu_ctx::Lane &ln = c->lane[c->next_lane++ % (unsigned)c->n_lanes];
-        // the lane's scratch is free again once its previous traceback is through
+        fadegpu_ctx::ScratchSet &ln = c->scratch[c->next_set++ % (unsigned)c->n_sets];
+        // the scratch set is free again once its previous traceback is through
         if (ln.used) CU(c, cudaStreamWaitEvent(sf, ln.ev_trace, 0));
         ln.used = true;
         const uint8_t *seq = b->dev_binning ? b->d_in_seq4 : b->d_seq;
@@ -431,7 +434,7 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
             ga.chunk = 1;
             ga.open = c->p.gap_open; ga.extend = c->p.gap_extend; ga.match = c->p.match; ga.mismatch = c->p.mismatch;
             ga.min_length = c->p.min_length;
-            CU(c, cudaEventRecord(ln.ev_fill, sf));        // (orders the lane: dep and the previous traceback)
+            CU(c, cudaEventRecord(ln.ev_fill, sf));        // (orders tstream after dep and the set's previous traceback)
             CU(c, cudaStreamWaitEvent(st, ln.ev_fill, 0));
             if (timed) CU(c, cudaEventRecord(e0, st));
             CU(c, cudaMemsetAsync(ln.d_cursor, 0, sizeof(unsigned int), st));
@@ -447,17 +450,16 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
         }
     }
     if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
-    b->lanes_used = 1;
     // every launch ends on tstream, in launch order: its tail is the batch's
-    CU(c, cudaEventRecord(b->ev_lane[0], b->plan.empty() ? sf : st));
+    CU(c, cudaEventRecord(b->ev_kernels, b->plan.empty() ? sf : st));
     if (launches) *launches = nl;
     return 0;
 }
 
-// the stream `s` continues after every lane the batch used
-int join_lanes(fadegpu_ctx *c, fadegpu_batch *b, cudaStream_t s)
+// the stream `s` continues after the batch's kernels
+int join_kernels(fadegpu_ctx *c, fadegpu_batch *b, cudaStream_t s)
 {
-    for (int l = 0; l < b->lanes_used; ++l) CU(c, cudaStreamWaitEvent(s, b->ev_lane[l], 0));
+    CU(c, cudaStreamWaitEvent(s, b->ev_kernels, 0));
     return 0;
 }
 
@@ -528,14 +530,14 @@ int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_alu, 64)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&c->tstream, cudaStreamNonBlocking, -1)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&c->lane[0].ev_fill, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&c->lane[1].ev_fill, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&c->lane[0].ev_trace, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&c->lane[1].ev_trace, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaMalloc(&c->lane[0].d_cursor, sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaMalloc(&c->lane[1].d_cursor, sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaMalloc(&c->lane[0].d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaMalloc(&c->lane[1].d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->scratch[0].ev_fill, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->scratch[1].ev_fill, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->scratch[0].ev_trace, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->scratch[1].ev_trace, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaMalloc(&c->scratch[0].d_cursor, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(&c->scratch[1].d_cursor, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(&c->scratch[0].d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(&c->scratch[1].d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, -2)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, -2)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
@@ -561,11 +563,11 @@ void fadegpu_destroy(fadegpu_ctx *c)
     if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
     free_reference(c);
     if (c->tstream) { cudaStreamSynchronize(c->tstream); cudaStreamDestroy(c->tstream); }
-    for (auto &ln : c->lane) {
+    for (auto &ln : c->scratch) {
         if (ln.ev_fill) cudaEventDestroy(ln.ev_fill);
         if (ln.ev_trace) cudaEventDestroy(ln.ev_trace);
     }
-    for (auto &ln : c->lane) { free_dev(ln.d_ck); free_dev(ln.d_gen); free_dev(ln.d_cursor); free_dev(ln.d_trace); free_dev(ln.d_qcount); }
+    for (auto &ln : c->scratch) { free_dev(ln.d_ck); free_dev(ln.d_gen); free_dev(ln.d_cursor); free_dev(ln.d_trace); free_dev(ln.d_qcount); }
     free_dev(c->d_alu);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -722,7 +724,7 @@ void fadegpu_free_batch(fadegpu_batch *b)
     if (b->ev_prep) cudaEventDestroy(b->ev_prep);
     if (b->ev_ready) cudaEventDestroy(b->ev_ready);
     if (b->ev_done) cudaEventDestroy(b->ev_done);
-    for (auto &e : b->ev_lane) if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (b->ev_kernels) cudaEventDestroy(b->ev_kernels);
     for (auto &e : b->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     delete b;
 }
@@ -771,7 +773,7 @@ int fadegpu_alloc_batch(fadegpu_ctx *c, int64_t max_reads, int64_t max_seq_bytes
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_prep);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_ready);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
-    for (auto &ev : b->ev_lane) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_kernels, cudaEventDisableTiming);
     for (auto &ev : b->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e != cudaSuccess) {
         int rc = cuda_fail(c, e, "fadegpu_alloc_batch");
@@ -1013,7 +1015,7 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     int nl = 0;
     { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl, b->ev_ready); if (rc) return rc; }
     b->st.kernel_launches = nl;
-    { int rc = join_lanes(c, b, c->stream3); if (rc) return rc; }
+    { int rc = join_kernels(c, b, c->stream3); if (rc) return rc; }
     CU(c, cudaEventRecord(b->ev[2], c->stream3));
     if (n_aln > 0)
         CU(c, cudaMemcpyAsync(b->h_out, b->d_out, (size_t)n_aln * sizeof(AlnOut), cudaMemcpyDeviceToHost, c->stream3));
@@ -1208,7 +1210,7 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
     { int rc = run_plan(c, b, nullptr, nullptr, nullptr, &nl, b->ev_ready); if (rc) return rc; }
     b->st.kernel_launches = nl + (n > 0 ? 1 : 0) + (n_aln > 0 ? (pull ? 3 : 2) : 0);
     cudaStream_t s3 = c->stream3;                    // results go home while the next batch computes
-    { int rc = join_lanes(c, b, s3); if (rc) return rc; }
+    { int rc = join_kernels(c, b, s3); if (rc) return rc; }
     CU(c, cudaEventRecord(b->ev[2], s3));
     if (n_aln > 0) CU(c, launch_result_index(b->d_out, (int)n_aln, n_reads, b->d_rflags, b->d_ridx, b->d_stats + 7, s3));
     if (n_reads > 0) {
@@ -1434,7 +1436,7 @@ static int replay_pass(fadegpu_ctx *c, fadegpu_batch *b)
     { int rc = replay_binning(c, b, &dep); if (rc) return rc; }
     { int rc = run_plan(c, b, nullptr, nullptr, nullptr, nullptr, dep); if (rc) return rc; }
     if (b->dev_binning && b->n_aln > 0) {
-        { int rc = join_lanes(c, b, c->stream3); if (rc) return rc; }
+        { int rc = join_kernels(c, b, c->stream3); if (rc) return rc; }
         CU(c, launch_result_index(b->d_out, (int)b->n_aln, b->n_reads, b->d_rflags, b->d_ridx, b->d_stats + 7, c->stream3));
         CU(c, cudaEventRecord(b->ev_done, c->stream3));
     }
@@ -1444,7 +1446,7 @@ static int replay_pass(fadegpu_ctx *c, fadegpu_batch *b)
 // the ctx stream continues after everything a replay pass of b queued
 static int replay_join(fadegpu_ctx *c, fadegpu_batch *b)
 {
-    { int rc = join_lanes(c, b, c->stream); if (rc) return rc; }
+    { int rc = join_kernels(c, b, c->stream); if (rc) return rc; }
     if (b->dev_binning && b->n_aln > 0) CU(c, cudaStreamWaitEvent(c->stream, b->ev_done, 0));
     return 0;
 }
