@@ -363,36 +363,45 @@ struct SamRec {
     }
 };
 
-struct Sam {
+struct Sam {   // header of the stream; the records are pulled one at a time (inputs need not fit in memory)
     std::vector<std::string> header, contigs;
-    std::vector<SamRec> recs;
     std::string last_pg;
-};
-
-bool read_sam(const std::string &path, Sam &sam)
-{
     samio::LineSource in;
-    if (!in.open(path)) return false;
-    std::string line;
-    while (in.getline(line)) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        if (line.empty()) continue;
-        if (line[0] == '@') {
-            sam.header.push_back(line);
+    std::string pending;      // first record line, read while looking for the end of the header
+    bool have_pending = false;
+
+    bool open(const std::string &path)
+    {
+        if (!in.open(path)) return false;
+        std::string line;
+        while (in.getline(line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            if (line.empty()) continue;
+            if (line[0] != '@') { pending.swap(line); have_pending = true; break; }
+            header.push_back(line);
             const auto f = split_tab(line);
-            if (f[0] == "@SQ") for (auto &x : f) if (x.rfind("SN:", 0) == 0) sam.contigs.push_back(x.substr(3));
-            if (f[0] == "@PG") for (auto &x : f) if (x.rfind("ID:", 0) == 0) sam.last_pg = x.substr(3);
-            continue;
+            if (f[0] == "@SQ") for (auto &x : f) if (x.rfind("SN:", 0) == 0) contigs.push_back(x.substr(3));
+            if (f[0] == "@PG") for (auto &x : f) if (x.rfind("ID:", 0) == 0) last_pg = x.substr(3);
+        }
+        return !in.failed();
+    }
+    // next record; 0 = end of input, -1 = malformed record or damaged input
+    int next(SamRec &r)
+    {
+        std::string line;
+        for (;;) {
+            if (have_pending) { line.swap(pending); have_pending = false; }
+            else if (!in.getline(line)) return in.failed() ? -1 : 0;
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            if (!line.empty()) break;
         }
         auto f = split_tab(line);
-        if (f.size() < 11) return false;
-        SamRec r;
+        if (f.size() < 11) return -1;
         r.f.assign(f.begin(), f.begin() + 11);
         r.tags.assign(f.begin() + 11, f.end());
-        sam.recs.push_back(std::move(r));
+        return 1;
     }
-    return !in.failed();
-}
+};
 
 void write_header(const Sam &sam, const char *id, const std::string &cl)
 {
@@ -538,12 +547,14 @@ int cmd_out(int argc, char **argv, const std::string &cl)
     if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
     open_output(con);
     Sam sam;
-    if (!read_sam(path, sam)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
+    if (!sam.open(path)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
     write_header(sam, "fade-extract", cl);   // sic: filter.d:173 uses the ID of extract
     OutStats st;
     auto put = [](const SamRec &r) { out_line(r.line()); };
+    int rc = 0;
+    SamRec r;
     if (clip) {   // filter.d:182-208
-        for (auto &r : sam.recs) {
+        while ((rc = sam.next(r)) == 1) {
             ++st.read_count;
             bool have;
             const int rs = rs_of(r, have);
@@ -551,31 +562,39 @@ int cmd_out(int argc, char **argv, const std::string &cl)
             st.parse(rs);
             if (!(rs & 6)) put(r); else put(clip_read(r, rs, sam));
         }
-    } else {      // filter.d:209-266
+    } else {      // filter.d:209-266: the first ten records decide whether the input is taken as name-sorted
+        std::vector<SamRec> head;
+        while (head.size() < 10 && (rc = sam.next(r)) == 1) head.push_back(r);
         bool sorted = true;
-        for (size_t k = 0; k + 1 < sam.recs.size() && k + 1 < 10; ++k)
-            if (natural_compare(sam.recs[k + 1].f[0], sam.recs[k].f[0]) < 0) sorted = false;
+        for (size_t k = 0; k + 1 < head.size(); ++k)
+            if (natural_compare(head[k + 1].f[0], head[k].f[0]) < 0) sorted = false;
+        size_t hp = 0;
+        auto next = [&](SamRec &o) -> int {   // the buffered head first, then the rest of the stream
+            if (hp < head.size()) { o = head[hp++]; return 1; }
+            if (rc != 1) return rc;
+            return rc = sam.next(o);
+        };
         if (sorted) {
             fprintf(stderr, "[W::fade-out] Output looks name-sorted, ejecting all reads with same readname if any have an artifact\n");
-            size_t k = 0;
-            while (k < sam.recs.size()) {
-                size_t e = k + 1;
-                while (e < sam.recs.size() && sam.recs[e].f[0] == sam.recs[e - 1].f[0]) ++e;
-                bool art = false;
-                for (size_t x = k; x < e; ++x) {
-                    ++st.read_count;
-                    bool have;
-                    const int rs = rs_of(sam.recs[x], have);
-                    if (!have) continue;
-                    st.parse(rs);
-                    if (rs & 6) art = true;
-                }
-                if (!art) for (size_t x = k; x < e; ++x) put(sam.recs[x]);
-                k = e;
+            std::vector<SamRec> group;
+            bool art = false;
+            auto flush_group = [&]() {
+                if (!art) for (auto &g : group) put(g);
+                group.clear();
+                art = false;
+            };
+            while (next(r) == 1) {
+                if (!group.empty() && group.back().f[0] != r.f[0]) flush_group();
+                ++st.read_count;
+                bool have;
+                const int rs = rs_of(r, have);
+                if (have) { st.parse(rs); if (rs & 6) art = true; }
+                group.push_back(r);
             }
+            flush_group();
         } else {
             fprintf(stderr, "[W::fade-out] Output doesn't look name-sorted, ejecting by only reads with an artifact\n");
-            for (auto &r : sam.recs) {
+            while (next(r) == 1) {
                 ++st.read_count;
                 bool have;
                 const int rs = rs_of(r, have);
@@ -585,6 +604,7 @@ int cmd_out(int argc, char **argv, const std::string &cl)
             }
         }
     }
+    if (rc < 0) { fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str()); return 1; }
     st.print();
     g_out->close();
     return 0;
@@ -604,11 +624,13 @@ int cmd_extract(int argc, char **argv, const std::string &cl)
     if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
     open_output(con);
     Sam sam;
-    if (!read_sam(path, sam)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
+    if (!sam.open(path)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
     write_header(sam, "fade-extract", cl);
     static const char comp[] = "=TGKCYSBAWRDMHVN";   // complement of "=ACMGRSVTWYHKDBN" (util.d:18-21)
     static const char nt16[] = "=ACMGRSVTWYHKDBN";
-    for (auto &r : sam.recs) {   // remap.d:29-85
+    SamRec r;
+    int rc;
+    while ((rc = sam.next(r)) == 1) {   // remap.d:29-85
         bool have;
         const int rs = rs_of(r, have);
         if (!have || !(rs & 6) || !r.has("am")) continue;
@@ -630,6 +652,7 @@ int cmd_extract(int argc, char **argv, const std::string &cl)
             if (!out_line(o)) return 1;
         }
     }
+    if (rc < 0) { fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str()); return 1; }
     g_out->close();
     return 0;
 }
