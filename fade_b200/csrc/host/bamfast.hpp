@@ -1,7 +1,8 @@
-// bamfast.hpp -- `fade-b200 annotate` on BAM input without a text detour (SURVEY 8f row 3:
-// "required for real-file end-to-end runs and for feeding 8 GPUs; the likely end-to-end bottleneck").
+// bamfast.hpp -- the record loop of `fade-b200 annotate` ("required for real-file
+// end-to-end runs and for feeding 8 GPUs; the likely end-to-end bottleneck").
 //
-// The batched mirror of anno.d:36-52 on binary records: BGZF blocks are inflated in parallel, the
+// The batched mirror of anno.d:36-52 on binary records: BGZF blocks are inflated in parallel (SAM text
+// input is cut into lines and converted to the same binary records in parallel), the
 // records of a batch are parsed in parallel (parse_clips / alignedLength / sc / sup through
 // fadehost_prepare, anno.d:61-74), their 4-bit bases are copied as they are into the pinned view of
 // a batch (the memcpy of INTEGRATION.md section 2), fadegpu_submit returns at once and the next
@@ -100,6 +101,95 @@ private:
     bool bad_ = false;
 };
 
+// SAM text as a source of binary records: lines are cut sequentially and converted side by side
+// (samio::sam_to_bam), appended to the stream as [block_size][record] exactly like a BAM payload
+class SamTextSource {
+public:
+    SamTextSource(FILE *f, const std::string &pre, int threads) : f_(f), threads_(std::max(1, threads)) { buf_.assign(pre.begin(), pre.end()); }
+    // header lines (up to the first record) into hdr
+    bool header(samio::Header &hdr)
+    {
+        std::string line;
+        for (;;) {
+            const int rc = peek_line(line);
+            if (rc <= 0 || line.empty() || line[0] != '@') return rc >= 0;
+            hdr.add_line(line);
+            pos_ = next_;
+        }
+    }
+    // up to max_lines further records appended to out; false when the input is exhausted (or bad())
+    bool more(std::vector<uint8_t> &out, const samio::Header &hdr, int max_lines)
+    {
+        std::vector<std::string> lines;
+        std::string line;
+        while ((int)lines.size() < max_lines) {
+            const int rc = peek_line(line);
+            if (rc <= 0) break;
+            pos_ = next_;
+            if (!line.empty()) lines.push_back(line);
+        }
+        if (lines.empty()) return false;
+        std::vector<std::string> recs(lines.size());
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad) num_threads(threads_)
+        for (long k = 0; k < (long)lines.size(); ++k)
+            if (!samio::sam_to_bam(lines[(size_t)k], hdr, recs[(size_t)k])) bad = 1;
+        if (bad) {
+            for (size_t k = 0; k < lines.size(); ++k)
+                if (recs[k].empty()) { fprintf(stderr, "fade-b200: malformed SAM record: %.200s\n", lines[k].c_str()); break; }
+            bad_ = true;
+            return false;
+        }
+        size_t tot = 0;
+        for (const auto &r : recs) tot += 4 + r.size();
+        size_t w = out.size();
+        out.resize(w + tot);
+        for (const auto &r : recs) {
+            const uint32_t n = (uint32_t)r.size();
+            for (int i = 0; i < 4; ++i) out[w + (size_t)i] = (uint8_t)(n >> (8 * i));
+            memcpy(&out[w + 4], r.data(), r.size());
+            w += 4 + r.size();
+        }
+        return true;
+    }
+    bool bad() const { return bad_; }
+
+private:
+    // the line starting at pos_ (without CR/LF) and where the next one starts; 0 = end of input
+    int peek_line(std::string &line)
+    {
+        for (;;) {
+            const char *s = buf_.data() + pos_;
+            const char *e = static_cast<const char *>(memchr(s, '\n', buf_.size() - pos_));
+            if (e) {
+                line.assign(s, (size_t)(e - s));
+                next_ = pos_ + (size_t)(e - s) + 1;
+                break;
+            }
+            if (eof_) {
+                if (pos_ == buf_.size()) return 0;
+                line.assign(s, buf_.size() - pos_);
+                next_ = buf_.size();
+                break;
+            }
+            buf_.erase(buf_.begin(), buf_.begin() + (long)pos_);   // keep the partial line, read on
+            pos_ = 0;
+            const size_t old = buf_.size();
+            buf_.resize(old + (8u << 20));
+            const size_t got = fread(buf_.data() + old, 1, 8u << 20, f_);
+            buf_.resize(old + got);
+            if (got == 0) eof_ = true;
+        }
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        return 1;
+    }
+    FILE *f_;
+    int threads_;
+    std::vector<char> buf_;
+    size_t pos_ = 0, next_ = 0;
+    bool eof_ = false, bad_ = false;
+};
+
 // BGZF blocks of `data`, compressed side by side, written in order (no EOF marker)
 inline void write_blocks(FILE *f, const uint8_t *data, size_t n, int level, int threads)
 {
@@ -186,20 +276,25 @@ struct Job {
 };
 
 // the whole command; returns the process exit code
-inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
-                        bool (*read_fasta)(const std::string &, std::map<std::string, std::string> &))
+inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, const Job &job,
+                            bool (*read_fasta)(const std::string &, std::map<std::string, std::string> &))
 {
     const int threads = job.prm.host_threads > 0 ? job.prm.host_threads : omp_get_max_threads();
-    BulkReader rd(fin, pre, threads);
+    BulkReader rd(fin, is_bam ? pre : std::string(), threads);
+    SamTextSource txt(fin, is_bam ? std::string() : pre, threads);
+    samio::Header hdr;
     std::vector<uint8_t> stream;
     size_t spos = 0;
     auto need = [&](size_t bytes) {   // make stream[spos, spos + bytes) available
-        while (stream.size() - spos < bytes) if (!rd.more(stream, 512)) return false;
+        while (stream.size() - spos < bytes)
+            if (!(is_bam ? rd.more(stream, 512) : txt.more(stream, hdr, 1 << 16))) return false;
         return true;
     };
-    // ---- header (SAMv1 4.2) ----
-    samio::Header hdr;
-    {
+    auto source_bad = [&]() { return is_bam ? rd.bad() : txt.bad(); };
+    // ---- header (SAMv1 1.3 / 4.2) ----
+    if (!is_bam) {
+        if (!txt.header(hdr)) { fprintf(stderr, "fade-b200: cannot read the SAM header\n"); return 1; }
+    } else {
         if (!need(12) || memcmp(&stream[spos], "BAM\1", 4) != 0) { fprintf(stderr, "fade-b200: not a BAM file\n"); return 1; }
         const uint32_t l_text = get_u32(&stream[spos + 4]);
         if (!need(12 + (size_t)l_text)) { fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
@@ -296,7 +391,7 @@ inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
         while ((int64_t)s.rec.size() < job.batch_n) {
             if (!need(4)) break;
             const uint32_t bs = get_u32(&stream[spos]);
-            if (bs < 32 || !need(4 + (size_t)bs)) { if (!rd.bad()) fprintf(stderr, "fade-b200: truncated BAM record\n"); rc_all = 1; break; }
+            if (bs < 32 || !need(4 + (size_t)bs)) { if (!source_bad()) fprintf(stderr, "fade-b200: truncated BAM record\n"); rc_all = 1; break; }
             const int32_t l_seq = get_i32(&stream[spos + 4 + 16]);
             if (l_seq < 0) { fprintf(stderr, "fade-b200: damaged BAM record\n"); rc_all = 1; break; }
             if (seq_bytes + (l_seq + 1) / 2 + 1024 > max_seq) {
@@ -309,7 +404,7 @@ inline int annotate_bam(FILE *fin, const std::string &pre, const Job &job,
             s.rec.push_back(m);
             spos += 4 + (size_t)bs;
         }
-        if (rd.bad()) { fprintf(stderr, "fade-b200: damaged BAM input\n"); rc_all = 1; }
+        if (source_bad()) { if (is_bam) fprintf(stderr, "fade-b200: damaged BAM input\n"); rc_all = 1; }
         if (s.rec.empty()) return false;
         t_read += omp_get_wtime() - t0; t0 = omp_get_wtime();
         // the slot takes the buffer (no copy, its capacity is reused two batches later); the unread tail moves on

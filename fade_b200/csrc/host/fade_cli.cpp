@@ -157,7 +157,7 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
         else if (a == "-w" || a == "--window-size") prm.window_size = atoi(need("--window-size"));
         else if (a == "--batch") batch_n = atoll(need("--batch"));
         else if (a == "--device") device = atoi(need("--device"));
-        else if (a == "--text-path") text_path = true;   // BAM input through the SAM text loop (A/B check of bamfast.hpp)
+        else if (a == "--text-path") text_path = true;   // the line-by-line SAM text loop (A/B check of bamfast.hpp)
         else if (a == "-h" || a == "--help") return usage();
         else if (output_flag(a, con)) {}
         else pos_args.push_back(a);
@@ -170,12 +170,14 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
     if (!fin_raw) { fprintf(stderr, "fade-b200: cannot open %s\n", pos_args[0].c_str()); return 1; }
     std::string pre(2, '\0');
     pre.resize(fread(&pre[0], 1, 2, fin_raw));
-    if (pre.size() == 2 && (uint8_t)pre[0] == 0x1f && (uint8_t)pre[1] == 0x8b && !text_path) {
-        // BAM input: binary records end to end (bamfast.hpp); SAM text input continues below
+    if (!text_path) {
+        // the record loop on binary records (bamfast.hpp): BAM as it is, SAM text converted on the way in;
+        // --text-path keeps the first, line-by-line implementation below (A/B check)
+        const bool is_bam = pre.size() == 2 && (uint8_t)pre[0] == 0x1f && (uint8_t)pre[1] == 0x8b;
         bamfast::Job job;
         job.prm = prm; job.device = device; job.batch_n = batch_n; job.con = con; job.cl = cl; job.version = kVersion;
         job.fasta_path = pos_args[1];
-        return bamfast::annotate_bam(fin_raw, pre, job, read_fasta);
+        return bamfast::annotate_records(fin_raw, pre, is_bam, job, read_fasta);
     }
     open_output(con);
 

@@ -105,8 +105,9 @@ def test_cli_annotate_reads_and_writes_bam(tmp_path):
         return p.stdout
 
     body = lambda ls: [ln for ln in ls if not ln.startswith("@PG\tID:fade-annotate")]
-    ref = body(run(sam).decode().splitlines())
+    ref = body(run(sam).decode().splitlines())                           # SAM text converted on the way in
     assert sum("\tam:Z:" in ln for ln in ref) > 50
+    assert body(run(sam, "--text-path").decode().splitlines()) == ref    # the line-by-line loop
     assert body(run(bam).decode().splitlines()) == ref                   # binary records end to end (bamfast.hpp)
     assert body(run(bam, "--text-path").decode().splitlines()) == ref    # BAM through the SAM text loop
     assert body(run(bam, "--batch", "700", "-t", "3").decode().splitlines()) == ref   # several double-buffered batches
