@@ -275,29 +275,39 @@ struct Job {
     std::string fasta_path;
 };
 
-// the whole command; returns the process exit code
-inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, const Job &job,
-                            bool (*read_fasta)(const std::string &, std::map<std::string, std::string> &))
-{
-    const int threads = job.prm.host_threads > 0 ? job.prm.host_threads : omp_get_max_threads();
-    BulkReader rd(fin, is_bam ? pre : std::string(), threads);
-    SamTextSource txt(fin, is_bam ? std::string() : pre, threads);
+// Records of a SAM or BAM input as one byte stream of [block_size][record] entries, plus its header
+struct RecordInput {
+    RecordInput(FILE *f, const std::string &pre, bool bam, int threads)
+        : is_bam(bam), rd(f, bam ? pre : std::string(), threads), txt(f, bam ? std::string() : pre, threads) {}
+    bool is_bam;
+    BulkReader rd;
+    SamTextSource txt;
     samio::Header hdr;
     std::vector<uint8_t> stream;
     size_t spos = 0;
-    auto need = [&](size_t bytes) {   // make stream[spos, spos + bytes) available
+
+    bool need(size_t bytes)   // make stream[spos, spos + bytes) available
+    {
         while (stream.size() - spos < bytes)
             if (!(is_bam ? rd.more(stream, 512) : txt.more(stream, hdr, 1 << 16))) return false;
         return true;
-    };
-    auto source_bad = [&]() { return is_bam ? rd.bad() : txt.bad(); };
-    // ---- header (SAMv1 1.3 / 4.2) ----
-    if (!is_bam) {
-        if (!txt.header(hdr)) { fprintf(stderr, "fade-b200: cannot read the SAM header\n"); return 1; }
-    } else {
-        if (!need(12) || memcmp(&stream[spos], "BAM\1", 4) != 0) { fprintf(stderr, "fade-b200: not a BAM file\n"); return 1; }
+    }
+    bool bad() const { return is_bam ? rd.bad() : txt.bad(); }
+    // header (SAMv1 1.3 / 4.2); false (with a message) when it cannot be read
+    bool read_header()
+    {
+        if (!is_bam) {
+            if (!txt.header(hdr)) { fprintf(stderr, "fade-b200: cannot read the SAM header\n"); return false; }
+            return true;
+        }
+        auto damaged = [] { fprintf(stderr, "fade-b200: damaged BAM input\n"); return false; };
+        if (!need(12) || memcmp(&stream[spos], "BAM\1", 4) != 0) {
+            if (bad()) return damaged();
+            fprintf(stderr, "fade-b200: not a BAM file\n");
+            return false;
+        }
         const uint32_t l_text = get_u32(&stream[spos + 4]);
-        if (!need(12 + (size_t)l_text)) { fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
+        if (!need(12 + (size_t)l_text)) return damaged();
         std::string text(reinterpret_cast<const char *>(&stream[spos + 8]), l_text);
         text.resize(strnlen(text.c_str(), text.size()));
         bool has_sq = false;
@@ -311,15 +321,98 @@ inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, cons
         const uint32_t n_ref = get_u32(&stream[spos]);
         spos += 4;
         for (uint32_t r = 0; r < n_ref; ++r) {
-            if (!need(4)) { fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
+            if (!need(4)) return damaged();
             const uint32_t l = get_u32(&stream[spos]);
-            if (!need(8 + (size_t)l)) { fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
+            if (!need(8 + (size_t)l)) return damaged();
             std::string nm(reinterpret_cast<const char *>(&stream[spos + 4]), l);
             nm.resize(strnlen(nm.c_str(), nm.size()));
+            // the binary reference list is authoritative when the text has no @SQ lines
             if (!has_sq) hdr.add_line("@SQ\tSN:" + nm + "\tLN:" + std::to_string(get_u32(&stream[spos + 4 + l])));
             spos += 8 + l;
         }
+        return true;
     }
+};
+
+// the header as SAM text (con 0) or as the first BGZF block(s) of a BAM file (util.d:65-76)
+inline void write_header(const samio::Header &hdr, int con, int threads)
+{
+    if (con == 0) {
+        for (const auto &l : hdr.lines) { fwrite(l.data(), 1, l.size(), stdout); fputc('\n', stdout); }
+        return;
+    }
+    std::string text, o("BAM\1", 4);
+    for (const auto &l : hdr.lines) { text += l; text += '\n'; }
+    samio::put_u32(o, (uint32_t)text.size());
+    o += text;
+    samio::put_u32(o, (uint32_t)hdr.names.size());
+    for (size_t r = 0; r < hdr.names.size(); ++r) {
+        samio::put_u32(o, (uint32_t)hdr.names[r].size() + 1);
+        o += hdr.names[r]; o.push_back('\0');
+        samio::put_u32(o, (uint32_t)hdr.lens[r]);
+    }
+    write_blocks(stdout, reinterpret_cast<const uint8_t *>(o.data()), o.size(), con == 1 ? 0 : 6, threads);
+}
+
+inline void write_eof_marker()
+{
+    static const uint8_t eof[28] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    fwrite(eof, 1, sizeof(eof), stdout);   // SAMv1 4.1.2
+}
+
+// `fade-b200 view --bulk`: every record through the parallel readers and writers of the annotate loop
+// (format conversion only; exercises this file's I/O without a GPU)
+inline int copy_records(FILE *fin, const std::string &pre, bool is_bam, int con, int threads)
+{
+    RecordInput in(fin, pre, is_bam, threads);
+    if (!in.read_header()) return 1;
+    write_header(in.hdr, con, threads);
+    for (;;) {
+        // whole records available in the stream
+        size_t end = in.spos;
+        while (end + 4 <= in.stream.size()) {
+            const uint32_t bs = get_u32(&in.stream[end]);
+            if (end + 4 + (size_t)bs > in.stream.size()) break;
+            end += 4 + (size_t)bs;
+        }
+        if (end > in.spos) {
+            if (con != 0) write_blocks(stdout, &in.stream[in.spos], end - in.spos, con == 1 ? 0 : 6, threads);
+            else {
+                std::string line;
+                for (size_t p = in.spos; p < end;) {
+                    const uint32_t bs = get_u32(&in.stream[p]);
+                    if (!samio::bam_to_sam(&in.stream[p + 4], bs, in.hdr, line)) { fprintf(stderr, "fade-b200: damaged BAM record\n"); return 1; }
+                    fwrite(line.data(), 1, line.size(), stdout); fputc('\n', stdout);
+                    p += 4 + (size_t)bs;
+                }
+            }
+            in.stream.erase(in.stream.begin(), in.stream.begin() + (long)end);
+            in.spos = 0;
+        }
+        const size_t have = in.stream.size();
+        if (!in.need(have + 1)) {   // nothing more to read
+            if (in.bad()) { if (is_bam) fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
+            if (have) { fprintf(stderr, "fade-b200: truncated BAM record\n"); return 1; }
+            break;
+        }
+    }
+    if (con != 0) write_eof_marker();
+    fflush(stdout);
+    return 0;
+}
+
+// the whole command; returns the process exit code
+inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, const Job &job,
+                            bool (*read_fasta)(const std::string &, std::map<std::string, std::string> &))
+{
+    const int threads = job.prm.host_threads > 0 ? job.prm.host_threads : omp_get_max_threads();
+    RecordInput in(fin, pre, is_bam, threads);
+    if (!in.read_header()) return 1;
+    samio::Header &hdr = in.hdr;
+    std::vector<uint8_t> &stream = in.stream;
+    size_t &spos = in.spos;
+    auto need = [&](size_t bytes) { return in.need(bytes); };
+    auto source_bad = [&]() { return in.bad(); };
     std::string last_pg;
     for (const auto &l : hdr.lines)
         if (l.compare(0, 3, "@PG") == 0) {
@@ -331,21 +424,7 @@ inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, cons
     pg += "\tCL:" + job.cl;
     hdr.add_line(pg);
     const int level = job.con == 1 ? 0 : 6;
-    if (job.con == 0) {
-        for (const auto &l : hdr.lines) { fwrite(l.data(), 1, l.size(), stdout); fputc('\n', stdout); }
-    } else {
-        std::string text, o("BAM\1", 4);
-        for (const auto &l : hdr.lines) { text += l; text += '\n'; }
-        samio::put_u32(o, (uint32_t)text.size());
-        o += text;
-        samio::put_u32(o, (uint32_t)hdr.names.size());
-        for (size_t r = 0; r < hdr.names.size(); ++r) {
-            samio::put_u32(o, (uint32_t)hdr.names[r].size() + 1);
-            o += hdr.names[r]; o.push_back('\0');
-            samio::put_u32(o, (uint32_t)hdr.lens[r]);
-        }
-        write_blocks(stdout, reinterpret_cast<const uint8_t *>(o.data()), o.size(), level, threads);
-    }
+    write_header(hdr, job.con, threads);
 
     // ---- reference (anno.d:23) ----
     std::map<std::string, std::string> fasta;
@@ -551,10 +630,7 @@ inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, cons
         cur ^= 1;
     }
     for (auto &s : slot) if (s.in_flight && rc_all == 0 && !emit(s)) rc_all = 1;
-    if (job.con != 0 && rc_all == 0) {
-        static const uint8_t eof[28] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-        fwrite(eof, 1, sizeof(eof), stdout);
-    }
+    if (job.con != 0 && rc_all == 0) write_eof_marker();
     fflush(stdout);
     fprintf(stderr, "[fade-b200 annotate] %lld records, %lld soft-clipped, %lld with artifact tags\n", n_total, n_sc, n_art);
     if (getenv("FADE_TIMING"))

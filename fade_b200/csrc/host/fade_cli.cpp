@@ -662,15 +662,26 @@ int cmd_extract(int argc, char **argv, const std::string &cl)
 // format conversion only: every header line and record, unchanged (SAM <-> BAM)
 int cmd_view(int argc, char **argv)
 {
-    int con = 0;
+    int con = 0, threads = 0;
+    bool bulk = false;
     std::string path;
     for (int i = 2; i < argc; ++i) {
         const std::string a = argv[i];
         if (output_flag(a, con)) {}
+        else if (a == "--bulk") bulk = true;      // through the parallel readers / writers of the annotate loop
+        else if ((a == "-t" || a == "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
         else path = a;
     }
     if (path.empty()) return usage();
     if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    if (bulk) {
+        FILE *f = path == "-" ? stdin : fopen(path.c_str(), "rb");
+        if (!f) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
+        std::string pre(2, '\0');
+        pre.resize(fread(&pre[0], 1, 2, f));
+        const bool is_bam = pre.size() == 2 && (uint8_t)pre[0] == 0x1f && (uint8_t)pre[1] == 0x8b;
+        return bamfast::copy_records(f, pre, is_bam, con, threads > 0 ? threads : omp_get_max_threads());
+    }
     open_output(con);
     samio::LineSource in;
     if (!in.open(path)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }

@@ -119,3 +119,33 @@ def test_consumers_read_and_write_bam(tmp_path):
         assert body(to_bam) == body(ref)
         to_ubam = bamcodec.decode(cli(args + ["-u"], path=bam_in))
         assert body(to_ubam) == body(ref)
+
+
+def test_parallel_readers_and_writers_of_the_annotate_loop():
+    """`view --bulk` pushes every record through bamfast.hpp's I/O (parallel BGZF inflate / deflate, SAM text cut
+    into lines and converted side by side) -- the part of `annotate` that needs no GPU.  Inputs large enough to
+    cross the 8 MiB text refills and the 512-block inflate groups; results equal the single-threaded samio path."""
+    lines = rich_lines(200000, seed=13)
+    sam = ("\n".join(lines) + "\n").encode()
+    bam = cli(["view", "-b"], sam)
+    payload = bgzf_payload(bam)
+    assert len(sam) > 48 << 20 and len(payload) > 520 * 0xff00                  # several text refills, > 512 BGZF blocks
+    assert bamcodec.decode(bam[:0] + bam)[:2000] == lines[:2000]
+    for src in (sam, bam):
+        for t in ("1", "5"):
+            assert cli(["view", "--bulk", "-t", t], src) == sam
+            assert bgzf_payload(cli(["view", "--bulk", "-b", "-t", t], src)) == payload
+        assert bgzf_payload(cli(["view", "--bulk", "-u"], src)) == payload
+    # CRLF line ends and blank lines in SAM text
+    crlf = ("\r\n".join(lines[:300]) + "\r\n\r\n").encode()
+    assert cli(["view", "--bulk"], crlf).decode().splitlines() == lines[:300]
+    # loud failures
+    broken = bytearray(bam)
+    broken[len(broken) // 3] ^= 0x41
+    p = subprocess.run([BIN, "view", "--bulk", "-"], input=bytes(broken), capture_output=True)
+    assert p.returncode != 0 and b"damaged" in p.stderr
+    p = subprocess.run([BIN, "view", "--bulk", "-"], input=bam[: len(bam) // 2], capture_output=True)
+    assert p.returncode != 0
+    bad_sam = ("\n".join(lines[:50] + ["name\t0\tchrA"] + lines[50:60]) + "\n").encode()
+    p = subprocess.run([BIN, "view", "--bulk", "-b", "-"], input=bad_sam, capture_output=True)
+    assert p.returncode != 0 and b"malformed" in p.stderr
