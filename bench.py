@@ -317,7 +317,7 @@ def main():
             + int(rec["score"].sum()) + len(ws)
 
     def e2e_step():
-        """host buffers -> C ABI -> host results, double-buffered; wall clock around the whole step."""
+        """host buffers -> C ABI -> host results, several chunks in flight; wall clock around the whole step."""
         t0 = time.perf_counter()
         pending = None
         acc = 0
@@ -333,12 +333,11 @@ def main():
                 acc += consume(batches[i])
                 note_copies(batches[i])
             return time.perf_counter() - t0, acc
+        # --e2e-path arrays: pageable numpy arrays -> fadegpu_submit_inputs, two batches alternating
         for i, (a, e) in enumerate(bounds):
-            if True:
-                b = batches[i & 1]
-                # host buffers (pageable numpy arrays) -> C ABI; seq_off holds absolute offsets into seq4
-                b.submit_arrays(e - a, rd.seq4, rd.seq_off[a:], rd.l_qseq[a:], rd.tid[a:], rd.pos[a:],
-                                rd.aligned_len[a:], rd.clip_left[a:], rd.clip_right[a:])
+            b = batches[i & 1]
+            b.submit_arrays(e - a, rd.seq4, rd.seq_off[a:], rd.l_qseq[a:], rd.tid[a:], rd.pos[a:],
+                            rd.aligned_len[a:], rd.clip_left[a:], rd.clip_right[a:])   # seq_off: absolute offsets
             if pending is not None:
                 pending.wait()
                 acc += consume(pending)
