@@ -126,6 +126,7 @@ int usage()
             "fade-b200 extract <annotated SAM or ->       emits the artifacts in their re-mapped state\n"
             "fade-b200 annotate: marks artifact reads in bam tags (B200 implementation of `fade annotate`)\n"
             "fade-b200 view <SAM/BAM or ->                 copies the records (format conversion)\n"
+            "fade-b200 sort -n <SAM/BAM or ->              name-sorted copy (for `out` without -c)\n"
             "every command: -b / --bam writes BAM, -u / --ubam uncompressed BAM, default SAM text; input may be SAM or BAM\n"
             "usage: fade-b200 annotate [options] <SAM/BAM or -> <FASTA>\n"
             "  -t, --threads N      host threads (default: all cores)\n"
@@ -659,6 +660,51 @@ int cmd_extract(int argc, char **argv, const std::string &cl)
     return 0;
 }
 
+// `fade-b200 sort -n`: name-sorted copy of the input (what config 5 of BASELINE.json uses `samtools sort -n`
+// for, between annotate and out).  Order: the natural order `fade out` itself tests for (filter.d:127-165),
+// then first-of-pair before second-of-pair (FLAG & 0xC0), then input order.  In memory.
+int cmd_sort(int argc, char **argv)
+{
+    int con = 0;
+    bool by_name = false;
+    std::string path;
+    for (int i = 2; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (output_flag(a, con)) {}
+        else if (a == "-n") by_name = true;
+        else if (a == "-t" || a == "--threads") ++i;
+        else path = a;
+    }
+    if (path.empty() || !by_name) { fprintf(stderr, "usage: fade-b200 sort -n [-b|-u] <SAM/BAM or ->   (only name order is implemented)\n"); return 1; }
+    if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    open_output(con);
+    Sam sam;
+    if (!sam.open(path)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
+    std::vector<SamRec> recs;
+    SamRec r;
+    int rc;
+    while ((rc = sam.next(r)) == 1) recs.push_back(r);
+    if (rc < 0) { fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str()); return 1; }
+    std::stable_sort(recs.begin(), recs.end(), [](const SamRec &a, const SamRec &b) {
+        const int c = natural_compare(a.f[0], b.f[0]);
+        if (c) return c < 0;
+        return (atoi(a.f[1].c_str()) & 0xc0) < (atoi(b.f[1].c_str()) & 0xc0);
+    });
+    bool have_hd = false;
+    for (auto &h : sam.header) {   // @HD SO:queryname, as samtools sort -n writes it
+        if (h.compare(0, 3, "@HD") != 0) continue;
+        have_hd = true;
+        const size_t a = h.find("\tSO:");
+        if (a == std::string::npos) h += "\tSO:queryname";
+        else { const size_t e = h.find('\t', a + 1); h.replace(a, (e == std::string::npos ? h.size() : e) - a, "\tSO:queryname"); }
+    }
+    if (!have_hd) out_line("@HD\tVN:1.6\tSO:queryname");
+    for (auto &h : sam.header) out_line(h);
+    for (auto &x : recs) if (!out_line(x.line())) return 1;
+    g_out->close();
+    return 0;
+}
+
 // format conversion only: every header line and record, unchanged (SAM <-> BAM)
 int cmd_view(int argc, char **argv)
 {
@@ -706,6 +752,7 @@ int main(int argc, char **argv)
     if (strcmp(argv[1], "out") == 0) return cmd_out(argc, argv, cl);
     if (strcmp(argv[1], "extract") == 0) return cmd_extract(argc, argv, cl);
     if (strcmp(argv[1], "view") == 0) return cmd_view(argc, argv);
+    if (strcmp(argv[1], "sort") == 0) return cmd_sort(argc, argv);
     usage();
     return 1;
 }

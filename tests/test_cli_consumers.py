@@ -142,3 +142,35 @@ def test_consumers_stream_short_empty_and_malformed_inputs(tmp_path):
     for args in (["out"], ["out", "-c"], ["extract"]):
         p = subprocess.run([BIN, *args, str(bad)], capture_output=True, text=True)
         assert p.returncode == 1 and "malformed" in p.stderr
+
+
+def test_sort_by_name_feeds_out(tmp_path):
+    """`fade-b200 sort -n` (the `samtools sort -n` step of BASELINE configs[4]): a shuffled annotated file comes
+    back in the natural name order `fade out` tests for, mates adjacent (first of pair first), and `out` then
+    ejects whole read groups exactly as on the originally sorted file."""
+    path, contigs = annotated_sam(tmp_path, n=2000, name_sorted=False)
+    (tmp_path / "s").mkdir()
+    sorted_path, _ = annotated_sam(tmp_path / "s", n=2000, name_sorted=True)
+    p = subprocess.run([BIN, "sort", "-n", str(path)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    out_lines = p.stdout.splitlines()
+    head = [ln for ln in out_lines if ln.startswith("@")]
+    body = [ln for ln in out_lines if not ln.startswith("@")]
+    assert head[0].startswith("@HD") and "SO:queryname" in head[0]
+    assert sorted(body) == sorted(ln for ln in open(path).read().splitlines() if not ln.startswith("@"))
+    names = [ln.split("\t")[0] for ln in body]
+    assert all(cons.natural_compare(a, b) <= 0 for a, b in zip(names, names[1:]))
+    flags = [int(ln.split("\t")[1]) & 0xc0 for ln in body]
+    assert all(fa <= fb for (na, fa), (nb, fb) in zip(zip(names, flags), zip(names[1:], flags[1:])) if na == nb)
+    srt = tmp_path / "sorted.sam"
+    srt.write_text(p.stdout)
+    _, got, err = run_cli(["out"], srt)
+    _, exp, _ = run_cli(["out"], sorted_path)
+    assert "looks name-sorted" in err and sorted(got) == sorted(exp) and 0 < len(got) < 2000
+    # BAM in / BAM out, and a header without @HD
+    import bamcodec
+    nohd = [ln for ln in open(path).read().splitlines() if not ln.startswith("@HD")]
+    p2 = subprocess.run([BIN, "sort", "-n", "-b", "-"], input=bamcodec.encode(nohd), capture_output=True)
+    assert p2.returncode == 0
+    dec = bamcodec.decode(p2.stdout)
+    assert dec[0] == "@HD\tVN:1.6\tSO:queryname" and [ln for ln in dec if not ln.startswith("@")] == body
