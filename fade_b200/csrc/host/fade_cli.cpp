@@ -100,8 +100,48 @@ std::vector<std::string> split_tab(const std::string &s)
     return f;
 }
 
+// <path>.fai (samtools faidx: name, length, offset, linebases, linewidth): every contig is read with one
+// fread and its line ends squeezed out in place, instead of line by line
+bool read_fasta_indexed(const std::string &path, std::map<std::string, std::string> &seqs)
+{
+    std::ifstream fai(path + ".fai");
+    if (!fai) return false;
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::string line;
+    bool ok = true;
+    while (ok && std::getline(fai, line)) {
+        const auto c = split_tab(line);
+        if (c.size() < 5) { ok = false; break; }
+        const long long len = atoll(c[1].c_str()), off = atoll(c[2].c_str()), lb = atoll(c[3].c_str()), lw = atoll(c[4].c_str());
+        if (len < 0 || off < 0 || lb <= 0 || lw < lb) { ok = false; break; }
+        const long long full = len / lb, rest = len % lb;
+        const size_t span = (size_t)(full * lw + rest);
+        std::string &dst = seqs[c[0]];
+        dst.resize(span);
+        if (fseeko(f, (off_t)off, SEEK_SET) != 0) { ok = false; break; }
+        const size_t got = fread(&dst[0], 1, span, f);
+        // bytes up to the last base (the file may end without a line end)
+        const size_t min_bytes = rest > 0 ? span : (full > 0 ? (size_t)((full - 1) * lw + lb) : 0);
+        if (got < min_bytes) { ok = false; break; }
+        size_t w = 0;
+        for (size_t r = 0; r < got;) {   // keep linebases, skip the line end
+            const size_t k = std::min<size_t>((size_t)lb, std::min<size_t>(got - r, (size_t)len - w));
+            memmove(&dst[w], &dst[r], k);
+            w += k; r += (size_t)lw;
+            if (w == (size_t)len) break;
+        }
+        if (w != (size_t)len) { ok = false; break; }
+        dst.resize((size_t)len);
+    }
+    fclose(f);
+    if (!ok) seqs.clear();
+    return ok;
+}
+
 bool read_fasta(const std::string &path, std::map<std::string, std::string> &seqs)
 {
+    if (read_fasta_indexed(path, seqs)) return true;   // no (usable) .fai: read the text
     std::ifstream in(path);
     if (!in) return false;
     std::string line, name;
@@ -705,6 +745,21 @@ int cmd_sort(int argc, char **argv)
     return 0;
 }
 
+// `fade-b200 fasta-digest <FASTA>`: name, length and FNV-1a hash of every contig as the loader sees it
+// (with or without a .fai); a check of the loader that needs no GPU
+int cmd_fasta_digest(int argc, char **argv)
+{
+    if (argc < 3) return usage();
+    std::map<std::string, std::string> fasta;
+    if (!read_fasta(argv[2], fasta)) { fprintf(stderr, "fade-b200: cannot read %s\n", argv[2]); return 1; }
+    for (const auto &kv : fasta) {
+        uint64_t h = 1469598103934665603ull;
+        for (unsigned char ch : kv.second) { h ^= ch; h *= 1099511628211ull; }
+        printf("%s\t%zu\t%016llx\n", kv.first.c_str(), kv.second.size(), (unsigned long long)h);
+    }
+    return 0;
+}
+
 // format conversion only: every header line and record, unchanged (SAM <-> BAM)
 int cmd_view(int argc, char **argv)
 {
@@ -753,6 +808,7 @@ int main(int argc, char **argv)
     if (strcmp(argv[1], "extract") == 0) return cmd_extract(argc, argv, cl);
     if (strcmp(argv[1], "view") == 0) return cmd_view(argc, argv);
     if (strcmp(argv[1], "sort") == 0) return cmd_sort(argc, argv);
+    if (strcmp(argv[1], "fasta-digest") == 0) return cmd_fasta_digest(argc, argv);
     usage();
     return 1;
 }

@@ -219,3 +219,37 @@ def test_codec_fuzz_against_independent_codec():
         assert cli(["view", "--bulk"], theirs).decode().splitlines() == lines
 
     run()
+
+
+def test_fasta_loader_with_and_without_fai(tmp_path):
+    """The reference (anno.d:23 IndexedFastaFile) is read whole: through <fasta>.fai when there is one (one read
+    per contig), line by line otherwise.  Same contigs either way: LF / CRLF, last line with and without a line
+    end, contig lengths around the line width."""
+    import random
+    rng = random.Random(3)
+    for nl, final_nl in (("\n", True), ("\n", False), ("\r\n", True)):
+        contigs = [(f"c{k} some description", "".join(rng.choice("ACGTNacgtn") for _ in range(n)))
+                   for k, n in enumerate((1, 59, 60, 61, 120, 1234, 60 * 50))]
+        text, fai, off = "", [], 0
+        for name, seq in contigs:
+            head = f">{name}{nl}"
+            off += len(head)
+            body = nl.join(seq[a:a + 60] for a in range(0, len(seq), 60)) + nl
+            fai.append(f"{name.split()[0]}\t{len(seq)}\t{off}\t60\t{60 + len(nl)}")
+            text += head + body
+            off += len(body)
+        if not final_nl:
+            text = text[: -len(nl)]
+        fa = tmp_path / f"r{len(nl)}{int(final_nl)}.fa"
+        fa.write_bytes(text.encode())
+        plain = subprocess.run([BIN, "fasta-digest", str(fa)], capture_output=True, text=True)
+        (tmp_path / (fa.name + ".fai")).write_text("\n".join(fai) + "\n")
+        indexed = subprocess.run([BIN, "fasta-digest", str(fa)], capture_output=True, text=True)
+        assert plain.returncode == 0 and indexed.returncode == 0
+        assert plain.stdout == indexed.stdout
+        rows = [ln.split("\t") for ln in indexed.stdout.splitlines()]
+        assert {r[0]: int(r[1]) for r in rows} == {n.split()[0]: len(s) for n, s in contigs}
+    # a .fai that does not match the file is refused and the text is read instead
+    (tmp_path / (fa.name + ".fai")).write_text("c0\t5\t999999\t60\t61\n")
+    again = subprocess.run([BIN, "fasta-digest", str(fa)], capture_output=True, text=True)
+    assert again.stdout == plain.stdout
