@@ -253,3 +253,18 @@ def test_fasta_loader_with_and_without_fai(tmp_path):
     (tmp_path / (fa.name + ".fai")).write_text("c0\t5\t999999\t60\t61\n")
     again = subprocess.run([BIN, "fasta-digest", str(fa)], capture_output=True, text=True)
     assert again.stdout == plain.stdout
+
+
+def test_golden_bam_bytes():
+    """tests/golden/tiny_bam.json (written by tests/golden/make_bam_golden.py): both codecs still produce the
+    committed uncompressed BAM stream from the committed SAM lines, and decode it to the committed text
+    (lower-case bases come back upper-case, as through htslib)."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_bam.json")))
+    sam = ("\n".join(g["sam"]) + "\n").encode()
+    want = bytes.fromhex(g["bam_payload_hex"])
+    assert bgzf_payload(bamcodec.encode(g["sam"], 0)) == want
+    assert bgzf_payload(cli(["view", "-u"], sam)) == want
+    assert bgzf_payload(cli(["view", "--bulk", "-b"], sam)) == want
+    assert cli(["view"], bamcodec.bgzf_blocks(want)).decode().splitlines() == g["sam_after_round_trip"]
+    assert g["sam_after_round_trip"][-1].split("\t")[9] == "ACG" and g["sam"][-1].split("\t")[9] == "acg"
