@@ -67,10 +67,17 @@ class Context:
         if rc:
             raise FadeGpuError(rc, lib().fadegpu_last_error(self._h).decode())
 
-    def load_reference(self, names: list[str], seqs: list[bytes]):
+    def load_reference(self, names: list[str], seqs: list):
+        """seqs: ASCII contigs as bytes or as C-contiguous uint8 numpy arrays (passed without a copy)."""
         n = len(seqs)
         cn = (C.c_char_p * n)(*[s.encode() for s in names])
-        cs = (C.c_char_p * n)(*seqs)
+        cs = (C.c_char_p * n)()
+        for k, s in enumerate(seqs):
+            if isinstance(s, np.ndarray):
+                assert s.dtype == np.uint8 and s.flags["C_CONTIGUOUS"]
+                C.cast(cs, C.POINTER(C.c_void_p))[k] = s.ctypes.data
+            else:
+                cs[k] = s
         ln = (C.c_int64 * n)(*[len(s) for s in seqs])
         self._check(lib().fadegpu_load_reference(self._h, n, cn, ln, cs))
         self.contig_names = list(names)

@@ -233,21 +233,26 @@ def align_batch(seq4, seq_off, l_qseq, tid, pos, aligned_len, clip_left, clip_ri
     aligned_len = np.ascontiguousarray(aligned_len, dtype=np.int32)
     clip_left = np.ascontiguousarray(clip_left, dtype=np.int32)
     clip_right = np.ascontiguousarray(clip_right, dtype=np.int32)
-    names = (C.c_char_p * len(contigs))(*contigs)
+    names = (C.c_char_p * len(contigs))()
+    for k_, c_ in enumerate(contigs):      # bytes, or uint8 numpy arrays passed without a copy
+        if isinstance(c_, np.ndarray):
+            assert c_.dtype == np.uint8 and c_.flags["C_CONTIGUOUS"]
+            C.cast(names, C.POINTER(C.c_void_p))[k_] = c_.ctypes.data
+        else:
+            names[k_] = c_
     clen = np.array([len(c) for c in contigs], dtype=np.int64)
-    res = (ReadResult * n)()
-    ops = np.zeros((n, ops_cap), dtype=np.uint32)
-    fn = lib().fo_align_batch_simd if simd else lib().fo_align_batch
-    rc = fn(n, seq4.ctypes.data, seq_off.ctypes.data, l_qseq.ctypes.data, tid.ctypes.data,
-                              pos.ctypes.data, aligned_len.ctypes.data, clip_left.ctypes.data,
-                              clip_right.ctypes.data, len(contigs), names, clen.ctypes.data, C.byref(p),
-                              C.addressof(res), ops.ctypes.data, ops_cap, n_threads)
-    if rc:
-        raise ValueError("fo_align_batch failed")
     dt = np.dtype([("aligned", "<i4"), ("art_left", "<i4"), ("art_right", "<i4"), ("_pad0", "<i4"),
                    ("win_start", "<i8"), ("tlen", "<i4"), ("score", "<i4"), ("end_query", "<i4"),
                    ("end_ref", "<i4"), ("beg_query", "<i4"), ("beg_ref", "<i4"), ("n_ops", "<i4"),
                    ("ref_span", "<i4")])
     assert dt.itemsize == C.sizeof(ReadResult), (dt.itemsize, C.sizeof(ReadResult))
-    arr = np.frombuffer(bytes(res), dtype=dt).copy() if n else np.zeros(0, dtype=dt)
+    arr = np.zeros(n, dtype=dt)
+    ops = np.zeros((n, ops_cap), dtype=np.uint32)
+    fn = lib().fo_align_batch_simd if simd else lib().fo_align_batch
+    rc = fn(n, seq4.ctypes.data, seq_off.ctypes.data, l_qseq.ctypes.data, tid.ctypes.data,
+                              pos.ctypes.data, aligned_len.ctypes.data, clip_left.ctypes.data,
+                              clip_right.ctypes.data, len(contigs), names, clen.ctypes.data, C.byref(p),
+                              arr.ctypes.data, ops.ctypes.data, ops_cap, n_threads)
+    if rc:
+        raise ValueError("fo_align_batch failed")
     return arr, ops

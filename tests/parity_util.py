@@ -65,3 +65,50 @@ def compare(batch, rd, contigs, params, max_report=5):
                     f"{orc.cigar_string(gops[b][:k[b]])} oracle {orc.cigar_string(oops[b][:k[b]])}")
     assert not errs, "\n".join(errs)
     return int(al.sum())
+
+
+def compare_compact(batch, n, res, ops, max_report=5):
+    """Same comparison on the compact results (fadegpu_get_results, F_NO_SCATTER contexts): every
+    per-read output of `batch` against oracle results `res` / `ops` for reads [0, n).  Vectorised,
+    so it can run over millions of reads.  Returns the number of aligned reads."""
+    rec, ws, ridx = batch.results()
+    flags = batch.flags[:n]
+    errs = []
+    al = res["aligned"] == 1
+    g_al = (flags & 1) == 1
+    if not np.array_equal(g_al, al):
+        bad = np.where(g_al != al)[0]
+        errs.append(f"aligned flag differs at reads {bad[:max_report].tolist()} ({len(bad)} total)")
+        assert not errs, "\n".join(errs)
+    idx = np.where(al)[0]
+    k = ridx[idx]
+    assert (k >= 0).all() and len(rec) == len(idx) and len(np.unique(k)) == len(k), "result index is not a bijection"
+    r = rec[k]
+    o = res[idx]
+    assert np.array_equal(r["read"], idx.astype(np.int32)), "result record points at another read"
+    for f in FIELDS:
+        bad = np.where(r[f] != o[f])[0]
+        if len(bad):
+            errs.append(f"{f} differs at reads {idx[bad[:max_report]].tolist()} ({len(bad)} total): "
+                        f"gpu {r[f][bad[:max_report]].tolist()} oracle {o[f][bad[:max_report]].tolist()}")
+    bad = np.where(ws[k] != o["win_start"])[0]
+    if len(bad):
+        errs.append(f"win_start differs at {idx[bad[:max_report]].tolist()}")
+    gl, gr = ((flags >> 1) & 1).astype(np.int32), ((flags >> 2) & 1).astype(np.int32)
+    for name, g, oo in (("art_left", gl, res["art_left"]), ("art_right", gr, res["art_right"])):
+        bad = np.where(g != oo)[0]
+        if len(bad):
+            errs.append(f"{name} differs at reads {bad[:max_report].tolist()} ({len(bad)} total)")
+    if not np.array_equal((r["flags"] >> 1) & 3, (flags[idx] >> 1) & 3):
+        errs.append("per-read flag byte and result record disagree")
+    kk = np.minimum(o["n_ops"], MAX_OPS)
+    mask = np.arange(MAX_OPS)[None, :] < kk[:, None]
+    gops = np.where(mask, r["ops"], 0)
+    oops = np.where(mask, ops[idx][:, :MAX_OPS], 0)
+    bad = np.where((gops != oops).any(axis=1))[0]
+    if len(bad):
+        b = int(bad[0])
+        errs.append(f"CIGAR differs at reads {idx[bad[:max_report]].tolist()} ({len(bad)} total): gpu "
+                    f"{orc.cigar_string(gops[b][:kk[b]])} oracle {orc.cigar_string(oops[b][:kk[b]])}")
+    assert not errs, "\n".join(errs)
+    return int(al.sum())

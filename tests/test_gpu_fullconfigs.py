@@ -1,0 +1,90 @@
+"""BASELINE.json configs at their FULL sizes, bit-exact for every read against the CPU oracle
+(oracle/fade_oracle_simd.c, the AVX2 port validated against the scalar oracle):
+
+  C2  configs[1]  10 M 2x150 reads vs a 100 Mbp chromosome, defaults
+  C3  configs[2]  3.1 Gbp / 24 contigs resident in HBM (global offsets > 2^31); 2 M of the 100 M reads
+                  here (the full 100 M run is bench.py --workload c3, profiles/), all 24 contigs covered
+  C4  configs[3]  2 M 2x250 reads, --window-size 1000, clip law U{1..40}
+
+Results compared: aligned flag, score, begin / end cell, window start, op count, every CIGAR op,
+art_left / art_right of every read (source/analysis.d:67-80,98-104)."""
+import numpy as np
+import pytest
+
+from fade_b200 import Context, api, default_params, sim
+from oracle import oracle as orc
+from parity_util import compare_compact, oracle_params
+
+pytestmark = pytest.mark.gpu
+
+CHUNK = 1_000_000
+
+
+def _run_chunks(ctx, rd, contigs, read_len, chunk=CHUNK):
+    """the view path (fadegpu_submit: binning on the device, bases pulled by the GPU), chunk by chunk"""
+    stride = (read_len + 1) // 2
+    prm = oracle_params(ctx.params)
+    b = ctx.alloc_batch(min(chunk, rd.n), min(chunk, rd.n) * stride)
+    tot_al = tot_art = 0
+    for a in range(0, rd.n, chunk):
+        e = min(rd.n, a + chunk)
+        m = e - a
+        b.fill(rd.seq4[a * stride: e * stride], rd.seq_off[a: e + 1] - rd.seq_off[a], rd.l_qseq[a:e], rd.tid[a:e],
+               rd.pos[a:e], rd.aligned_len[a:e], rd.clip_left[a:e], rd.clip_right[a:e]).run()
+        res, ops = orc.align_batch(b.seq4[: m * stride], b.seq_off[: m + 1], b.l_qseq[:m], b.tid[:m], b.pos[:m],
+                                   b.aligned_len[:m], b.clip_left[:m], b.clip_right[:m], contigs, params=prm,
+                                   ops_cap=api.MAX_OPS, simd=True)
+        tot_al += compare_compact(b, m, res, ops)
+        tot_art += int(((b.flags[:m] & 6) != 0).sum())
+    b.close()
+    return tot_al, tot_art
+
+
+def test_c2_full_10M_reads_bit_exact():
+    ref = sim.make_contig(1002, 0, 100_000_000, 0, 0, 0.0)
+    cfg = sim.default_cfg(read_seed=2002)
+    rd = sim.make_reads(cfg, 0, 10_000_000, [ref], with_records=False)
+    with Context(0, default_params(flags=api.F_NO_SCATTER)) as ctx:
+        ctx.load_reference(["chrS"], [ref])
+        n_al, n_art = _run_chunks(ctx, rd, [ref], cfg.read_len)
+    assert 1_600_000 < n_al < 1_700_000 and 900_000 < n_art < 1_100_000
+
+
+def test_c4_full_2M_reads_bit_exact():
+    ref = sim.make_contig(1002, 0, 100_000_000, 0, 0, 0.0)
+    cfg = sim.default_cfg(read_seed=2004, read_len=250, window=1000, frag_mean=600, frag_sd=80, short_clip_law=1)
+    rd = sim.make_reads(cfg, 0, 2_000_000, [ref], with_records=False)
+    with Context(0, default_params(window_size=1000, min_length=5, flags=api.F_NO_SCATTER)) as ctx:
+        ctx.load_reference(["chrS"], [ref])
+        n_al, n_art = _run_chunks(ctx, rd, [ref], cfg.read_len)
+    assert n_al > 200_000 and n_art > 50_000
+
+
+# hg38 chr1-22,X,Y lengths, scaled to sum 3.1 Gbp
+HG38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422,
+        135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167,
+        46709983, 50818468, 156040895, 57227415]
+
+
+def c3_contigs():
+    scale = 3.1e9 / sum(HG38)
+    lens = [int(x * scale) for x in HG38]
+    names = [f"chr{i + 1}" for i in range(22)] + ["chrX", "chrY"]
+    return names, [sim.make_contig(1003, i, n, 1_000_000, 10_000, 0.0) for i, n in enumerate(lens)]
+
+
+def test_c3_hg38_sized_reference_2M_reads_bit_exact():
+    import psutil
+    if psutil.virtual_memory().available < 14 * (1 << 30):
+        pytest.skip("needs 14 GB of free host RAM for the 3.1 Gbp synthetic reference")
+    names, contigs = c3_contigs()
+    cfg = sim.default_cfg(read_seed=2003)
+    rd = sim.make_reads(cfg, 0, 2_000_000, contigs, with_records=False)
+    assert len(np.unique(rd.tid)) == 24
+    with Context(0, default_params(flags=api.F_NO_SCATTER)) as ctx:
+        ctx.load_reference(names, contigs)
+        n_contigs, total, dev_bytes = ctx.reference_info()
+        assert n_contigs == 24 and total == sum(len(c) for c in contigs) and dev_bytes < 0.52 * total
+        n_al, n_art = _run_chunks(ctx, rd, contigs, cfg.read_len)
+    late = rd.tid >= 20            # contigs whose global base offsets lie beyond 2^31
+    assert late.sum() > 50_000 and n_al > 300_000 and n_art > 150_000
