@@ -41,7 +41,7 @@ static inline int fo_map(unsigned char c)
 
 static inline int fo_sub(const fo_params *p, int a, int b)
 {
-    if (a == 5 || b == 5) return 0;
+    if (a == 5 || b == 5) return (p->switches & FO_SW_WILD_MISMATCH) ? p->mismatch : 0;
     return a == b ? p->match : p->mismatch;
 }
 
@@ -158,23 +158,26 @@ int fo_sw_trace(const char *q, int qlen, const char *t, int tlen, const fo_param
                 if (sw & FO_SW_EQ_BY_MATRIX) eq = fo_sub(p, qi[i], fo_map((unsigned char)t[j])) > 0;
                 else eq = fo_upper((unsigned char)q[i]) == fo_upper((unsigned char)t[j]);
                 PUSH(eq ? FO_EQ : FO_X);
-                ++ref_span;
                 --i; --j;
             } else if (src == T_F) state = 1;
             else state = 2;
         } else if (state == 1) {
-            PUSH(FO_I);
+            PUSH((sw & FO_SW_SWAP_ID) ? FO_D : FO_I);
             --i;
             if (tb & T_FOPEN) state = 0;
         } else {
-            PUSH(FO_D);
-            ++ref_span;
+            PUSH((sw & FO_SW_SWAP_ID) ? FO_I : FO_D);
             --j;
             if (tb & T_EOPEN) state = 0;
         }
     }
 #undef PUSH
     const int beg_query = i + 1, beg_ref = j + 1;
+    /* res.cigar.alignedLength as dhtslib computes it: by op letter (= X D), source/analysis.d:110-113 */
+    for (int k = 0; k < nrev; ++k) {
+        const uint32_t op = rev[k] & 0xf;
+        if (op == FO_EQ || op == FO_X || op == FO_D) ref_span += (int)(rev[k] >> 4);
+    }
 
     /* P5: dparasail result wrapper adds S ops for the unaligned query ends (U1) */
     int n = 0;

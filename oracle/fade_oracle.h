@@ -33,8 +33,13 @@ enum {
     FO_SW_END_LAST_COL    = 1 << 1, /* U4: pick the LAST column / row among maxima            */
     FO_SW_E_BEFORE_F      = 1 << 2, /* U5: trace priority DIAG > E(D) > F(I)                  */
     FO_SW_GAP_TIE_OPEN    = 1 << 3, /* U5: gap open wins ties against gap extend              */
-    FO_SW_EQ_BY_MATRIX    = 1 << 4  /* U7: '=' iff matrix score > 0 (instead of byte equality)*/
+    FO_SW_EQ_BY_MATRIX    = 1 << 4, /* U7: '=' iff matrix score > 0 (instead of byte equality)*/
+    FO_SW_SWAP_ID         = 1 << 5, /* U3: the gap along the target is written 'I', along the query 'D' */
+    FO_SW_WILD_MISMATCH   = 1 << 6  /* P1: a letter outside "ACTGN" scores `mismatch` instead of 0    */
 };
+/* Also assumed, not switchable (they would change the shape of the outputs, not a tie-break):
+ * U2 res.position == parasail beg_ref (0-based, window relative); U6 Cigar.alignedLength counts the
+ * reference-consuming ops; ZERO has priority over every other source (U8 below). */
 /* U8 (not switchable): a cell whose H is 0 always ends the traceback (ZERO has priority), even
  * when F or E is exactly 0 there.  parasail's lazy-F pass may label such a cell differently
  * depending on the SIMD lane layout; this cannot be modelled width-independently. */

@@ -16,6 +16,9 @@ _SO = os.path.join(_HERE, "libfadeoracle.so")
 
 OPS = "MIDNSHP=XB"
 FO_S, FO_EQ, FO_X, FO_I, FO_D = 4, 7, 8, 1, 2
+# fo_params.switches (fade_oracle.h)
+FO_SW_NO_SOFTCLIP_PAD, FO_SW_END_LAST_COL, FO_SW_E_BEFORE_F, FO_SW_GAP_TIE_OPEN, FO_SW_EQ_BY_MATRIX = 1, 2, 4, 8, 16
+FO_SW_SWAP_ID, FO_SW_WILD_MISMATCH = 32, 64
 
 
 class Params(C.Structure):
@@ -47,13 +50,21 @@ class Tags(C.Structure):
                 ("ar", C.c_void_p), ("ab", C.c_void_p)]
 
 
+class FuzzReport(C.Structure):
+    _fields_ = [("n_pairs", C.c_int64), ("n_diverged", C.c_int64), ("n_gapped", C.c_int64),
+                ("n_multi_max", C.c_int64), ("n_zero_ef", C.c_int64), ("first_div", C.c_int64),
+                ("first_qlen", C.c_int32), ("first_tlen", C.c_int32), ("first_q", C.c_char * 512),
+                ("first_t", C.c_char * 2048), ("explained_by", C.c_uint32)]
+
+
 _lib = None
 
 
 def build(force: bool = False) -> str:
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(
             os.path.join(_HERE, "fade_oracle.c")) or os.path.getmtime(_SO) < os.path.getmtime(
-            os.path.join(_HERE, "fade_oracle_simd.c")):
+            os.path.join(_HERE, "fade_oracle_simd.c")) or os.path.getmtime(_SO) < os.path.getmtime(
+            os.path.join(_HERE, "parasail_striped.c")):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
@@ -85,6 +96,12 @@ def lib():
         L.fo_align_batch.restype = C.c_int
         L.fo_align_batch_simd.argtypes = L.fo_align_batch.argtypes
         L.fo_align_batch_simd.restype = C.c_int
+        L.ps_sw_trace.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(Params), C.c_int,
+                                  C.POINTER(SwResult), C.POINTER(C.c_uint32), C.c_int]
+        L.ps_sw_trace.restype = C.c_int
+        L.ps_fuzz.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.c_int,
+                              C.POINTER(FuzzReport)]
+        L.ps_fuzz.restype = C.c_int
         _lib = L
     return _lib
 
@@ -142,6 +159,46 @@ def sw_trace(q: bytes | str, t: bytes | str, params: Params | None = None, ops_c
         raise ValueError("fo_sw_trace failed")
     return Sw(r.score, r.end_query, r.end_ref, r.beg_query, r.beg_ref, r.n_ops, r.ref_span,
               [int(ops[k]) for k in range(min(r.n_ops, ops_cap))])
+
+
+def sw_trace_striped(q: bytes | str, t: bytes | str, lanes: int = 16, params: Params | None = None,
+                     ops_cap: int = 4096) -> Sw:
+    """The same contract through the structural restatement of parasail's striped kernel
+    (oracle/parasail_striped.c): lanes = 8 for the 128-bit builds, 16 for AVX2."""
+    if isinstance(q, str):
+        q = q.encode()
+    if isinstance(t, str):
+        t = t.encode()
+    p = params or default_params()
+    r = SwResult()
+    ops = (C.c_uint32 * ops_cap)()
+    rc = lib().ps_sw_trace(q, len(q), t, len(t), C.byref(p), lanes, C.byref(r), ops, ops_cap)
+    if rc:
+        raise ValueError("ps_sw_trace failed")
+    return Sw(r.score, r.end_query, r.end_ref, r.beg_query, r.beg_ref, r.n_ops, r.ref_span,
+              [int(ops[k]) for k in range(min(r.n_ops, ops_cap))])
+
+
+SWITCH_NAMES = {1: "U1 FO_SW_NO_SOFTCLIP_PAD", 2: "U4 FO_SW_END_LAST_COL", 4: "U5 FO_SW_E_BEFORE_F",
+                8: "U5 FO_SW_GAP_TIE_OPEN", 16: "U7 FO_SW_EQ_BY_MATRIX", 32: "U3 FO_SW_SWAP_ID",
+                64: "P1 FO_SW_WILD_MISMATCH"}
+
+
+def fuzz_striped(seed: int, n_pairs: int, lanes: int, qmax: int = 72, tmax: int = 160,
+                 params: Params | None = None, n_threads: int = 0) -> dict:
+    """ps_fuzz: n_pairs generated pairs (random / planted / gapped / low-complexity / wildcard letters)
+    through fo_sw_trace and the striped restatement; returns the census and the first divergence."""
+    p = params or default_params()
+    rep = FuzzReport()
+    rc = lib().ps_fuzz(seed, n_pairs, lanes, qmax, tmax, C.byref(p), n_threads, C.byref(rep))
+    if rc:
+        raise ValueError("ps_fuzz failed")
+    out = {k: getattr(rep, k) for k in ("n_pairs", "n_diverged", "n_gapped", "n_multi_max", "n_zero_ef", "first_div")}
+    if rep.first_div >= 0:
+        out["first_q"] = rep.first_q.decode()
+        out["first_t"] = rep.first_t.decode()
+        out["explained_by"] = SWITCH_NAMES.get(rep.explained_by, "no single switch")
+    return out
 
 
 NT16 = "=ACMGRSVTWYHKDBN"

@@ -35,6 +35,8 @@
 #endif
 
 #define PS_MAX_LANES 32
+/* vectors are ps_vec of PS_MAX_LANES slots of which only the first `lanes` are ever written or read */
+#pragma GCC diagnostic ignored "-Wmaybe-uninitialized"
 
 /* parasail.h trace bits */
 enum {
@@ -114,10 +116,9 @@ typedef struct {
  * ops receives parasail's BAM-encoded CIGAR (no clipping ops) in forward order.
  * lanes = 8 (128-bit builds) or 16 (AVX2); any value in [1, 32] is accepted for experiments.
  */
-int ps_sw_trace_striped(const char *s1, int s1Len, const char *s2, int s2Len, int open, int gap,
-                        int match, int mismatch, int lanes, ps_result *res, uint32_t *ops, int ops_cap)
+static inline __attribute__((always_inline)) int ps_core(const char *s1, int s1Len, const char *s2, int s2Len, int open, int gap,
+                        int match, int mismatch, const int lanes, ps_result *res, uint32_t *ops, int ops_cap)
 {
-    if (!s1 || !s2 || s1Len <= 0 || s2Len <= 0 || lanes < 1 || lanes > PS_MAX_LANES || !res) return -1;
     const int L = lanes;
     ps_matrix mat;
     ps_matrix_create(&mat, "ACTGN", match, mismatch);
@@ -352,6 +353,17 @@ end:
     return 0;
 }
 
+int ps_sw_trace_striped(const char *s1, int s1Len, const char *s2, int s2Len, int open, int gap,
+                        int match, int mismatch, int lanes, ps_result *res, uint32_t *ops, int ops_cap)
+{
+    if (!s1 || !s2 || s1Len <= 0 || s2Len <= 0 || lanes < 1 || lanes > PS_MAX_LANES || !res) return -1;
+    switch (lanes) {   /* the two widths upstream ships get a specialised (vectorisable) copy */
+    case 8: return ps_core(s1, s1Len, s2, s2Len, open, gap, match, mismatch, 8, res, ops, ops_cap);
+    case 16: return ps_core(s1, s1Len, s2, s2Len, open, gap, match, mismatch, 16, res, ops, ops_cap);
+    default: return ps_core(s1, s1Len, s2, s2Len, open, gap, match, mismatch, lanes, res, ops, ops_cap);
+    }
+}
+
 /* dparasail result wrapper on top (U1/U2): S(beg_query) first, S(qlen-1-end_query) last; same output
  * contract as fo_sw_trace so the two can be compared field by field. */
 int ps_sw_trace(const char *q, int qlen, const char *t, int tlen, const fo_params *p, int lanes,
@@ -531,7 +543,7 @@ int ps_fuzz(uint64_t seed, int64_t n_pairs, int lanes, int qmax, int tmax, const
         fo_sw_result b;
         uint32_t ob[64];
         ps_sw_trace(rep->first_q, ql, rep->first_t, tl, p, lanes, &b, ob, 64);
-        for (uint32_t sw = 1; sw <= FO_SW_EQ_BY_MATRIX; sw <<= 1) {
+        for (uint32_t sw = 1; sw <= FO_SW_WILD_MISMATCH; sw <<= 1) {
             fo_params p2 = *p;
             p2.switches ^= sw;
             fo_sw_result a;
