@@ -46,7 +46,8 @@ class BatchView(C.Structure):
                 ("beg_query", C.POINTER(C.c_int32)), ("end_query", C.POINTER(C.c_int32)),
                 ("beg_ref", C.POINTER(C.c_int32)), ("end_ref", C.POINTER(C.c_int32)),
                 ("win_start", C.POINTER(C.c_int64)), ("n_ops", C.POINTER(C.c_int32)),
-                ("ops", C.POINTER(C.c_uint32))]
+                ("ops", C.POINTER(C.c_uint32)),
+                ("gate", C.POINTER(C.c_uint8)), ("meta", C.c_void_p)]
 
 
 class Inputs(C.Structure):
@@ -58,7 +59,7 @@ class Inputs(C.Structure):
 class Result(C.Structure):
     _fields_ = [("score", C.c_int32), ("end_query", C.c_int32), ("end_ref", C.c_int32), ("beg_query", C.c_int32),
                 ("beg_ref", C.c_int32), ("n_ops", C.c_int32), ("flags", C.c_uint32), ("read", C.c_int32),
-                ("ops", C.c_uint32 * 16)]   # FADEGPU_MAX_OPS
+                ("ops", C.c_uint32 * 10)]   # FADEGPU_MAX_OPS
 
 
 class ResultsView(C.Structure):
@@ -72,7 +73,8 @@ class Stats(C.Structure):
                 ("kernel_ms", C.c_float), ("fill_ms", C.c_float), ("trace_ms", C.c_float),
                 ("generic_ms", C.c_float), ("total_ms", C.c_float), ("scratch_bytes", C.c_int64),
                 ("host_submit_ms", C.c_float), ("host_wait_ms", C.c_float), ("host_classify_ms", C.c_float),
-                ("host_sort_ms", C.c_float), ("host_gather_ms", C.c_float), ("host_threads", C.c_int32)]
+                ("host_sort_ms", C.c_float), ("host_gather_ms", C.c_float), ("host_threads", C.c_int32),
+                ("reserved", C.c_int32), ("n_oversize", C.c_int64)]
 
 
 class HostRecord(C.Structure):
@@ -86,7 +88,7 @@ ABI_SYMBOLS = [
     "fadegpu_abi_version", "fadegpu_device_count", "fadegpu_default_params", "fadegpu_create",
     "fadegpu_destroy", "fadegpu_last_error", "fadegpu_load_reference", "fadegpu_share_reference",
     "fadegpu_reference_info", "fadegpu_alloc_batch", "fadegpu_get_batch_view", "fadegpu_free_batch",
-    "fadegpu_submit", "fadegpu_submit_inputs", "fadegpu_wait", "fadegpu_get_results", "fadegpu_get_stats", "fadegpu_replay_kernels", "fadegpu_replay_batches",
+    "fadegpu_submit", "fadegpu_submit_compact", "fadegpu_submit_inputs", "fadegpu_wait", "fadegpu_get_results", "fadegpu_get_stats", "fadegpu_get_timeline", "fadegpu_replay_kernels", "fadegpu_replay_batches",
     "fadegpu_measure_alu_peak",
     "fadehost_parse_clips", "fadehost_aligned_length", "fadehost_prepare", "fadehost_finish",
 ]
@@ -118,10 +120,12 @@ def lib():
     L.fadegpu_free_batch.argtypes = [vp]
     L.fadegpu_free_batch.restype = None
     L.fadegpu_submit.argtypes = [vp, vp, i64]
+    L.fadegpu_submit_compact.argtypes = [vp, vp, i64, i64]
     L.fadegpu_submit_inputs.argtypes = [vp, vp, i64, C.POINTER(Inputs)]
     L.fadegpu_wait.argtypes = [vp, vp]
     L.fadegpu_get_results.argtypes = [vp, C.POINTER(ResultsView)]
     L.fadegpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.fadegpu_get_timeline.argtypes = [vp, vp, C.POINTER(C.c_float)]
     L.fadegpu_replay_kernels.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]
     L.fadegpu_replay_batches.argtypes = [vp, C.POINTER(vp), i32, i32, C.POINTER(C.c_float)]
     L.fadegpu_measure_alu_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -134,7 +138,7 @@ def lib():
     L.fadehost_finish.argtypes = [C.POINTER(HostRecord), C.c_char_p, C.c_uint8, i32, i32, i32, C.c_uint8, i64, i32,
                                   i32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.c_char_p, C.c_char_p,
                                   C.c_char_p, C.c_char_p, C.c_size_t]
-    if L.fadegpu_abi_version() != 1:
+    if L.fadegpu_abi_version() != 2:
         raise FadeGpuError(-101, "libfadegpu.so ABI version mismatch")
     _lib = L
     return L

@@ -10,8 +10,8 @@ import numpy as np
 
 from ._lib import BatchView, FadeGpuError, HostRecord, Inputs, Params, Result, ResultsView, Stats, lib
 
-MAX_OPS = 16
-R_ALIGNED, R_ART_LEFT, R_ART_RIGHT, R_OPS_TRUNC, R_GENERIC = 1, 2, 4, 8, 16
+MAX_OPS = 10
+R_ALIGNED, R_ART_LEFT, R_ART_RIGHT, R_OPS_TRUNC, R_GENERIC, R_OVERSIZE = 1, 2, 4, 8, 16, 32
 F_FORCE_GENERIC = 1
 F_NO_SCATTER = 2
 F_NO_SHORTCUT = 8
@@ -20,6 +20,10 @@ F_SYNC_SUBMIT = 32
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_query", "<i4"), ("end_ref", "<i4"), ("beg_query", "<i4"),
                          ("beg_ref", "<i4"), ("n_ops", "<i4"), ("flags", "<u4"), ("read", "<i4"),
                          ("ops", "<u4", (MAX_OPS,))])
+# fadegpu_read_meta: one read of the compact input layout (fadegpu_submit_compact)
+META_DTYPE = np.dtype([("pos", "<i8"), ("seq_off", "<u4"), ("l_qseq", "<i4"), ("tid", "<i4"), ("aligned_len", "<i4"),
+                       ("clip_left", "<u4"), ("clip_right", "<u4")])
+assert META_DTYPE.itemsize == 32
 OPCHARS = "MIDNSHP=XB"
 
 
@@ -148,6 +152,9 @@ class Batch:
         self.clip_left = _np_view(v.clip_left, n, np.int32)
         self.clip_right = _np_view(v.clip_right, n, np.int32)
         self.flags = _np_view(v.flags, n, np.uint8)
+        self.gate = _np_view(v.gate, n, np.uint8)
+        self.meta = _np_view(C.cast(v.meta, C.POINTER(C.c_uint8)), n * META_DTYPE.itemsize, np.uint8).view(META_DTYPE)
+        self.seq_bytes = 0
         if v.score:     # per-read output arrays exist unless the ctx has F_NO_SCATTER
             self.score = _np_view(v.score, n, np.int32)
             self.beg_query = _np_view(v.beg_query, n, np.int32)
@@ -176,6 +183,33 @@ class Batch:
         self.clip_right[:n] = clip_right
         self.n = n
         return self
+
+    def fill_compact(self, seq4, seq_off, l_qseq, tid, pos, aligned_len, clip_left, clip_right):
+        """the same reads in the compact layout: gate[] (one byte per read) + meta[] (32-byte records) + seq4"""
+        n = len(l_qseq)
+        nb = int(seq_off[n])
+        if n > self.max_reads or nb > self.max_seq_bytes:
+            raise ValueError("batch too small")
+        self.seq4[:nb] = seq4[:nb]
+        m = self.meta[:n]
+        m["pos"] = pos
+        m["seq_off"] = seq_off[:n]
+        m["l_qseq"] = l_qseq
+        m["tid"] = tid
+        m["aligned_len"] = aligned_len
+        m["clip_left"] = np.asarray(clip_left).astype(np.uint32)
+        m["clip_right"] = np.asarray(clip_right).astype(np.uint32)
+        np.minimum(np.maximum(m["clip_left"], m["clip_right"]), 255, out=self.gate[:n], casting="unsafe")
+        self.n = n
+        self.seq_bytes = nb
+        return self
+
+    def submit_compact(self, n: int | None = None, seq_bytes: int | None = None):
+        if n is not None:
+            self.n = n
+        if seq_bytes is not None:
+            self.seq_bytes = seq_bytes
+        self.ctx._check(lib().fadegpu_submit_compact(self.ctx._h, self._h, self.n, self.seq_bytes))
 
     def submit(self, n: int | None = None):
         if n is not None:
@@ -222,6 +256,12 @@ class Batch:
         s = Stats()
         self.ctx._check(lib().fadegpu_get_stats(self._h, C.byref(s)))
         return s
+
+    def timeline(self, origin: "Batch"):
+        """device ms of (uploads start, inputs ready, kernels done, results on the host) relative to origin's start"""
+        ms = (C.c_float * 4)()
+        self.ctx._check(lib().fadegpu_get_timeline(self._h, origin._h, ms))
+        return [float(x) for x in ms]
 
     def replay_kernels(self, iters: int = 1) -> float:
         ms = C.c_float()

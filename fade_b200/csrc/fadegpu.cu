@@ -5,7 +5,7 @@
 // caller's thread) -> on the ctx thread: upload, bin_classify_kernel (length floor of
 // source/analysis.d:34, window arithmetic of source/analysis.d:45-59, histogram), launch plan from the
 // histogram, bin_scatter_kernel (sorted descriptors), seq_pull_kernel (bases fetched from the pinned
-// view), then fills on `stream` and traceback rounds on `tstream` over two alternating scratch sets,
+// view), then fills on `stream` and traceback rounds on `tstream` over alternating scratch sets (three by default),
 // result_index_kernel and the copies home on `stream3`.  FADEGPU_F_HOST_BINNING keeps the first
 // implementation, which evaluates the floor and the windows and sorts on the host.
 // There is no CPU fallback: every compute entry point needs a CUDA device.
@@ -37,6 +37,8 @@ static_assert(sizeof(AlnDesc) == 40, "AlnDesc layout");
 
 static thread_local std::string g_last_error;
 
+constexpr int MAX_SETS = 4;
+
 struct fadegpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -55,7 +57,7 @@ struct fadegpu_ctx {
     // Fills run back to back on `stream`; the traceback rounds (and the generic kernel) of a launch
     // run on `tstream`, at higher priority, under the fill of the NEXT launch (of this batch or of
     // the following one): their many small, latency-bound grids take SM slots as fill blocks retire.
-    // Two scratch sets alternate between consecutive launches, ordered by events.
+    // The scratch sets (three by default) take turns between consecutive launches, ordered by events.
     cudaStream_t tstream = nullptr;
     unsigned next_set = 0;
     struct ScratchSet {
@@ -70,8 +72,8 @@ struct fadegpu_ctx {
         uint8_t *d_trace = nullptr;
         size_t trace_bytes = 0;
         unsigned int *d_qcount = nullptr;
-    } scratch[2];
-    int n_sets = 2;
+    } scratch[MAX_SETS];
+    int n_sets = 3;                      // FADEGPU_SCRATCH_SETS=2..4 overrides (A/B measurements)
     uint32_t *d_alu = nullptr;
     int sm_count = 148;
     int host_threads = 1;
@@ -135,8 +137,12 @@ struct fadegpu_batch {
     uint8_t *d_in_seq4 = nullptr;
     int64_t *d_in_seq_off = nullptr, *d_in_pos = nullptr, *d_start = nullptr, *d_aln_start = nullptr;
     int32_t *d_in_lq = nullptr, *d_in_tid = nullptr, *d_in_alen = nullptr, *d_in_cl = nullptr, *d_in_cr = nullptr;
-    int32_t *d_key = nullptr, *d_tlen = nullptr, *d_hist = nullptr, *d_keybase = nullptr, *d_cursor = nullptr, *d_ridx = nullptr;
+    int32_t *d_key = nullptr, *d_tlen = nullptr, *d_hist = nullptr, *d_keybase = nullptr, *d_cursor = nullptr;
+    int32_t *d_ridx = nullptr;                         // per read: index into the results (built on the device, copied home)
     uint8_t *d_rflags = nullptr;
+    uint8_t *d_gate = nullptr;                         // compact inputs: the one byte per read that is uploaded
+    const uint4 *d_view_meta = nullptr;                // device address of the pinned view's 32-byte records
+    int32_t *d_over = nullptr, *h_over = nullptr;      // reads left unaligned because their window exceeds 2^31 cells
     unsigned long long *d_stats = nullptr;
     int32_t *h_hist = nullptr, *h_keybase = nullptr;   // pinned
     unsigned long long *h_stats = nullptr;            // pinned
@@ -147,7 +153,6 @@ struct fadegpu_batch {
     int32_t *h_c_lq = nullptr, *h_c_tid = nullptr, *h_c_alen = nullptr, *h_c_cl = nullptr, *h_c_cr = nullptr, *h_c_read = nullptr;
     int32_t *d_in_read = nullptr;
     int64_t n_c = 0, seq_c = 0;                        // gathered reads / their sequence bytes
-    bool job_pull = false;                             // the queued submit reads the batch's own pinned view
     bool pulled = false;
     int64_t *d_src_off = nullptr;
     const uint8_t *d_view_seq4 = nullptr;              // device address of the pinned view's seq4
@@ -156,7 +161,9 @@ struct fadegpu_batch {
     bool ba_valid = false;
     AlnDesc *d_aln_scratch = nullptr;                  // replays scatter into these instead of the live descriptors
     int64_t *d_i64_scratch = nullptr;
-    cudaEvent_t ev_prep = nullptr, ev_ready = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_prep = nullptr, ev_ready = nullptr;
+    int mode = 0;                                      // SubmitMode of the queued / last submit
+    int64_t job_seq_bytes = 0;
     cudaEvent_t ev_kernels = nullptr;                  // end of the batch's kernels (recorded on tstream)
     // asynchronous submit (guarded by ctx->q_mu)
     bool queued = false;
@@ -495,7 +502,14 @@ int fadegpu_default_params(fadegpu_params *p)
     return FADEGPU_OK;
 }
 
-const char *fadegpu_last_error(const fadegpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+const char *fadegpu_last_error(const fadegpu_ctx *ctx)
+{
+    // copied under the lock into a buffer of the calling thread: the ctx thread may be rewriting ctx->err
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> g(g_err_mu);
+    copy = ctx ? ctx->err : g_last_error;
+    return copy.c_str();
+}
 
 int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
 {
@@ -530,20 +544,24 @@ int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_alu, 64)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&c->tstream, cudaStreamNonBlocking, -1)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&c->scratch[0].ev_fill, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&c->scratch[1].ev_fill, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&c->scratch[0].ev_trace, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&c->scratch[1].ev_trace, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaMalloc(&c->scratch[0].d_cursor, sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaMalloc(&c->scratch[1].d_cursor, sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaMalloc(&c->scratch[0].d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaMalloc(&c->scratch[1].d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, -2)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, -2)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "fadegpu_create");
         delete c;
         return rc;
+    }
+    if (const char *ev = getenv("FADEGPU_SCRATCH_SETS")) c->n_sets = std::min(MAX_SETS, std::max(2, atoi(ev)));
+    for (int l = 0; l < c->n_sets; ++l) {
+        fadegpu_ctx::ScratchSet &ln = c->scratch[l];
+        if ((e = cudaEventCreateWithFlags(&ln.ev_fill, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&ln.ev_trace, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaMalloc(&ln.d_cursor, sizeof(unsigned int))) != cudaSuccess ||
+            (e = cudaMalloc(&ln.d_qcount, 2 * sizeof(unsigned int))) != cudaSuccess) {
+            int rc = cuda_fail(nullptr, e, "fadegpu_create");
+            fadegpu_destroy(c);
+            return rc;
+        }
     }
     *out = c;
     return FADEGPU_OK;
@@ -671,6 +689,13 @@ int fadegpu_share_reference(fadegpu_ctx *dst, const fadegpu_ctx *src)
     std::lock_guard<std::mutex> submit_guard(dst->submit_mu);
     CU(dst, cudaSetDevice(dst->device));
     { CU(dst, cudaStreamSynchronize(dst->stream)); CU(dst, cudaStreamSynchronize(dst->tstream)); }
+    if (dst->device != src->device) {   // direct NVLink copies need peer access; without it the copy is staged through the host
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dst->device, src->device) == cudaSuccess && can) {
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (pe != cudaSuccess) cudaGetLastError();   // already enabled (or not possible): the copy still works
+        }
+    }
     free_reference(dst);
     dst->n_contigs = src->n_contigs; dst->names = src->names; dst->clen = src->clen; dst->coff = src->coff;
     dst->total_bases = src->total_bases; dst->padded_bases = src->padded_bases; dst->n_x = src->n_x;
@@ -708,6 +733,7 @@ void fadegpu_free_batch(fadegpu_batch *b)
     fadegpu_batch_view &v = b->v;
     free_host(v.seq4); free_host(v.seq_off); free_host(v.l_qseq); free_host(v.tid); free_host(v.pos);
     free_host(v.aligned_len); free_host(v.clip_left); free_host(v.clip_right);
+    free_host(v.gate); free_host(v.meta);
     free_host(v.flags); free_host(v.score); free_host(v.beg_query); free_host(v.end_query);
     free_host(v.beg_ref); free_host(v.end_ref); free_host(v.win_start); free_host(v.n_ops); free_host(v.ops);
     free_host(b->h_aln); free_host(b->h_items); free_host(b->h_seq); free_host(b->h_out); free_host(b->h_ridx);
@@ -715,15 +741,15 @@ void fadegpu_free_batch(fadegpu_batch *b)
     free_dev(b->d_fillres);
     free_dev(b->d_in_seq4); free_dev(b->d_in_seq_off); free_dev(b->d_in_pos); free_dev(b->d_in_lq); free_dev(b->d_in_tid);
     free_dev(b->d_in_alen); free_dev(b->d_in_cl); free_dev(b->d_in_cr); free_dev(b->d_key); free_dev(b->d_tlen); free_dev(b->d_start);
-    free_dev(b->d_aln_start); free_dev(b->d_hist); free_dev(b->d_keybase); free_dev(b->d_cursor); free_dev(b->d_ridx);
-    free_dev(b->d_rflags); free_dev(b->d_stats);
+    free_dev(b->d_aln_start); free_dev(b->d_hist); free_dev(b->d_keybase); free_dev(b->d_cursor);
+    free_dev(b->d_ridx); free_dev(b->d_rflags);
+    free_dev(b->d_gate); free_dev(b->d_over); free_host(b->h_over); free_dev(b->d_stats);
     free_host(b->h_hist); free_host(b->h_keybase); free_host(b->h_stats); free_host(b->h_aln_start);
     free_host(b->h_c_seq4); free_host(b->h_c_seq_off); free_host(b->h_c_pos); free_host(b->h_c_lq); free_host(b->h_c_tid);
     free_host(b->h_c_alen); free_host(b->h_c_cl); free_host(b->h_c_cr); free_host(b->h_c_read); free_dev(b->d_in_read); free_dev(b->d_src_off);
     free_dev(b->d_aln_scratch); free_dev(b->d_i64_scratch);
     if (b->ev_prep) cudaEventDestroy(b->ev_prep);
     if (b->ev_ready) cudaEventDestroy(b->ev_ready);
-    if (b->ev_done) cudaEventDestroy(b->ev_done);
     if (b->ev_kernels) cudaEventDestroy(b->ev_kernels);
     for (auto &e : b->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     delete b;
@@ -749,7 +775,7 @@ int fadegpu_alloc_batch(fadegpu_ctx *c, int64_t max_reads, int64_t max_seq_bytes
     auto D = [&](auto **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc((void **)p, std::max<size_t>(bytes, 16)); };
     H(&v.seq4, (size_t)max_seq_bytes + 16); H(&v.seq_off, (n + 1) * 8); H(&v.l_qseq, n * 4); H(&v.tid, n * 4);
     H(&v.pos, n * 8); H(&v.aligned_len, n * 4); H(&v.clip_left, n * 4); H(&v.clip_right, n * 4);
-    H(&v.flags, n);
+    H(&v.flags, n); H(&v.gate, n); H(&v.meta, n * sizeof(fadegpu_read_meta));
     if (!(c->p.flags & FADEGPU_F_NO_SCATTER)) {   // the per-read output arrays are only filled without NO_SCATTER
         H(&v.score, n * 4); H(&v.beg_query, n * 4); H(&v.end_query, n * 4); H(&v.beg_ref, n * 4);
         H(&v.end_ref, n * 4); H(&v.win_start, n * 8); H(&v.n_ops, n * 4); H(&v.ops, n * 4 * FADEGPU_MAX_OPS);
@@ -767,12 +793,14 @@ int fadegpu_alloc_batch(fadegpu_ctx *c, int64_t max_reads, int64_t max_seq_bytes
     D(&b->d_in_lq, n * 4); D(&b->d_in_tid, n * 4); D(&b->d_in_alen, n * 4); D(&b->d_in_cl, n * 4); D(&b->d_in_cr, n * 4);
     D(&b->d_key, n * 4); D(&b->d_tlen, n * 4); D(&b->d_start, n * 8); D(&b->d_aln_start, n * 8);
     D(&b->d_hist, (size_t)BIN_KEYS * 4); D(&b->d_keybase, (size_t)BIN_KEYS * 4); D(&b->d_cursor, (size_t)BIN_KEYS * 4);
-    D(&b->d_ridx, n * 4); D(&b->d_rflags, n); D(&b->d_stats, 128); D(&b->d_src_off, n * 8);
+    D(&b->d_ridx, n * 4); D(&b->d_rflags, n);
+    D(&b->d_gate, n); D(&b->d_over, (size_t)OVER_CAP * 4); H(&b->h_over, (size_t)OVER_CAP * 4);
+    D(&b->d_stats, 128); D(&b->d_src_off, n * 8);
     H(&b->h_hist, (size_t)BIN_KEYS * 4); H(&b->h_keybase, (size_t)BIN_KEYS * 4); H(&b->h_stats, 128); H(&b->h_aln_start, n * 8);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&b->d_view_seq4, v.seq4, 0);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&b->d_view_meta, v.meta, 0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_prep);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_ready);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_kernels, cudaEventDisableTiming);
     for (auto &ev : b->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e != cudaSuccess) {
@@ -802,13 +830,14 @@ static int ensure_host_staging(fadegpu_ctx *c, fadegpu_batch *b)
 }
 
 static int gather_reads(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, const fadegpu_inputs &in);
-static int queue_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, bool gather);
+static int queue_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, int mode, int64_t seq_bytes);
+static bool batch_in_flight(fadegpu_ctx *c, fadegpu_batch *b);
 
 int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, const fadegpu_inputs *in)
 {
     if (!c || !b || b->ctx != c || !in) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: bad ctx/batch/inputs");
     if (!c->d_two) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: no reference loaded");
-    if (b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: batch already in flight (call fadegpu_wait)");
+    if (batch_in_flight(c, b)) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: batch already in flight (call fadegpu_wait)");
     if (n_reads < 0 || n_reads > b->v.max_reads) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: n_reads out of range");
     if (n_reads > 0 && (!in->seq4 || !in->seq_off || !in->l_qseq || !in->tid || !in->pos || !in->aligned_len ||
                         !in->clip_left || !in->clip_right))
@@ -817,7 +846,7 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
         // the caller's arrays are only read here; uploads, binning and launches follow on the ctx thread
         CU(c, cudaSetDevice(c->device));
         { int rc = gather_reads(c, b, n_reads, *in); if (rc) return rc; }
-        return queue_submit(c, b, n_reads, false);
+        return queue_submit(c, b, n_reads, 0 /* MODE_GATHERED */, 0);
     }
     std::lock_guard<std::mutex> submit_guard(c->submit_mu);
     CU(c, cudaSetDevice(c->device));
@@ -840,7 +869,7 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     const uint32_t floor_u = (uint32_t)c->p.min_length;  // uint <= int compare of analysis.d:34
     const int64_t W = c->p.window_size;
     const int64_t seq_total = n > 0 ? in->seq_off[n] : 0;
-    int64_t cells = 0;
+    int64_t cells = 0, n_over = 0;
     int bad = 0;
 #pragma omp parallel num_threads(nthr) reduction(+ : cells) reduction(| : bad)
     {
@@ -867,7 +896,12 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
             if (end <= start) continue;                              // empty window: nothing to align
             // a window this large (spliced alignment spanning megabases) would need a multi-GB trace
             // for ONE read in the reference as well; refuse it loudly instead of running for hours
-            if (end - start > 0x7fffffff || (end - start) * (int64_t)ql > ((int64_t)1 << 31)) { bad = 2; continue; }
+            if (end - start > 0x7fffffff || (end - start) * (int64_t)ql > ((int64_t)1 << 31)) {
+                // (the reference would need a multi-GB trace for this ONE read) left unaligned and reported
+#pragma omp critical(fadegpu_oversize)
+                { if (n_over < OVER_CAP) b->h_over[n_over] = (int32_t)r; ++n_over; }
+                continue;
+            }
             const int tlen = (int)(end - start);
             const int cls = class_of(c, ql, tlen);
             const int rk = cls_rank(cls);
@@ -878,8 +912,8 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
         }
     }
     if (bad & 1) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
-    if (bad & 2) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: a read's window exceeds 2^31 DP cells (aligned_len too large)");
     b->st.cells = cells;
+    b->st.n_oversize = n_over;
     b->st.host_classify_ms = ms_since(t_begin);
     const auto t_sort = std::chrono::steady_clock::now();
 
@@ -1101,20 +1135,29 @@ static int gather_reads(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, const fadeg
     return FADEGPU_OK;
 }
 
-// Stage B: the gathered reads go to the GPU, a classify kernel does the window arithmetic
-// (analysis.d:45-59) and histograms them by (row class, window length), the host turns the 96 KB
-// histogram into the launch plan, a scatter kernel writes the sorted descriptors, the SW kernels
-// follow on the compute stream and the results come back on a third stream.  Uploads and binning of
-// batch k+1 overlap the kernels of batch k.
-static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, bool pull)
+// Where a queued submit finds its inputs
+enum SubmitMode : int {
+    MODE_GATHERED = 0,   // fadegpu_submit_inputs: the reads past the length floor, staged by gather_reads
+    MODE_VIEW = 1,       // fadegpu_submit: the seven input arrays of the pinned view are DMA'd as they are (36 B / read)
+    MODE_COMPACT = 2     // fadegpu_submit_compact: one gate byte per read is DMA'd, the GPU fetches the rest it needs
+};
+
+// Stage B: the inputs go to the GPU, a classify kernel applies the length floor (analysis.d:34) and the window
+// arithmetic (analysis.d:45-59) and histograms the reads that need SW by (row class, window length), the host
+// turns the 96 KB histogram into the launch plan, a scatter kernel writes the sorted descriptors, the GPU pulls the
+// bases of those reads from the pinned view, the SW kernels follow on the compute stream and the result records
+// come back on a third stream.  Uploads and binning of batch k+1 overlap the kernels of batch k.
+static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, int mode, int64_t seq_bytes)
 {
     const auto t_begin = std::chrono::steady_clock::now();
     auto ms_since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
+    const bool pull = mode != MODE_GATHERED;
     b->n_reads = n_reads;
     b->plan.clear();
     b->dev_binning = true;
+    b->mode = mode;
     {
         const float g = pull ? 0.f : b->st.host_gather_ms; const int32_t th = pull ? 1 : b->st.host_threads;
         memset(&b->st, 0, sizeof(b->st));
@@ -1125,22 +1168,24 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
     b->ba_valid = false;
     cudaStream_t s2 = c->stream2;
     CU(c, cudaEventRecord(b->ev[0], s2));
-    // pull: every read's fields are DMA'd from the pinned view (36 B/read), the bases stay there until
-    // seq_pull_kernel fetches those of the reads that get aligned.  Otherwise: what gather_reads staged.
     b->pulled = pull;
     const fadegpu_batch_view &v = b->v;
     const int64_t n = pull ? n_reads : b->n_c;
-    const int64_t seq_total = pull ? (n > 0 ? v.seq_off[n] : 0) : b->seq_c;
-    int64_t n_aln = 0;
+    const int64_t seq_total = mode == MODE_COMPACT ? seq_bytes : mode == MODE_VIEW ? (n > 0 ? v.seq_off[n] : 0) : b->seq_c;
+    int64_t n_aln = 0, up_bytes = 0;
+    memset(b->h_stats, 0, 128);
     if (n > 0) {
-        auto up = [&](void *d, const void *h, size_t bytes) { return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s2); };
-        if (!pull) CU(c, up(b->d_in_seq4, b->h_c_seq4, (size_t)seq_total));
-        CU(c, up(b->d_in_seq_off, pull ? v.seq_off : b->h_c_seq_off, (size_t)(n + 1) * 8));
-        CU(c, up(b->d_in_lq, pull ? v.l_qseq : b->h_c_lq, (size_t)n * 4)); CU(c, up(b->d_in_tid, pull ? v.tid : b->h_c_tid, (size_t)n * 4));
-        CU(c, up(b->d_in_pos, pull ? v.pos : b->h_c_pos, (size_t)n * 8)); CU(c, up(b->d_in_alen, pull ? v.aligned_len : b->h_c_alen, (size_t)n * 4));
-        CU(c, up(b->d_in_cl, pull ? v.clip_left : b->h_c_cl, (size_t)n * 4)); CU(c, up(b->d_in_cr, pull ? v.clip_right : b->h_c_cr, (size_t)n * 4));
-        if (!pull) CU(c, up(b->d_in_read, b->h_c_read, (size_t)n * 4));
-    CU(c, cudaMemsetAsync(b->d_hist, 0, (size_t)BIN_KEYS * 4, s2));
+        auto up = [&](void *d, const void *h, size_t bytes) { up_bytes += (int64_t)bytes; return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s2); };
+        if (mode == MODE_COMPACT) CU(c, up(b->d_gate, v.gate, (size_t)n));
+        else {
+            if (!pull) CU(c, up(b->d_in_seq4, b->h_c_seq4, (size_t)seq_total));
+            CU(c, up(b->d_in_seq_off, pull ? v.seq_off : b->h_c_seq_off, (size_t)(n + 1) * 8));
+            CU(c, up(b->d_in_lq, pull ? v.l_qseq : b->h_c_lq, (size_t)n * 4)); CU(c, up(b->d_in_tid, pull ? v.tid : b->h_c_tid, (size_t)n * 4));
+            CU(c, up(b->d_in_pos, pull ? v.pos : b->h_c_pos, (size_t)n * 8)); CU(c, up(b->d_in_alen, pull ? v.aligned_len : b->h_c_alen, (size_t)n * 4));
+            CU(c, up(b->d_in_cl, pull ? v.clip_left : b->h_c_cl, (size_t)n * 4)); CU(c, up(b->d_in_cr, pull ? v.clip_right : b->h_c_cr, (size_t)n * 4));
+            if (!pull) CU(c, up(b->d_in_read, b->h_c_read, (size_t)n * 4));
+        }
+        CU(c, cudaMemsetAsync(b->d_hist, 0, (size_t)BIN_KEYS * 4, s2));
         CU(c, cudaMemsetAsync(b->d_cursor, 0, (size_t)BIN_KEYS * 4, s2));
         CU(c, cudaMemsetAsync(b->d_stats, 0, 128, s2));
         BinArgs ba{};
@@ -1148,20 +1193,21 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
         ba.aligned_len = b->d_in_alen; ba.clip_left = b->d_in_cl; ba.clip_right = b->d_in_cr;
         ba.read = pull ? nullptr : b->d_in_read;
         ba.seq_cursor = pull ? b->d_stats + 8 : nullptr; ba.src_off = b->d_src_off;
+        ba.gate = mode == MODE_COMPACT ? b->d_gate : nullptr; ba.host_meta = b->d_view_meta; ba.over_list = b->d_over;
         ba.n = n; ba.seq_total = seq_total; ba.clen = c->d_clen; ba.coff = c->d_coff; ba.n_contigs = c->n_contigs;
         ba.window = c->p.window_size; ba.min_length = c->p.min_length; ba.flags = c->p.flags;
         ba.key = b->d_key; ba.tlen = b->d_tlen; ba.start = b->d_start; ba.hist = b->d_hist; ba.stats = b->d_stats;
         ba.keybase = b->d_keybase; ba.cursor = b->d_cursor; ba.aln = b->d_aln; ba.aln_start = b->d_aln_start;
         b->ba = ba; b->ba_valid = true;
-        CU(c, launch_bin_classify(ba, s2));
+        CU(c, launch_bin_classify(ba, c->sm_count, s2));
         CU(c, cudaMemcpyAsync(b->h_hist, b->d_hist, (size_t)BIN_KEYS * 4, cudaMemcpyDeviceToHost, s2));
-        CU(c, cudaMemcpyAsync(b->h_stats, b->d_stats, 64, cudaMemcpyDeviceToHost, s2));
+        CU(c, cudaMemcpyAsync(b->h_stats, b->d_stats, 128, cudaMemcpyDeviceToHost, s2));
+        CU(c, cudaMemcpyAsync(b->h_over, b->d_over, (size_t)OVER_CAP * 4, cudaMemcpyDeviceToHost, s2));
         CU(c, cudaEventRecord(b->ev_prep, s2));
         CU(c, cudaEventSynchronize(b->ev_prep));   // the previous batch keeps computing on c->stream meanwhile
         b->st.host_classify_ms = ms_since(t_begin);
         if (b->h_stats[6] & 1ull) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off / l_qseq inconsistent");
-        b->h_stats[7] = 0;
-        if (b->h_stats[6] & 2ull) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: a read's window exceeds 2^31 DP cells (aligned_len too large)");
+        b->st.n_oversize = (int64_t)b->h_stats[11];
         // ---- plan from the histogram ----
         const auto t_sort = std::chrono::steady_clock::now();
         n_aln = (int64_t)b->h_stats[1];
@@ -1191,11 +1237,10 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
         }
         b->st.host_sort_ms = ms_since(t_sort);
         if (n_aln > 0) {
-            CU(c, cudaMemcpyAsync(b->d_keybase, b->h_keybase, (size_t)BIN_KEYS * 4, cudaMemcpyHostToDevice, s2));
-            if (b->n_items > 0)
-                CU(c, cudaMemcpyAsync(b->d_items, b->h_items, (size_t)b->n_items * sizeof(WarpItem), cudaMemcpyHostToDevice, s2));
-            CU(c, launch_bin_scatter(ba, s2));
-            if (pull) CU(c, launch_seq_pull(b->d_view_seq4, b->d_aln, b->d_src_off, (int)n_aln, b->d_in_seq4, s2));
+            CU(c, up(b->d_keybase, b->h_keybase, (size_t)BIN_KEYS * 4));
+            if (b->n_items > 0) CU(c, up(b->d_items, b->h_items, (size_t)b->n_items * sizeof(WarpItem)));
+            CU(c, launch_bin_scatter(ba, c->sm_count, s2));
+            if (pull) CU(c, launch_seq_pull(b->d_view_seq4, b->d_aln, b->d_src_off, (int)n_aln, b->d_in_seq4, c->sm_count, s2));
         }
     }
     if (n_reads > 0) {
@@ -1212,19 +1257,20 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
     cudaStream_t s3 = c->stream3;                    // results go home while the next batch computes
     { int rc = join_kernels(c, b, s3); if (rc) return rc; }
     CU(c, cudaEventRecord(b->ev[2], s3));
-    if (n_aln > 0) CU(c, launch_result_index(b->d_out, (int)n_aln, n_reads, b->d_rflags, b->d_ridx, b->d_stats + 7, s3));
+    if (n_aln > 0) CU(c, launch_result_index(b->d_out, (int)n_aln, n_reads, b->d_rflags, b->d_ridx, b->d_stats + 7, c->sm_count, s3));
     if (n_reads > 0) {
         CU(c, cudaMemcpyAsync(b->v.flags, b->d_rflags, (size_t)n_reads, cudaMemcpyDeviceToHost, s3));
         CU(c, cudaMemcpyAsync(b->h_ridx, b->d_ridx, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, s3));
     }
-    if (n_aln > 0) CU(c, cudaMemcpyAsync(b->h_stats + 7, b->d_stats + 7, 16, cudaMemcpyDeviceToHost, s3));
+    if (n_aln > 0) CU(c, cudaMemcpyAsync(b->h_stats + 7, b->d_stats + 7, 8, cudaMemcpyDeviceToHost, s3));
     if (n_aln > 0) {
         CU(c, cudaMemcpyAsync(b->h_out, b->d_out, (size_t)n_aln * sizeof(AlnOut), cudaMemcpyDeviceToHost, s3));
         CU(c, cudaMemcpyAsync(b->h_aln_start, b->d_aln_start, (size_t)n_aln * 8, cudaMemcpyDeviceToHost, s3));
     }
-    // (pull: the bytes seq_pull_kernel fetched are added by fadegpu_wait, from the device's cursor)
-    b->st.h2d_bytes = (pull ? 0 : seq_total + n * 4) + (n + 1) * 8 + n * 28 + (int64_t)BIN_KEYS * 4 + b->n_items * (int64_t)sizeof(WarpItem);
-    b->st.d2h_bytes = n_aln * (int64_t)(sizeof(AlnOut) + 8) + n_reads * 5 + (int64_t)BIN_KEYS * 4 + 72;
+    // (the bytes the GPU fetched itself -- bases, compact records -- are added from the device's counters)
+    b->st.h2d_bytes = up_bytes + (pull ? (int64_t)b->h_stats[10] * (int64_t)sizeof(fadegpu_read_meta) : 0);
+    b->st.d2h_bytes = n_aln * (int64_t)(sizeof(AlnOut) + 8) + n_reads * 5 + (n > 0 ? (int64_t)BIN_KEYS * 4 + 128 + OVER_CAP * 4 : 0);
+    if (pull && n_aln > 0) CU(c, cudaMemcpyAsync(b->h_stats + 8, b->d_stats + 8, 8, cudaMemcpyDeviceToHost, s3));   // bases pulled
     CU(c, cudaEventRecord(b->ev[3], s3));
     b->in_flight = true;
     b->st.host_submit_ms = ms_since(t_begin);
@@ -1241,26 +1287,25 @@ static fadegpu_inputs view_inputs(const fadegpu_batch_view &v)
     return in;
 }
 
-// gather = the inputs are the batch's own pinned view: nothing was gathered, the GPU pulls what it needs
-static int submit_stages(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, bool gather)
+static int submit_stages(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, int mode, int64_t seq_bytes)
 {
     if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, FADEGPU_E_CUDA, "fadegpu_submit: cudaSetDevice failed");
-    return submit_device_binning(c, b, n, gather);
+    return submit_device_binning(c, b, n, mode, seq_bytes);
 }
 
-// queue stage B (and stage A when the inputs are the batch's own view) for the ctx thread
-static int queue_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, bool gather)
+// queue stage B for the ctx thread
+static int queue_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n, int mode, int64_t seq_bytes)
 {
     if (c->p.flags & FADEGPU_F_SYNC_SUBMIT) {
         std::lock_guard<std::mutex> g(c->submit_mu);
-        return submit_stages(c, b, n, gather);
+        return submit_stages(c, b, n, mode, seq_bytes);
     }
     std::lock_guard<std::mutex> lk(c->q_mu);
     if (!c->worker.joinable()) {
         try { c->worker = std::thread(worker_main, c); }
         catch (const std::exception &e) { return fail(c, FADEGPU_E_STATE, std::string("fadegpu_submit: cannot start the submit thread: ") + e.what()); }
     }
-    b->queued = true; b->submit_rc = 0; b->job_pull = gather;
+    b->queued = true; b->submit_rc = 0; b->mode = mode; b->job_seq_bytes = seq_bytes;
     b->in_flight = true;
     c->jobs.emplace_back(b, n);
     c->q_cv.notify_one();
@@ -1277,12 +1322,14 @@ static void worker_main(fadegpu_ctx *c)
         auto job = c->jobs.front();
         c->jobs.pop_front();
         c->worker_busy = true;
+        const int mode = job.first->mode;
+        const int64_t seq_bytes = job.first->job_seq_bytes;
         lk.unlock();
         int rc;
         std::string err;
         {
             std::lock_guard<std::mutex> g(c->submit_mu);
-            rc = submit_stages(c, job.first, job.second, job.first->job_pull);
+            rc = submit_stages(c, job.first, job.second, mode, seq_bytes);
             if (rc) { std::lock_guard<std::mutex> ge(g_err_mu); err = c->err; }
         }
         lk.lock();
@@ -1301,6 +1348,13 @@ static void drain_submits(fadegpu_ctx *c)
     c->done_cv.wait(lk, [&] { return c->jobs.empty() && !c->worker_busy; });
 }
 
+// a batch is "in flight" from its submit to its wait; the flag is shared with the ctx thread
+static bool batch_in_flight(fadegpu_ctx *c, fadegpu_batch *b)
+{
+    std::lock_guard<std::mutex> lk(c->q_mu);
+    return b->in_flight;
+}
+
 int fadegpu_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
 {
     if (!c || !b || b->ctx != c) return fail(c, FADEGPU_E_ARG, "fadegpu_submit: bad ctx/batch");
@@ -1310,72 +1364,97 @@ int fadegpu_submit(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads)
         return fail(c, FADEGPU_E_ARG, "fadegpu_submit: seq_off[n] exceeds max_seq_bytes");
     if (!(c->p.flags & FADEGPU_F_HOST_BINNING)) {
         if (!c->d_two) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: no reference loaded");
-        if (b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: batch already in flight (call fadegpu_wait)");
-        return queue_submit(c, b, n_reads, true);
+        if (batch_in_flight(c, b)) return fail(c, FADEGPU_E_STATE, "fadegpu_submit: batch already in flight (call fadegpu_wait)");
+        return queue_submit(c, b, n_reads, MODE_VIEW, 0);
     }
     fadegpu_inputs in = view_inputs(v);
     return fadegpu_submit_inputs(c, b, n_reads, &in);
 }
 
+int fadegpu_submit_compact(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, int64_t seq_bytes)
+{
+    if (!c || !b || b->ctx != c) return fail(c, FADEGPU_E_ARG, "fadegpu_submit_compact: bad ctx/batch");
+    const fadegpu_batch_view &v = b->v;
+    if (n_reads < 0 || n_reads > v.max_reads) return fail(c, FADEGPU_E_ARG, "fadegpu_submit_compact: n_reads out of range");
+    if (seq_bytes < 0 || seq_bytes > v.max_seq_bytes || seq_bytes > (int64_t)0xffffffffll)
+        return fail(c, FADEGPU_E_ARG, "fadegpu_submit_compact: seq_bytes out of range");
+    if (!c->d_two) return fail(c, FADEGPU_E_STATE, "fadegpu_submit_compact: no reference loaded");
+    if (batch_in_flight(c, b)) return fail(c, FADEGPU_E_STATE, "fadegpu_submit_compact: batch already in flight (call fadegpu_wait)");
+    if (c->p.flags & FADEGPU_F_HOST_BINNING) {
+        // A/B switch: expand the compact records into the view's arrays and take the host path
+        fadegpu_batch_view &w = b->v;
+        for (int64_t k = 0; k < n_reads; ++k) {
+            const fadegpu_read_meta &m = w.meta[k];
+            w.seq_off[k] = m.seq_off; w.l_qseq[k] = m.l_qseq; w.tid[k] = m.tid; w.pos[k] = m.pos;
+            w.aligned_len[k] = m.aligned_len; w.clip_left[k] = (int32_t)m.clip_left; w.clip_right[k] = (int32_t)m.clip_right;
+        }
+        w.seq_off[n_reads] = seq_bytes;
+        fadegpu_inputs in = view_inputs(w);
+        return fadegpu_submit_inputs(c, b, n_reads, &in);
+    }
+    return queue_submit(c, b, n_reads, MODE_COMPACT, seq_bytes);
+}
+
 int fadegpu_wait(fadegpu_ctx *c, fadegpu_batch *b)
 {
     if (!c || !b || b->ctx != c) return fail(c, FADEGPU_E_ARG, "fadegpu_wait: bad ctx/batch");
-    if (!b->in_flight) return fail(c, FADEGPU_E_STATE, "fadegpu_wait: batch not submitted");
     {   // a queued submit reports its outcome here
         std::unique_lock<std::mutex> lk(c->q_mu);
+        if (!b->in_flight) { lk.unlock(); return fail(c, FADEGPU_E_STATE, "fadegpu_wait: batch not submitted"); }
         c->done_cv.wait(lk, [&] { return !b->queued; });
+        b->in_flight = false;
         if (b->submit_rc) {
-            b->in_flight = false;
             const int rc = b->submit_rc;
             b->submit_rc = 0;
+            lk.unlock();
             return fail(c, rc, b->submit_err);
         }
     }
     CU(c, cudaSetDevice(c->device));
-    b->in_flight = false;
     CU(c, cudaEventSynchronize(b->ev[3]));
     float t;
     if (cudaEventElapsedTime(&t, b->ev[1], b->ev[2]) == cudaSuccess) b->st.kernel_ms = t;
     if (cudaEventElapsedTime(&t, b->ev[0], b->ev[3]) == cudaSuccess) b->st.total_ms = t;
+    if (b->dev_binning && b->pulled) {
+        if (b->n_aln > 0) b->st.h2d_bytes += (int64_t)b->h_stats[8];
+        b->pulled = false;
+    }
+    // Device-binned submits: flags[] and the per-read index into the results were built on the device; only the
+    // per-read output arrays (unless FADEGPU_F_NO_SCATTER) are filled here.  Host-binned submits: all of it here.
     const auto t_scatter = std::chrono::steady_clock::now();
     fadegpu_batch_view &v = b->v;
     const int64_t n = b->n_reads;
-    int bad = 0;
-    const int nthr = std::max(1, c->host_threads);
     const bool scatter = !(c->p.flags & FADEGPU_F_NO_SCATTER) && v.score != nullptr;
+    // (no parallel region unless there is real work: its threads would spin for milliseconds afterwards on the
+    // cores the ctx thread needs to queue the next batch)
+    const bool walk = scatter || !b->dev_binning;
+    const int nthr = walk ? (int)std::max<int64_t>(1, std::min<int64_t>(c->host_threads, b->n_aln / 8192 + 1)) : 1;
+    const int64_t *wstart = b->dev_binning ? b->h_aln_start : b->aln_start.data();
+    int64_t bad = 0;
     if (b->dev_binning) {
-        // flags[] and the result index were produced on the device; only validate (and, unless
-        // FADEGPU_F_NO_SCATTER, fill the per-read arrays)
         if (b->n_aln > 0 && (int64_t)b->h_stats[7] != b->n_aln) bad = 1;   // result records counted on the device
-        if (b->n_aln > 0 && b->pulled) { b->st.h2d_bytes += (int64_t)b->h_stats[8]; b->pulled = false; }
-#pragma omp parallel for schedule(static) reduction(| : bad) num_threads(nthr) if (scatter)
-        for (int64_t k = 0; k < (scatter ? b->n_aln : 0); ++k) {
-            const AlnOut &o = b->h_out[k];
-            const int64_t r = o.read;
-            if (r < 0 || r >= n || (o.flags & 0x80000000u) || b->h_ridx[r] != (int32_t)k) { bad = 1; continue; }
-            v.score[r] = o.score; v.beg_query[r] = o.beg_query; v.end_query[r] = o.end_query;
-            v.beg_ref[r] = o.beg_ref; v.end_ref[r] = o.end_ref; v.n_ops[r] = o.n_ops;
-            v.win_start[r] = b->h_aln_start[k];
-            memcpy(v.ops + (size_t)r * FADEGPU_MAX_OPS, o.ops, sizeof(o.ops));
-        }
-        b->st.host_wait_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_scatter).count();
-        if (bad) return fail(c, FADEGPU_E_CUDA, "fadegpu_wait: a kernel did not produce a result record (internal error)");
-        return FADEGPU_OK;
+    } else {
+        memset(v.flags, 0, (size_t)n);   // the other per-read outputs are defined only where FADEGPU_R_ALIGNED is set
+        memset(b->h_ridx, 0xff, (size_t)n * sizeof(int32_t));
     }
-    memset(v.flags, 0, (size_t)n);   // the other per-read outputs are defined only where FADEGPU_R_ALIGNED is set
-    memset(b->h_ridx, 0xff, (size_t)n * sizeof(int32_t));
-#pragma omp parallel for schedule(static) reduction(| : bad) num_threads(nthr)
-    for (int64_t k = 0; k < b->n_aln; ++k) {
+#pragma omp parallel for schedule(static) reduction(+ : bad) num_threads(nthr) if (nthr > 1)
+    for (int64_t k = 0; k < (walk ? b->n_aln : 0); ++k) {
         const AlnOut &o = b->h_out[k];
-        const int64_t r = b->h_aln[k].read;
-        if (o.read != (int32_t)r || (o.flags & 0x80000000u)) { bad = 1; continue; }
-        v.flags[r] = (uint8_t)(o.flags & 0xff);
-        b->h_ridx[r] = (int32_t)k;
+        const int64_t r = o.read;
+        if (r < 0 || r >= n || (o.flags & 0x80000000u) || !(o.flags & 1u) || (!b->dev_binning && b->h_aln[k].read != (int32_t)r)) { ++bad; continue; }
+        if (!b->dev_binning) {
+            v.flags[r] = (uint8_t)(o.flags & 0xff);
+            b->h_ridx[r] = (int32_t)k;
+        } else if (b->h_ridx[r] != (int32_t)k) { ++bad; continue; }
         if (!scatter) continue;
         v.score[r] = o.score; v.beg_query[r] = o.beg_query; v.end_query[r] = o.end_query;
         v.beg_ref[r] = o.beg_ref; v.end_ref[r] = o.end_ref; v.n_ops[r] = o.n_ops;
-        v.win_start[r] = b->aln_start[(size_t)k];
+        v.win_start[r] = wstart[k];
         memcpy(v.ops + (size_t)r * FADEGPU_MAX_OPS, o.ops, sizeof(o.ops));
+    }
+    for (int64_t k = 0; k < std::min<int64_t>(b->st.n_oversize, OVER_CAP); ++k) {
+        const int64_t r = b->h_over[k];
+        if (r >= 0 && r < n) v.flags[r] = FADEGPU_R_OVERSIZE;
     }
     b->st.host_wait_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_scatter).count();
     if (bad) return fail(c, FADEGPU_E_CUDA, "fadegpu_wait: a kernel did not produce a result record (internal error)");
@@ -1401,10 +1480,18 @@ int fadegpu_get_stats(const fadegpu_batch *b, fadegpu_stats *s)
     return FADEGPU_OK;
 }
 
+int fadegpu_get_timeline(const fadegpu_batch *b, const fadegpu_batch *origin, float ms[4])
+{
+    if (!b || !origin || !ms || b->ctx != origin->ctx) return fail(b ? b->ctx : nullptr, FADEGPU_E_ARG, "fadegpu_get_timeline: bad arguments");
+    for (int k = 0; k < 4; ++k)
+        if (cudaEventElapsedTime(&ms[k], origin->ev[0], b->ev[k]) != cudaSuccess) { cudaGetLastError(); ms[k] = -1.f; }
+    return FADEGPU_OK;
+}
+
 // Replays re-run the device side of a submit on what it left resident in HBM: the binning kernels
 // (length floor, window arithmetic, histogram, scatter of the descriptors -- into scratch, because the
 // order among equal window lengths is not reproducible and the live descriptors point at the bases
-// already fetched), then fills / traceback / generic, then the result index.  No host work, no copies.
+// already fetched), then fills / traceback / generic.  No host work, no copies.
 static int replay_binning(fadegpu_ctx *c, fadegpu_batch *b, cudaEvent_t *dep)
 {
     *dep = nullptr;
@@ -1419,11 +1506,12 @@ static int replay_binning(fadegpu_ctx *c, fadegpu_batch *b, cudaEvent_t *dep)
     CU(c, cudaMemsetAsync(b->d_cursor, 0, (size_t)BIN_KEYS * 4, s2));
     CU(c, cudaMemsetAsync(b->d_stats, 0, 128, s2));
     BinArgs ba = b->ba;
-    CU(c, launch_bin_classify(ba, s2));
+    ba.gate = nullptr;        // compact inputs: the records fetched by the submit are resident in the device mirrors
+    CU(c, launch_bin_classify(ba, c->sm_count, s2));
     if (b->n_aln > 0) {
         ba.aln = b->d_aln_scratch; ba.aln_start = b->d_i64_scratch; ba.src_off = b->d_i64_scratch + n;
         if (ba.seq_cursor) ba.seq_cursor = b->d_stats + 9;
-        CU(c, launch_bin_scatter(ba, s2));
+        CU(c, launch_bin_scatter(ba, c->sm_count, s2));
     }
     CU(c, cudaEventRecord(b->ev_ready, s2));
     *dep = b->ev_ready;
@@ -1435,11 +1523,6 @@ static int replay_pass(fadegpu_ctx *c, fadegpu_batch *b)
     cudaEvent_t dep = nullptr;
     { int rc = replay_binning(c, b, &dep); if (rc) return rc; }
     { int rc = run_plan(c, b, nullptr, nullptr, nullptr, nullptr, dep); if (rc) return rc; }
-    if (b->dev_binning && b->n_aln > 0) {
-        { int rc = join_kernels(c, b, c->stream3); if (rc) return rc; }
-        CU(c, launch_result_index(b->d_out, (int)b->n_aln, b->n_reads, b->d_rflags, b->d_ridx, b->d_stats + 7, c->stream3));
-        CU(c, cudaEventRecord(b->ev_done, c->stream3));
-    }
     return 0;
 }
 
@@ -1447,7 +1530,6 @@ static int replay_pass(fadegpu_ctx *c, fadegpu_batch *b)
 static int replay_join(fadegpu_ctx *c, fadegpu_batch *b)
 {
     { int rc = join_kernels(c, b, c->stream); if (rc) return rc; }
-    if (b->dev_binning && b->n_aln > 0) CU(c, cudaStreamWaitEvent(c->stream, b->ev_done, 0));
     return 0;
 }
 

@@ -49,12 +49,13 @@ public:
                 i += 4 + sl;
             }
             const int64_t clen = bsize - xlen - 19;
-            if (bsize < 0 || clen < 0) { bad_ = true; return false; }
+            if (bsize < 0 || clen < 0 || clen > 0x10000) { bad_ = true; return false; }
             Blk b;
             b.c.resize((size_t)clen + 8);
             if (raw(b.c.data(), b.c.size()) != b.c.size()) { bad_ = true; return false; }
             b.crc = get_u32(&b.c[(size_t)clen]);
             b.isize = get_u32(&b.c[(size_t)clen + 4]);
+            if (b.isize > 0x10000) { bad_ = true; return false; }   // SAMv1 4.1: a block inflates to at most 64 KiB
             b.off = total;
             total += b.isize;
             blks.push_back(std::move(b));
@@ -261,6 +262,7 @@ struct RecMeta {
 struct Slot {
     std::vector<uint8_t> buf;   // the batch's records, as in the file
     std::vector<RecMeta> rec;
+    fadegpu_ctx *ctx = nullptr; // the GPU this slot's batches go to
     fadegpu_batch *bt = nullptr;
     fadegpu_batch_view v{};
     bool in_flight = false;
@@ -268,7 +270,8 @@ struct Slot {
 
 struct Job {
     fadegpu_params prm;
-    int device = 0;
+    int device = 0;             // first device
+    int n_gpus = 1;             // devices device .. device + n_gpus - 1, batches dealt round-robin
     int64_t batch_n = 1 << 20;
     int con = 0;                // util.d:65-76: 0 SAM, 1 uBAM, 2 BAM
     std::string cl, version;
@@ -441,23 +444,39 @@ inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, cons
     }
     fadegpu_params prm = job.prm;
     prm.flags |= FADEGPU_F_NO_SCATTER;
-    fadegpu_ctx *ctx = nullptr;
-    if (fadegpu_create(job.device, &prm, &ctx) != 0) { fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(nullptr)); return 1; }
-    if (!hdr.names.empty() &&
-        fadegpu_load_reference(ctx, (int32_t)hdr.names.size(), cnames.data(), hdr.lens.data(), cseqs.data()) != 0) {
-        fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(ctx));
+    // One ctx (and its submit thread) per GPU; the reference is packed and uploaded once and copied GPU to GPU
+    // (NVLink peer copy) to the others: every GPU holds its own copy, reads are independent, nothing is exchanged
+    // on the data path.  The reference's merge is its mutex-guarded writer (anno.d:47-49); here the one writer
+    // below emits the batches in input order.
+    int n_dev = 0;
+    if (fadegpu_device_count(&n_dev) != 0 || job.device < 0 || job.device + job.n_gpus > n_dev) {
+        fprintf(stderr, "fade-b200: --device %d --gpus %d asks for devices this machine does not have (%d visible)\n", job.device, job.n_gpus, n_dev);
         return 1;
     }
+    std::vector<fadegpu_ctx *> ctxs((size_t)job.n_gpus, nullptr);
+    const double t_ref0 = omp_get_wtime();
+    for (int g = 0; g < job.n_gpus; ++g) {
+        if (fadegpu_create(job.device + g, &prm, &ctxs[(size_t)g]) != 0) { fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(nullptr)); return 1; }
+        if (hdr.names.empty()) continue;
+        const int rc = g == 0 ? fadegpu_load_reference(ctxs[0], (int32_t)hdr.names.size(), cnames.data(), hdr.lens.data(), cseqs.data())
+                              : fadegpu_share_reference(ctxs[(size_t)g], ctxs[0]);
+        if (rc != 0) { fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(ctxs[(size_t)g])); return 1; }
+    }
+    const double t_ref = omp_get_wtime() - t_ref0;
     fasta.clear();
 
     const int64_t max_seq = job.batch_n * 160;
-    Slot slot[2];
-    for (auto &s : slot)
-        if (fadegpu_alloc_batch(ctx, job.batch_n, max_seq, &s.bt) != 0 || fadegpu_get_batch_view(s.bt, &s.v) != 0) {
-            fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(ctx));
+    const int n_slots = 2 * job.n_gpus;          // two batches per GPU: one computing, one being read / written
+    std::vector<Slot> slot((size_t)n_slots);
+    for (int i = 0; i < n_slots; ++i) {
+        Slot &s = slot[(size_t)i];
+        s.ctx = ctxs[(size_t)(i % job.n_gpus)];
+        if (fadegpu_alloc_batch(s.ctx, job.batch_n, max_seq, &s.bt) != 0 || fadegpu_get_batch_view(s.bt, &s.v) != 0) {
+            fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(s.ctx));
             return 1;
         }
-    long long n_total = 0, n_art = 0, n_sc = 0;
+    }
+    long long n_total = 0, n_art = 0, n_sc = 0, n_oversize = 0;
     int rc_all = 0;
     double t_read = 0, t_parse = 0, t_wait = 0, t_tag = 0, t_write = 0;   // FADE_TIMING=1 prints them
     const double t_start = omp_get_wtime();
@@ -472,7 +491,12 @@ inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, cons
             const uint32_t bs = get_u32(&stream[spos]);
             if (bs < 32 || !need(4 + (size_t)bs)) { if (!source_bad()) fprintf(stderr, "fade-b200: truncated BAM record\n"); rc_all = 1; break; }
             const int32_t l_seq = get_i32(&stream[spos + 4 + 16]);
-            if (l_seq < 0) { fprintf(stderr, "fade-b200: damaged BAM record\n"); rc_all = 1; break; }
+            {   // the variable-length fields must fit the record (64-bit arithmetic: the sizes come from the file)
+                const uint64_t l_name = stream[spos + 4 + 8], n_cig = get_u16(&stream[spos + 4 + 12]);
+                if (l_seq < 0 || 32 + l_name + 4 * n_cig + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq > (uint64_t)bs) {
+                    fprintf(stderr, "fade-b200: damaged BAM record\n"); rc_all = 1; break;
+                }
+            }
             if (seq_bytes + (l_seq + 1) / 2 + 1024 > max_seq) {
                 if (s.rec.empty()) { fprintf(stderr, "fade-b200: a read of %d bases does not fit a batch (raise --batch)\n", l_seq); rc_all = 1; }
                 break;
@@ -494,10 +518,9 @@ inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, cons
         fadegpu_batch_view &v = s.v;
         int64_t off = 0;
         for (long k = 0; k < n; ++k) {   // offsets of the bases inside the view
-            v.seq_off[k] = off;
+            v.meta[k].seq_off = (uint32_t)off;
             off += (get_i32(&s.buf[s.rec[(size_t)k].off + 4 + 16]) + 1) / 2;
         }
-        v.seq_off[n] = off;
         int bad = 0;
 #pragma omp parallel for schedule(static) reduction(| : bad) num_threads(threads)
         for (long k = 0; k < n; ++k) {
@@ -523,12 +546,15 @@ inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, cons
             hr.flag = (int32_t)flag; hr.has_sa = has_sa; hr.cigar = cg; hr.n_cigar = (int32_t)n_cig;
             hr.seq4 = seq; hr.qual = qual; hr.l_qseq = l_seq; hr.tid = get_i32(p); hr.pos = get_i32(p + 4);
             fadehost_prepare(&hr, &m.aligned_len, &m.clip_left, &m.clip_right, &m.rs_base);   // anno.d:61-74
-            memcpy(v.seq4 + v.seq_off[k], seq, (size_t)(l_seq + 1) / 2);
-            v.l_qseq[k] = l_seq; v.tid[k] = hr.tid; v.pos[k] = hr.pos;
-            v.aligned_len[k] = m.aligned_len; v.clip_left[k] = m.clip_left; v.clip_right[k] = m.clip_right;
+            // the compact layout of the batch: one gate byte + one 32-byte record per read, bases as they are in the file
+            fadegpu_read_meta &mm = v.meta[k];
+            memcpy(v.seq4 + mm.seq_off, seq, (size_t)(l_seq + 1) / 2);
+            mm.pos = hr.pos; mm.l_qseq = l_seq; mm.tid = hr.tid; mm.aligned_len = m.aligned_len;
+            mm.clip_left = (uint32_t)m.clip_left; mm.clip_right = (uint32_t)m.clip_right;
+            v.gate[k] = (uint8_t)std::min<uint32_t>(255u, std::max(mm.clip_left, mm.clip_right));
         }
         if (bad) { fprintf(stderr, "fade-b200: damaged BAM record\n"); rc_all = 1; return false; }
-        if (fadegpu_submit(ctx, s.bt, n) != 0) { fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(ctx)); rc_all = 1; return false; }
+        if (fadegpu_submit_compact(s.ctx, s.bt, n, off) != 0) { fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(s.ctx)); rc_all = 1; return false; }
         t_parse += omp_get_wtime() - t0;
         s.in_flight = true;
         return true;
@@ -539,9 +565,13 @@ inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, cons
         s.in_flight = false;
         fadegpu_results_view rv;
         double t0 = omp_get_wtime();
-        if (fadegpu_wait(ctx, s.bt) != 0 || fadegpu_get_results(s.bt, &rv) != 0) {
-            fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(ctx));
+        if (fadegpu_wait(s.ctx, s.bt) != 0 || fadegpu_get_results(s.bt, &rv) != 0) {
+            fprintf(stderr, "fade-b200: %s\n", fadegpu_last_error(s.ctx));
             return false;
+        }
+        {
+            fadegpu_stats st;
+            if (fadegpu_get_stats(s.bt, &st) == 0) n_oversize += st.n_oversize;
         }
         t_wait += omp_get_wtime() - t0; t0 = omp_get_wtime();
         const long n = (long)s.rec.size();
@@ -620,24 +650,33 @@ inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, cons
         return true;
     };
 
-    // anno.d:44-50, batched and double-buffered: the GPU works on one slot while the host reads the other
+    // anno.d:44-50, batched: the slots form a ring that is filled in order (slot i goes to GPU i mod N) and emitted in
+    // the same order, so the records keep their input order; a slot is emitted only when the ring wraps around to
+    // the one before it, i.e. every GPU always has one batch computing while the host reads and writes others
     int cur = 0;
     for (;;) {
-        const bool got = load(slot[cur]);
-        Slot &prev = slot[cur ^ 1];
-        if (prev.in_flight && !emit(prev)) { rc_all = 1; break; }
+        const bool got = load(slot[(size_t)cur]);
+        Slot &oldest = slot[(size_t)((cur + 1) % n_slots)];
+        if (oldest.in_flight && !emit(oldest)) { rc_all = 1; break; }
         if (!got) break;
-        cur ^= 1;
+        cur = (cur + 1) % n_slots;
     }
-    for (auto &s : slot) if (s.in_flight && rc_all == 0 && !emit(s)) rc_all = 1;
+    for (int k = 1; k <= n_slots && rc_all == 0; ++k) {      // drain in ring order, oldest first
+        Slot &s = slot[(size_t)((cur + k) % n_slots)];
+        if (s.in_flight && !emit(s)) rc_all = 1;
+    }
     if (job.con != 0 && rc_all == 0) write_eof_marker();
     fflush(stdout);
     fprintf(stderr, "[fade-b200 annotate] %lld records, %lld soft-clipped, %lld with artifact tags\n", n_total, n_sc, n_art);
+    if (n_oversize)
+        fprintf(stderr, "[W::fade-b200 annotate] %lld reads were NOT realigned: their window exceeds 2^31 DP cells (rs lacks the artifact bits for them)\n",
+                n_oversize);
     if (getenv("FADE_TIMING"))
-        fprintf(stderr, "[fade-b200 annotate] %d threads; record loop %.3f s: inflate+split %.3f, parse+fill+submit %.3f, wait for GPU %.3f, "
-                        "tag %.3f, deflate+write %.3f\n", threads, omp_get_wtime() - t_start, t_read, t_parse, t_wait, t_tag, t_write);
-    for (auto &s : slot) { if (s.in_flight) fadegpu_wait(ctx, s.bt); fadegpu_free_batch(s.bt); }
-    fadegpu_destroy(ctx);
+        fprintf(stderr, "[fade-b200 annotate] %d threads, %d GPU(s); reference to the GPUs %.3f s; record loop %.3f s: inflate+split %.3f, "
+                        "parse+fill+submit %.3f, wait for GPU %.3f, tag %.3f, deflate+write %.3f\n", threads, job.n_gpus, t_ref,
+                omp_get_wtime() - t_start, t_read, t_parse, t_wait, t_tag, t_write);
+    for (auto &s : slot) { if (s.in_flight) fadegpu_wait(s.ctx, s.bt); fadegpu_free_batch(s.bt); }
+    for (auto *cx : ctxs) fadegpu_destroy(cx);
     return rc_all;
 }
 

@@ -37,12 +37,63 @@ bool out_line(const std::string &l)
     return false;
 }
 
-// -b / --bam, -u / --ubam as in app.d:82-83,94 (con = bam << 1 | ubam)
-bool output_flag(const std::string &a, int &con)
+// Command-line options the way std.getopt with config.bundling reads them in the reference (app.d:73-107):
+// short flags may be bundled (-cb), a value may be attached (-t4, -t=4, --threads=4) or follow (-t 4,
+// --threads 4), "--" ends the options, "-" is a positional (stdin), and an unknown option is an error.
+struct OptSpec { char s; const char *l; bool value; };
+struct Options {
+    std::map<std::string, std::string> val;   // by long name; flags map to "1"
+    std::vector<std::string> pos;
+    bool ok = true;
+    bool has(const char *l) const { return val.count(l) != 0; }
+    long long num(const char *l, long long dflt) const { auto it = val.find(l); return it == val.end() ? dflt : atoll(it->second.c_str()); }
+};
+
+Options parse_options(int argc, char **argv, int first, const std::vector<OptSpec> &spec)
 {
-    if (a == "-b" || a == "--bam") { con |= 2; return true; }
-    if (a == "-u" || a == "--ubam") { con |= 1; return true; }
-    return false;
+    Options o;
+    auto by_long = [&](const std::string &l) -> const OptSpec * { for (auto &x : spec) if (l == x.l) return &x; return nullptr; };
+    auto by_short = [&](char c) -> const OptSpec * { for (auto &x : spec) if (x.s && x.s == c) return &x; return nullptr; };
+    auto bad = [&](const std::string &what) { fprintf(stderr, "fade-b200: %s\n", what.c_str()); o.ok = false; };
+    bool opts_done = false;
+    for (int i = first; i < argc && o.ok; ++i) {
+        const std::string a = argv[i];
+        if (opts_done || a == "-" || a.empty() || a[0] != '-') { o.pos.push_back(a); continue; }
+        if (a == "--") { opts_done = true; continue; }
+        if (a[1] == '-') {
+            const size_t eq = a.find('=');
+            const std::string name = a.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+            const OptSpec *sp = by_long(name);
+            if (!sp) { bad("unrecognized option --" + name); break; }
+            if (!sp->value) { if (eq != std::string::npos) bad("option --" + name + " takes no value"); else o.val[sp->l] = "1"; continue; }
+            if (eq != std::string::npos) o.val[sp->l] = a.substr(eq + 1);
+            else if (i + 1 < argc) o.val[sp->l] = argv[++i];
+            else bad("missing value for --" + name);
+            continue;
+        }
+        for (size_t k = 1; k < a.size() && o.ok; ++k) {   // a bundle of short options
+            const OptSpec *sp = by_short(a[k]);
+            if (!sp) { bad(std::string("unrecognized option -") + a[k]); break; }
+            if (!sp->value) { o.val[sp->l] = "1"; continue; }
+            std::string v = a.substr(k + 1);
+            if (!v.empty() && v[0] == '=') v.erase(0, 1);
+            if (v.empty()) {
+                if (i + 1 < argc) v = argv[++i];
+                else { bad(std::string("missing value for -") + a[k]); break; }
+            }
+            o.val[sp->l] = v;
+            break;
+        }
+    }
+    return o;
+}
+
+// -b / --bam, -u / --ubam as in app.d:82-83,94 (con = bam << 1 | ubam); false (with a message) when both are given
+bool output_container(const Options &o, int &con)
+{
+    con = (o.has("bam") ? 2 : 0) | (o.has("ubam") ? 1 : 0);
+    if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return false; }
+    return true;
 }
 
 void open_output(int con)
@@ -173,7 +224,10 @@ int usage()
             "      --min-length N   minimum soft-clip length considered (default 5)\n"
             "  -w, --window-size N  bases considered outside of the read region (default 300)\n"
             "      --batch N        records per GPU batch (default 1048576)\n"
-            "      --device N       CUDA device (default 0)\n");
+            "      --device N       first CUDA device (default 0)\n"
+            "      --gpus N         GPUs: batches are dealt round-robin to devices N0..N0+N-1, every GPU holds the reference\n"
+            "                       (packed once, copied GPU to GPU), the records keep their input order (default 1)\n"
+            "options may be bundled (-cb) and written --name=value, as in fade\n");
     return 0;
 }
 
@@ -183,28 +237,22 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
 {
     fadegpu_params prm;
     fadegpu_default_params(&prm);
-    int64_t batch_n = 1 << 20;
-    int device = 0, con = 0;
-    bool text_path = false;
-    std::vector<std::string> pos_args;
-    for (int i = 2; i < argc; ++i) {
-        const std::string a = argv[i];
-        auto need = [&](const char *what) -> const char * {
-            if (i + 1 >= argc) { fprintf(stderr, "fade-b200: %s needs a value\n", what); exit(1); }
-            return argv[++i];
-        };
-        if (a == "-t" || a == "--threads") prm.host_threads = atoi(need("--threads"));
-        else if (a == "--min-length") prm.min_length = atoi(need("--min-length"));
-        else if (a == "-w" || a == "--window-size") prm.window_size = atoi(need("--window-size"));
-        else if (a == "--batch") batch_n = atoll(need("--batch"));
-        else if (a == "--device") device = atoi(need("--device"));
-        else if (a == "--text-path") text_path = true;   // the line-by-line SAM text loop (A/B check of bamfast.hpp)
-        else if (a == "-h" || a == "--help") return usage();
-        else if (output_flag(a, con)) {}
-        else pos_args.push_back(a);
-    }
-    if (pos_args.size() < 2) { usage(); return 0; }
-    if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    const Options opt = parse_options(argc, argv, 2, { { 't', "threads", true }, { 0, "min-length", true }, { 'w', "window-size", true },
+                                                      { 0, "batch", true }, { 0, "device", true }, { 0, "gpus", true }, { 0, "text-path", false },
+                                                      { 'h', "help", false }, { 'b', "bam", false }, { 'u', "ubam", false } });
+    if (!opt.ok) { usage(); return 1; }
+    if (opt.has("help")) return usage();
+    prm.host_threads = (int32_t)opt.num("threads", prm.host_threads);
+    prm.min_length = (int32_t)opt.num("min-length", prm.min_length);
+    prm.window_size = (int32_t)opt.num("window-size", prm.window_size);
+    const int64_t batch_n = opt.num("batch", 1 << 20);
+    const int device = (int)opt.num("device", 0), n_gpus = (int)opt.num("gpus", 1);
+    const bool text_path = opt.has("text-path");   // the line-by-line SAM text loop (A/B check of bamfast.hpp)
+    const std::vector<std::string> &pos_args = opt.pos;
+    int con = 0;
+    if (pos_args.size() != 2) { usage(); return pos_args.empty() ? 0 : 1; }
+    if (!output_container(opt, con)) return 1;
+    if (batch_n <= 0 || n_gpus < 1 || (text_path && n_gpus != 1)) { fprintf(stderr, "fade-b200: bad --batch / --gpus\n"); return 1; }
     fprintf(stderr, "[W::fade annotate] Output will keep the input order\n");
 
     FILE *fin_raw = pos_args[0] == "-" ? stdin : fopen(pos_args[0].c_str(), "rb");
@@ -216,7 +264,7 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
         // --text-path keeps the first, line-by-line implementation below (A/B check)
         const bool is_bam = pre.size() == 2 && (uint8_t)pre[0] == 0x1f && (uint8_t)pre[1] == 0x8b;
         bamfast::Job job;
-        job.prm = prm; job.device = device; job.batch_n = batch_n; job.con = con; job.cl = cl; job.version = kVersion;
+        job.prm = prm; job.device = device; job.n_gpus = n_gpus; job.batch_n = batch_n; job.con = con; job.cl = cl; job.version = kVersion;
         job.fasta_path = pos_args[1];
         return bamfast::annotate_records(fin_raw, pre, is_bam, job, read_fasta);
     }
@@ -366,9 +414,13 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
             hr.flag = r.flag; hr.has_sa = r.has_sa; hr.cigar = r.cigar.data(); hr.n_cigar = (int32_t)r.cigar.size();
             hr.seq4 = r.seq4.data(); hr.qual = r.qual.data(); hr.l_qseq = r.l_qseq; hr.tid = r.tid; hr.pos = r.pos;
             fadehost_prepare(&hr, &r.aligned_len, &r.clip_left, &r.clip_right, &r.rs_base);   // anno.d:61-74
-            seq_bytes += (int64_t)r.seq4.size();
+            // the bases must fit the pinned view: flush BEFORE a record that would not, refuse one that never can
+            const int64_t nb = (int64_t)r.seq4.size();
+            if (nb > max_seq) { fprintf(stderr, "fade-b200: a read of %d bases does not fit a batch (raise --batch)\n", r.l_qseq); return 1; }
+            if (seq_bytes + nb > max_seq) { if (flush()) return 1; seq_bytes = 0; }
+            seq_bytes += nb;
             recs.push_back(std::move(r));
-            if ((int64_t)recs.size() == batch_n || seq_bytes + 1024 > max_seq) { if (flush()) return 1; seq_bytes = 0; }
+            if ((int64_t)recs.size() == batch_n) { if (flush()) return 1; seq_bytes = 0; }
         }
         have_line = in->getline(line);
     }
@@ -576,24 +628,21 @@ int rs_of(const SamRec &r, bool &have)
 
 int cmd_out(int argc, char **argv, const std::string &cl)
 {
-    bool clip = false;
+    const Options opt = parse_options(argc, argv, 2, { { 'c', "clip", false }, { 't', "threads", true }, { 'h', "help", false },
+                                                      { 'b', "bam", false }, { 'u', "ubam", false } });
+    if (!opt.ok || opt.pos.size() > 1) { usage(); return 1; }
+    if (opt.has("help") || opt.pos.empty()) return usage();
+    const bool clip = opt.has("clip");
+    const std::string path = opt.pos[0];
     int con = 0;
-    std::string path;
-    for (int i = 2; i < argc; ++i) {
-        const std::string a = argv[i];
-        if (a == "-c" || a == "--clip") clip = true;
-        else if (a == "-t" || a == "--threads") ++i;
-        else if (output_flag(a, con)) {}
-        else path = a;
-    }
-    if (path.empty()) return usage();
-    if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    if (!output_container(opt, con)) return 1;
     open_output(con);
     Sam sam;
     if (!sam.open(path)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
     write_header(sam, "fade-extract", cl);   // sic: filter.d:173 uses the ID of extract
     OutStats st;
-    auto put = [](const SamRec &r) { out_line(r.line()); };
+    bool put_failed = false;
+    auto put = [&put_failed](const SamRec &r) { if (!out_line(r.line())) put_failed = true; };
     int rc = 0;
     SamRec r;
     if (clip) {   // filter.d:182-208
@@ -650,21 +699,18 @@ int cmd_out(int argc, char **argv, const std::string &cl)
     if (rc < 0) { fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str()); return 1; }
     st.print();
     g_out->close();
-    return 0;
+    return put_failed ? 1 : 0;   // a record that cannot be encoded for the chosen container is an error, not a silent drop
 }
 
 int cmd_extract(int argc, char **argv, const std::string &cl)
 {
+    const Options opt = parse_options(argc, argv, 2, { { 't', "threads", true }, { 'h', "help", false }, { 'b', "bam", false },
+                                                      { 'u', "ubam", false } });
+    if (!opt.ok || opt.pos.size() > 1) { usage(); return 1; }
+    if (opt.has("help") || opt.pos.empty()) return usage();
+    const std::string path = opt.pos[0];
     int con = 0;
-    std::string path;
-    for (int i = 2; i < argc; ++i) {
-        const std::string a = argv[i];
-        if (a == "-t" || a == "--threads") ++i;
-        else if (output_flag(a, con)) {}
-        else path = a;
-    }
-    if (path.empty()) return usage();
-    if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    if (!output_container(opt, con)) return 1;
     open_output(con);
     Sam sam;
     if (!sam.open(path)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
@@ -705,18 +751,15 @@ int cmd_extract(int argc, char **argv, const std::string &cl)
 // then first-of-pair before second-of-pair (FLAG & 0xC0), then input order.  In memory.
 int cmd_sort(int argc, char **argv)
 {
-    int con = 0;
-    bool by_name = false;
-    std::string path;
-    for (int i = 2; i < argc; ++i) {
-        const std::string a = argv[i];
-        if (output_flag(a, con)) {}
-        else if (a == "-n") by_name = true;
-        else if (a == "-t" || a == "--threads") ++i;
-        else path = a;
+    const Options opt = parse_options(argc, argv, 2, { { 'n', "name", false }, { 't', "threads", true }, { 'b', "bam", false },
+                                                      { 'u', "ubam", false } });
+    if (!opt.ok || opt.pos.size() != 1 || !opt.has("name")) {
+        fprintf(stderr, "usage: fade-b200 sort -n [-b|-u] <SAM/BAM or ->   (only name order is implemented)\n");
+        return 1;
     }
-    if (path.empty() || !by_name) { fprintf(stderr, "usage: fade-b200 sort -n [-b|-u] <SAM/BAM or ->   (only name order is implemented)\n"); return 1; }
-    if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    const std::string path = opt.pos[0];
+    int con = 0;
+    if (!output_container(opt, con)) return 1;
     open_output(con);
     Sam sam;
     if (!sam.open(path)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
@@ -763,18 +806,15 @@ int cmd_fasta_digest(int argc, char **argv)
 // format conversion only: every header line and record, unchanged (SAM <-> BAM)
 int cmd_view(int argc, char **argv)
 {
-    int con = 0, threads = 0;
-    bool bulk = false;
-    std::string path;
-    for (int i = 2; i < argc; ++i) {
-        const std::string a = argv[i];
-        if (output_flag(a, con)) {}
-        else if (a == "--bulk") bulk = true;      // through the parallel readers / writers of the annotate loop
-        else if ((a == "-t" || a == "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
-        else path = a;
-    }
-    if (path.empty()) return usage();
-    if (con > 2) { fprintf(stderr, "fade-b200: -b and -u are exclusive\n"); return 1; }
+    const Options opt = parse_options(argc, argv, 2, { { 0, "bulk", false }, { 't', "threads", true }, { 'h', "help", false },
+                                                      { 'b', "bam", false }, { 'u', "ubam", false } });
+    if (!opt.ok || opt.pos.size() > 1) { usage(); return 1; }
+    if (opt.has("help") || opt.pos.empty()) return usage();
+    const std::string path = opt.pos[0];
+    const int threads = (int)opt.num("threads", 0);
+    const bool bulk = opt.has("bulk");      // through the parallel readers / writers of the annotate loop
+    int con = 0;
+    if (!output_container(opt, con)) return 1;
     if (bulk) {
         FILE *f = path == "-" ? stdin : fopen(path.c_str(), "rb");
         if (!f) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }

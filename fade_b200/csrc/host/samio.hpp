@@ -80,6 +80,7 @@ private:
             std::vector<uint8_t> cdata((size_t)clen + 8);
             if (!raw_read(cdata.data(), (size_t)clen + 8)) { bad_ = true; return false; }
             const uint32_t crc = get_u32(&cdata[(size_t)clen]), isize = get_u32(&cdata[(size_t)clen + 4]);
+            if (isize > 0x10000) { bad_ = true; return false; }   // SAMv1 4.1: a block inflates to at most 64 KiB
             blk_.resize(isize);
             pos_ = 0;
             if (isize) {

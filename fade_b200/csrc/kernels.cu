@@ -12,6 +12,12 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// Footprint of the helper kernels that run UNDER a fill (binning of the next batch, traceback bookkeeping):
+// 128 threads x <= 32 registers = 4096 registers, exactly what five resident fill blocks (5 x 128 x 96) leave
+// free on an SM, so one such block per SM is resident at once without waiting for a fill block to retire.
+#define FADE_SMALL_KERNEL __launch_bounds__(128, 16)
+
+
 // Stage one pair: target selector words (window gather from the packed reference,
 // source/analysis.d:45-64) into shared memory, query selector words (reverse complement of the
 // BAM 4-bit bases, source/util.d:18-34) into registers.  `wild` gets bit0/bit1 when alignment
@@ -143,7 +149,7 @@ struct GlobalAcc {
 };
 
 template <int R>
-__global__ void __launch_bounds__(128) trace_init_kernel(const KernelArgs a)
+__global__ void FADE_SMALL_KERNEL trace_init_kernel(const KernelArgs a)
 {
     for (int aln = blockIdx.x * blockDim.x + threadIdx.x; aln < a.n_aln; aln += gridDim.x * blockDim.x) {
         a.out[aln].read = -1;              // "no result yet": fadegpu_wait refuses such a record
@@ -508,7 +514,7 @@ __device__ __forceinline__ void advance_round(const KernelArgs &a, int round, un
 }
 
 template <int R>
-__global__ void __launch_bounds__(128) trace_advance_kernel(const KernelArgs a)
+__global__ void FADE_SMALL_KERNEL trace_advance_kernel(const KernelArgs a)
 {
     __shared__ AdvanceSmem adv[4];
     advance_round<R>(a, a.round, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5), adv);
@@ -696,15 +702,39 @@ __global__ void __launch_bounds__(128) sw_generic_kernel(const GenericArgs a)
 // host path evaluates while building descriptors -- length floor (analysis.d:34), window
 // arithmetic (analysis.d:45-59) -- plus the length binning, without touching host cores
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bin_classify_kernel(const BinArgs a)
+__global__ void FADE_SMALL_KERNEL bin_classify_kernel(const BinArgs a)
 {
     const uint32_t floor_u = (uint32_t)a.min_length;   // uint <= int compare of analysis.d:34
     unsigned long long cells = 0, bad = 0;
-    int qmax = 0, tmax = 0, qmax_g = 0, tmax_g = 0, cnt = 0;
+    int qmax = 0, tmax = 0, qmax_g = 0, tmax_g = 0, cnt = 0, fetched = 0;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (int64_t)gridDim.x * blockDim.x) {
         int key = -1;
-        const uint32_t cl = (uint32_t)a.clip_left[r], cr = (uint32_t)a.clip_right[r];
-        const bool need = (cl != 0 && !(cl <= floor_u)) || (cr != 0 && !(cr <= floor_u));
+        uint32_t cl, cr;
+        bool need;
+        if (a.gate) {
+            // compact inputs: gate = min(255, max clip).  Below 255 it decides the floor exactly; at 255 (or with a
+            // floor of 255 and more) the record itself does.
+            const uint32_t g = a.gate[r];
+            need = floor_u < 255u ? g > floor_u : g == 255u;
+            cl = cr = 0;
+            if (need) {
+                const uint4 m0 = a.host_meta[2 * r], m1 = a.host_meta[2 * r + 1];   // one 32-byte PCIe read
+                ++fetched;
+                a.pos[r] = (int64_t)(((unsigned long long)m0.y << 32) | m0.x);
+                a.seq_off[r] = (int64_t)m0.z;
+                a.l_qseq[r] = (int32_t)m0.w;
+                a.tid[r] = (int32_t)m1.x;
+                a.aligned_len[r] = (int32_t)m1.y;
+                a.clip_left[r] = (int32_t)(cl = m1.z);
+                a.clip_right[r] = (int32_t)(cr = m1.w);
+                need = (cl != 0 && !(cl <= floor_u)) || (cr != 0 && !(cr <= floor_u));
+            } else {
+                a.clip_left[r] = 0; a.clip_right[r] = 0;   // so that a replay from the device mirrors skips the read as well
+            }
+        } else {
+            cl = (uint32_t)a.clip_left[r]; cr = (uint32_t)a.clip_right[r];
+            need = (cl != 0 && !(cl <= floor_u)) || (cr != 0 && !(cr <= floor_u));
+        }
         if (need) {
             const int tid = a.tid[r], ql = a.l_qseq[r];
             if (tid >= 0 && tid < a.n_contigs && ql > 0) {
@@ -716,8 +746,12 @@ __global__ void __launch_bounds__(256) bin_classify_kernel(const BinArgs a)
                     int64_t end = a.pos[r] + (int64_t)a.aligned_len[r] + a.window;
                     if (end > a.clen[tid]) end = a.clen[tid];
                     if (end > start) {
-                        if (end - start > 0x7fffffff || (end - start) * (int64_t)ql > ((int64_t)1 << 31)) bad |= 2ull;
-                        else {
+                        if (end - start > 0x7fffffff || (end - start) * (int64_t)ql > ((int64_t)1 << 31)) {
+                            // a window of more than 2^31 DP cells (a spliced record spanning megabases): the read is left
+                            // unaligned and reported, the batch goes on
+                            const unsigned long long slot = atomicAdd(&a.stats[11], 1ull);
+                            if (slot < (unsigned long long)OVER_CAP) a.over_list[slot] = a.read ? a.read[r] : (int32_t)r;
+                        } else {
                             const int tl = (int)(end - start);
                             const int rk = bin_rank(ql, tl, (a.flags & 1u) != 0);
                             key = bin_key(rk, tl);
@@ -741,6 +775,7 @@ __global__ void __launch_bounds__(256) bin_classify_kernel(const BinArgs a)
         cells += __shfl_xor_sync(FULL, cells, o);
         bad |= __shfl_xor_sync(FULL, bad, o);
         cnt += __shfl_xor_sync(FULL, cnt, o);
+        fetched += __shfl_xor_sync(FULL, fetched, o);
         qmax = max(qmax, __shfl_xor_sync(FULL, qmax, o)); tmax = max(tmax, __shfl_xor_sync(FULL, tmax, o));
         qmax_g = max(qmax_g, __shfl_xor_sync(FULL, qmax_g, o)); tmax_g = max(tmax_g, __shfl_xor_sync(FULL, tmax_g, o));
     }
@@ -752,10 +787,11 @@ __global__ void __launch_bounds__(256) bin_classify_kernel(const BinArgs a)
         if (qmax_g) atomicMax(&a.stats[4], (unsigned long long)qmax_g);
         if (tmax_g) atomicMax(&a.stats[5], (unsigned long long)tmax_g);
         if (bad) atomicOr(&a.stats[6], bad);
+        if (fetched) atomicAdd(&a.stats[10], (unsigned long long)fetched);
     }
 }
 
-__global__ void __launch_bounds__(256) bin_scatter_kernel(const BinArgs a)
+__global__ void FADE_SMALL_KERNEL bin_scatter_kernel(const BinArgs a)
 {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (int64_t)gridDim.x * blockDim.x) {
         const int key = a.key[r];
@@ -787,7 +823,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const BinArgs a)
 // 8 lanes per alignment, one aligned uint4 each per pass, i.e. one 128-byte PCIe read per pass.
 // Only ~20 % of a batch's bases are ever needed, so the other 80 % never cross PCIe
 // and no host core touches any of them.
-__global__ void __launch_bounds__(256) seq_pull_kernel(const uint8_t *__restrict__ host_seq4, const AlnDesc *__restrict__ aln,
+__global__ void FADE_SMALL_KERNEL seq_pull_kernel(const uint8_t *__restrict__ host_seq4, const AlnDesc *__restrict__ aln,
                                                        const int64_t *__restrict__ src_off, int n_aln, uint8_t *__restrict__ dst)
 {
     const int lane = threadIdx.x & 7;
@@ -801,9 +837,11 @@ __global__ void __launch_bounds__(256) seq_pull_kernel(const uint8_t *__restrict
     }
 }
 
-// per-read flags and index into the compact results (what fadegpu_wait scatters on the host path)
-__global__ void __launch_bounds__(256) result_index_kernel(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx,
-                                                           unsigned long long *n_ok)
+// per-read flags and index into the compact results: the random stores of the scatter cost a host core milliseconds
+// per batch (the records arrive in window-length order) and the device microseconds, so they are made here and 5
+// bytes per read are copied home
+__global__ void FADE_SMALL_KERNEL result_index_kernel(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx,
+                                                      unsigned long long *n_ok)
 {
     int ok = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_aln; k += gridDim.x * blockDim.x) {
@@ -934,35 +972,36 @@ size_t trace_tile_bytes(int R)
     }
 }
 
-cudaError_t launch_bin_classify(const BinArgs &a, cudaStream_t s)
+cudaError_t launch_bin_classify(const BinArgs &a, int sm_count, cudaStream_t s)
 {
     if (a.n <= 0) return cudaSuccess;
-    const int grid = (int)std::min<int64_t>((a.n + 255) / 256, 148 * 16);
-    bin_classify_kernel<<<grid, 256, 0, s>>>(a);
+    const int grid = (int)std::min<int64_t>((a.n + 127) / 128, (int64_t)sm_count * 16);
+    bin_classify_kernel<<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bin_scatter(const BinArgs &a, cudaStream_t s)
+cudaError_t launch_bin_scatter(const BinArgs &a, int sm_count, cudaStream_t s)
 {
     if (a.n <= 0) return cudaSuccess;
-    const int grid = (int)std::min<int64_t>((a.n + 255) / 256, 148 * 16);
-    bin_scatter_kernel<<<grid, 256, 0, s>>>(a);
+    const int grid = (int)std::min<int64_t>((a.n + 127) / 128, (int64_t)sm_count * 16);
+    bin_scatter_kernel<<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_seq_pull(const uint8_t *host_seq4, const AlnDesc *aln, const int64_t *src_off, int n_aln, uint8_t *dst, cudaStream_t s)
+cudaError_t launch_seq_pull(const uint8_t *host_seq4, const AlnDesc *aln, const int64_t *src_off, int n_aln, uint8_t *dst, int sm_count,
+                            cudaStream_t s)
 {
     if (n_aln <= 0) return cudaSuccess;
-    const int grid = std::min((n_aln * 8 + 255) / 256, 148 * 16);
-    seq_pull_kernel<<<grid, 256, 0, s>>>(host_seq4, aln, src_off, n_aln, dst);
+    const int grid = std::min((n_aln * 8 + 127) / 128, sm_count * 16);
+    seq_pull_kernel<<<grid, 128, 0, s>>>(host_seq4, aln, src_off, n_aln, dst);
     return cudaGetLastError();
 }
 
 cudaError_t launch_result_index(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx, unsigned long long *n_ok,
-                                cudaStream_t s)
+                                int sm_count, cudaStream_t s)
 {
     if (n_aln <= 0) return cudaSuccess;
-    result_index_kernel<<<std::min((n_aln + 255) / 256, 148 * 8), 256, 0, s>>>(out, n_aln, n_reads, flags, ridx, n_ok);
+    result_index_kernel<<<std::min((n_aln + 127) / 128, sm_count * 16), 128, 0, s>>>(out, n_aln, n_reads, flags, ridx, n_ok);
     return cudaGetLastError();
 }
 
@@ -981,7 +1020,5 @@ cudaError_t launch_alu_peak(uint32_t *out, int iters, int blocks, int threads, c
     alu_peak_kernel<<<blocks, threads, 0, s>>>(out, iters);
     return cudaGetLastError();
 }
-
-cudaError_t configure_kernels() { return cudaSuccess; }
 
 }  // namespace fade

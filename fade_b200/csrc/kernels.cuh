@@ -87,10 +87,10 @@ struct GenericArgs {
 struct BinArgs {
     // device mirrors of the batch inputs
     const uint8_t *seq4;
-    const int64_t *seq_off;
-    const int32_t *l_qseq, *tid;
-    const int64_t *pos;
-    const int32_t *aligned_len, *clip_left, *clip_right;
+    int64_t *seq_off;
+    int32_t *l_qseq, *tid;
+    int64_t *pos;
+    int32_t *aligned_len, *clip_left, *clip_right;
     const int32_t *read;            // [n] index of each entry in the caller's batch (nullptr = identity)
     int64_t n, seq_total;
     const int64_t *clen, *coff;     // contig lengths / global base offsets
@@ -101,18 +101,26 @@ struct BinArgs {
     int32_t *tlen;                  // [n]
     int64_t *start;                 // [n] window start inside the contig
     int32_t *hist;                  // [BIN_KEYS]
-    unsigned long long *stats;      // [8] cells, n_aln, qmax_all, tmax_all, qmax_generic, tmax_generic, bad
+    unsigned long long *stats;      // [0..6] cells, n_aln, qmax_all, tmax_all, qmax_generic, tmax_generic, bad;
+                                    // [8] bytes of bases pulled, [10] records fetched (compact inputs)
     // scatter
     const int32_t *keybase;         // [BIN_KEYS] first sorted position of each key
     int32_t *cursor;                // [BIN_KEYS]
     AlnDesc *aln;
     int64_t *aln_start;
+    // compact inputs (fadegpu_submit_compact): one gate byte per read on the device, the 32-byte records stay in
+    // the caller's pinned view; the classify kernel fetches those of the reads that pass the length floor and
+    // stores their fields into the (writable) device mirrors above
+    int32_t *over_list;             // [OVER_CAP] reads whose window exceeds 2^31 DP cells (left unaligned, reported); count in stats[11]
+    const uint8_t *gate;            // [n] device copy; nullptr = the seven input arrays above are complete
+    const uint4 *host_meta;         // [2n] device-mapped address of the view's fadegpu_read_meta records
     // pull mode (the bases stay in the caller's pinned view until the GPU fetches the ones it needs)
     unsigned long long *seq_cursor; // device byte cursor into the compact sequence buffer; nullptr = seq_off is final
     int64_t *src_off;               // [n_aln] offset of each alignment's bases in the pinned view
 };
 
 constexpr int FILL_THREADS = 128;
+constexpr int OVER_CAP = 256;        // oversize reads listed per batch (all of them are counted)
 // row classes: R rows per thread x 8 threads cover reads of up to 104 / 152 / 200 / 256 / 304 bases
 constexpr int N_ROW_CLASSES = 5;
 __host__ __device__ constexpr int row_class(int k) { return k == 0 ? 13 : k == 1 ? 19 : k == 2 ? 25 : k == 3 ? 32 : 38; }
@@ -133,15 +141,15 @@ __host__ __device__ inline int bin_rank(int qlen, int tlen, bool force_generic)
     for (int k = 0; k < N_ROW_CLASSES; ++k) if (qlen <= FG * row_class(k)) return k;
     return N_ROW_CLASSES;
 }
-cudaError_t launch_bin_classify(const BinArgs &a, cudaStream_t s);
-cudaError_t launch_bin_scatter(const BinArgs &a, cudaStream_t s);
-cudaError_t launch_seq_pull(const uint8_t *host_seq4, const AlnDesc *aln, const int64_t *src_off, int n_aln, uint8_t *dst, cudaStream_t s);
+cudaError_t launch_bin_classify(const BinArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bin_scatter(const BinArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_seq_pull(const uint8_t *host_seq4, const AlnDesc *aln, const int64_t *src_off, int n_aln, uint8_t *dst, int sm_count,
+                            cudaStream_t s);
 cudaError_t launch_result_index(const AlnOut *out, int n_aln, int64_t n_reads, uint8_t *flags, int32_t *ridx, unsigned long long *n_ok,
-                                cudaStream_t s);
+                                int sm_count, cudaStream_t s);
 cudaError_t launch_fill(int R, const KernelArgs &a, cudaStream_t s);
 cudaError_t launch_trace(int R, const KernelArgs &a, cudaStream_t s, int sm_count, int *launches);
 cudaError_t launch_generic(const GenericArgs &a, int n_slots, cudaStream_t s);
 cudaError_t launch_alu_peak(uint32_t *out, int iters, int blocks, int threads, cudaStream_t s);
-cudaError_t configure_kernels();
 
 }  // namespace fade

@@ -7,8 +7,12 @@
 // fragment from (read_seed, k/2), so any sharding of the read range yields identical reads.
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <string>
+#include <vector>
+#include <zlib.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -275,6 +279,163 @@ void fadesim_reads(const fadesim_cfg *cfg, int64_t first, int64_t n, int32_t n_c
         if (has_sa) has_sa[kk] = sa ? 1 : 0;
         if (truth) truth[kk] = tr;
     }
+}
+
+
+// ---- the simulated records as a BAM file (bench.py's e2e_file leg, the C5 chain at scale, tools/) --------------
+// Same records as tests/samio.py:write_sam writes as text: QNAME r<name_base+k>, MAPQ 60, RNEXT *, NM:i:0 and, for
+// has_sa reads, the SA:Z string of that writer.  BGZF blocks are deflated side by side (zlib `level`).
+namespace {
+
+void put32(std::string &o, uint32_t v) { for (int i = 0; i < 4; ++i) o.push_back((char)(v >> (8 * i))); }
+void put16(std::string &o, uint32_t v) { o.push_back((char)(v & 0xff)); o.push_back((char)((v >> 8) & 0xff)); }
+
+int reg2bin(int64_t beg, int64_t end)   // SAMv1 5.3
+{
+    --end;
+    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+
+bool write_bgzf(FILE *f, const uint8_t *data, size_t n, int level)
+{
+    constexpr size_t kBlock = 0xff00;
+    const long nb = (long)((n + kBlock - 1) / kBlock);
+    constexpr long kGroup = 4096;
+    for (long g0 = 0; g0 < nb; g0 += kGroup) {
+        const long g1 = std::min(nb, g0 + kGroup);
+        std::vector<std::string> out((size_t)(g1 - g0));
+#pragma omp parallel for schedule(dynamic, 8)
+        for (long k = g0; k < g1; ++k) {
+            const uint8_t *src = data + (size_t)k * kBlock;
+            const size_t len = std::min(kBlock, n - (size_t)k * kBlock);
+            std::string &o = out[(size_t)(k - g0)];
+            o.resize(0x10000 + 64);
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+            zs.next_in = const_cast<uint8_t *>(src); zs.avail_in = (uInt)len;
+            zs.next_out = reinterpret_cast<uint8_t *>(&o[18]); zs.avail_out = (uInt)(o.size() - 26);
+            deflate(&zs, Z_FINISH);
+            const size_t clen = zs.total_out;
+            deflateEnd(&zs);
+            static const uint8_t head[16] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0 };
+            memcpy(&o[0], head, 16);
+            const uint32_t bsize = (uint32_t)(clen + 25);
+            o[16] = (char)(bsize & 0xff); o[17] = (char)(bsize >> 8);
+            const uint32_t crc = (uint32_t)crc32(crc32(0, nullptr, 0), src, (uInt)len);
+            for (int i = 0; i < 4; ++i) { o[18 + clen + (size_t)i] = (char)(crc >> (8 * i)); o[22 + clen + (size_t)i] = (char)((uint32_t)len >> (8 * i)); }
+            o.resize(26 + clen);
+        }
+        for (const auto &o : out) if (fwrite(o.data(), 1, o.size(), f) != o.size()) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+// returns 0, or -1 when the file cannot be written
+int fadesim_write_bam(const char *path, int32_t n_contigs, const char *const *names, const int64_t *lens, int64_t n,
+                      int32_t read_len, int64_t name_base, const uint8_t *seq4, const uint8_t *qual, const uint32_t *cigar,
+                      const int32_t *n_cigar, const int32_t *flag, const int32_t *tid, const int64_t *pos,
+                      const int32_t *aligned_len, const uint8_t *has_sa, int32_t level)
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) return -1;
+    std::string text = "@HD\tVN:1.6\tSO:unsorted\n";
+    for (int t = 0; t < n_contigs; ++t) text += std::string("@SQ\tSN:") + names[t] + "\tLN:" + std::to_string(lens[t]) + "\n";
+    text += "@PG\tID:simulator\tPN:fadesim\n";
+    std::string hdr("BAM\1", 4);
+    put32(hdr, (uint32_t)text.size());
+    hdr += text;
+    put32(hdr, (uint32_t)n_contigs);
+    for (int t = 0; t < n_contigs; ++t) {
+        put32(hdr, (uint32_t)strlen(names[t]) + 1);
+        hdr += names[t]; hdr.push_back('\0');
+        put32(hdr, (uint32_t)lens[t]);
+    }
+    bool ok = write_bgzf(f, reinterpret_cast<const uint8_t *>(hdr.data()), hdr.size(), level);
+    const std::string sa = std::string("SAZ") + names[0] + ",1,+,50M100S,60,0;";
+    const int64_t stride = (read_len + 1) / 2;
+    constexpr int64_t kChunk = 1 << 18;                     // records encoded (in parallel) and written per round
+    std::vector<std::string> part;
+    for (int64_t c0 = 0; c0 < n && ok; c0 += kChunk) {
+        const int64_t c1 = std::min(n, c0 + kChunk);
+        int T = 1;
+#ifdef _OPENMP
+        T = std::max(1, omp_get_max_threads());
+#endif
+        part.assign((size_t)T, std::string());
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+        for (int t = 0; t < T; ++t) {
+            std::string &o = part[(size_t)t];
+            char nm[32];
+            for (int64_t k = c0 + (c1 - c0) * t / T; k < c0 + (c1 - c0) * (t + 1) / T; ++k) {
+                const int ln = snprintf(nm, sizeof(nm), "r%lld", (long long)(name_base + k));
+                const int nc = n_cigar[k];
+                const size_t bs = 32 + (size_t)ln + 1 + 4u * (size_t)nc + (size_t)stride + (size_t)read_len + 4 + (has_sa[k] ? sa.size() + 1 : 0);
+                put32(o, (uint32_t)bs);
+                put32(o, (uint32_t)tid[k]);
+                put32(o, (uint32_t)pos[k]);
+                o.push_back((char)(ln + 1));
+                o.push_back((char)60);
+                const int64_t end = pos[k] + std::max<int64_t>(1, nc ? aligned_len[k] : 1);
+                put16(o, (uint32_t)reg2bin(pos[k], end));
+                put16(o, (uint32_t)nc);
+                put16(o, (uint32_t)flag[k]);
+                put32(o, (uint32_t)read_len);
+                put32(o, 0xffffffffu); put32(o, 0xffffffffu); put32(o, 0);
+                o.append(nm, (size_t)ln + 1);
+                o.append(reinterpret_cast<const char *>(cigar + 6 * k), 4u * (size_t)nc);
+                o.append(reinterpret_cast<const char *>(seq4 + stride * k), (size_t)stride);
+                o.append(reinterpret_cast<const char *>(qual + (int64_t)read_len * k), (size_t)read_len);
+                o.append("NMC", 3); o.push_back('\0');
+                if (has_sa[k]) { o += sa; o.push_back('\0'); }
+            }
+        }
+        std::string all;
+        size_t tot = 0;
+        for (const auto &p : part) tot += p.size();
+        all.reserve(tot);
+        for (const auto &p : part) all += p;
+        ok = write_bgzf(f, reinterpret_cast<const uint8_t *>(all.data()), all.size(), level);
+    }
+    static const uint8_t eof[28] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    ok = ok && fwrite(eof, 1, sizeof(eof), f) == sizeof(eof);
+    ok = (fclose(f) == 0) && ok;
+    return ok ? 0 : -1;
+}
+
+// FASTA text of the contigs, `width` bases per line (what tests/samio.py:write_fasta writes)
+int fadesim_write_fasta(const char *path, int32_t n_contigs, const char *const *names, const int64_t *lens,
+                        const uint8_t *const *seqs, int32_t width)
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) return -1;
+    bool ok = true;
+    std::string buf;
+    for (int t = 0; t < n_contigs && ok; ++t) {
+        fprintf(f, ">%s synthetic\n", names[t]);
+        const int64_t len = lens[t];
+        constexpr int64_t kPiece = 64 << 20;
+        for (int64_t a = 0; a < len && ok; a += kPiece - kPiece % width) {
+            const int64_t e = std::min(len, a + (kPiece - kPiece % width));
+            buf.clear();
+            buf.reserve((size_t)(e - a) + (size_t)((e - a) / width) + 2);
+            for (int64_t p = a; p < e; p += width) {
+                const int64_t q = std::min(e, p + width);
+                buf.append(reinterpret_cast<const char *>(seqs[t] + p), (size_t)(q - p));
+                buf.push_back('\n');
+            }
+            ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+        }
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? 0 : -1;
 }
 
 }  // extern "C"

@@ -27,7 +27,7 @@ namespace fade {
 
 constexpr int FG = 8;     // threads per group
 constexpr int FBLK = 32;  // steps per checkpoint block
-constexpr int OPS_CAP = 16;  // == FADEGPU_MAX_OPS
+constexpr int OPS_CAP = 10;  // == FADEGPU_MAX_OPS: fade rejects CIGARs of more than 10 ops (analysis.d:69)
 
 // symbol codes (P1: parasail_matrix_create("ACTGN",...) order), plus padding codes
 enum : int { C_A = 0, C_C = 1, C_T = 2, C_G = 3, C_N = 4, C_WILD = 5, C_TPAD = 6, C_QPAD = 7 };
@@ -186,10 +186,11 @@ FD uint32_t FADE_VIADDMAX_RELU(uint32_t a, uint32_t b, uint32_t c)
 //   hdiag = H[first_row-1][j-1], f_in = F[first_row][j]; returns f_out = F[first_row+R][j].
 // P2: E[i][j+1] = max(H[i][j]-o, E[i][j]-e); F[i+1][j] = max(H[i][j]-o, F[i][j]-e);
 //     H = max(0, Hdiag + s, E, F).
-// Per packed cell pair: LOP3 + PRMT (score), VIADDMNMX.RELU, VIMNMX, VIADD (H-open), 2x VIADDMNMX,
-// VIMNMX (running maximum) = 8 ALU-pipe issue units.  (Measured on B200: VIMNMX3 costs two units,
-// and moving H-open to the FMA pipe as IMAD in a biased domain needs one more max for the zero
-// floor, so neither reduces the ALU-pipe time)
+// Per packed cell pair: LOP3 + PRMT (score), VIADDMNMX.RELU, VIMNMX, VIADD (H-open), 2x VIADDMNMX and
+// half a VIMNMX3 (running maximum over two rows) = 7.5 ALU-pipe instructions, all of them issued at
+// 64 threads / clk / SM (profiles/r01_ubench_b200.txt).  Moving H-open to the FMA pipe as IMAD in a
+// biased domain needs one more max for the zero floor and does not reduce the ALU-pipe time; see
+// DESIGN.md 4.1.
 template <int R>
 FD void fill_step(uint32_t (&H)[R], uint32_t (&E)[R], const uint32_t (&qs)[R], uint32_t &M,
                   uint32_t ts, uint32_t hdiag, uint32_t f_in, uint32_t &f_out, const SwConsts &k)

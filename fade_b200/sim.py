@@ -36,6 +36,11 @@ def _l():
         L.fadesim_reads.argtypes = [C.POINTER(SimCfg), C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_void_p),
                                     C.c_void_p] + [C.c_void_p] * 14
         L.fadesim_reads.restype = None
+        L.fadesim_write_bam.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_int64, C.c_int32, C.c_int64] + \
+            [C.c_void_p] * 9 + [C.c_int32]
+        L.fadesim_write_bam.restype = C.c_int
+        L.fadesim_write_fasta.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]
+        L.fadesim_write_fasta.restype = C.c_int
         L.fadesim_set_threads.argtypes = [C.c_int]
         L.fadesim_set_threads.restype = None
         _lib = L
@@ -107,6 +112,29 @@ def make_reads(cfg: SimCfg, first: int, n: int, contigs: list[np.ndarray], with_
                        p(clip_right), p(has_sa), p(truth))
     return Reads(n, L, seq4, seq_off, l_qseq, qual, cigar, n_cigar, flag, tid, pos, aligned_len, clip_left,
                  clip_right, has_sa, truth)
+
+
+def write_bam(path: str, names: list[str], contigs: list[np.ndarray], rd: Reads, name_base: int = 0, level: int = 1):
+    """The simulated records (make_reads(..., with_records=True)) as a BGZF-compressed BAM file; the same records
+    tests/samio.py:write_sam writes as text (QNAME r<k>, MAPQ 60, NM:i:0, SA:Z for has_sa reads)."""
+    assert rd.qual is not None and rd.cigar is not None, "make_reads(..., with_records=True) needed"
+    cn = (C.c_char_p * len(names))(*[s.encode() for s in names])
+    lens = np.array([len(c) for c in contigs], dtype=np.int64)
+    cig = np.ascontiguousarray(rd.cigar, dtype=np.uint32)
+    rc = _l().fadesim_write_bam(str(path).encode(), len(names), cn, lens.ctypes.data, rd.n, rd.read_len, name_base,
+                                rd.seq4.ctypes.data, rd.qual.ctypes.data, cig.ctypes.data, rd.n_cigar.ctypes.data,
+                                rd.flag.ctypes.data, rd.tid.ctypes.data, rd.pos.ctypes.data, rd.aligned_len.ctypes.data,
+                                rd.has_sa.ctypes.data, level)
+    if rc:
+        raise OSError(f"cannot write {path}")
+
+
+def write_fasta(path: str, names: list[str], contigs: list[np.ndarray], width: int = 60):
+    cn = (C.c_char_p * len(names))(*[s.encode() for s in names])
+    lens = np.array([len(c) for c in contigs], dtype=np.int64)
+    ptrs = (C.c_void_p * len(contigs))(*[c.ctypes.data for c in contigs])
+    if _l().fadesim_write_fasta(str(path).encode(), len(names), cn, lens.ctypes.data, ptrs, width):
+        raise OSError(f"cannot write {path}")
 
 
 def config_c1():

@@ -35,8 +35,9 @@
 extern "C" {
 #endif
 
-#define FADEGPU_ABI_VERSION 1
-#define FADEGPU_MAX_OPS 16 /* CIGAR ops materialised per read (fade rejects > 10, analysis.d:69) */
+#define FADEGPU_ABI_VERSION 2
+#define FADEGPU_MAX_OPS 10 /* CIGAR ops materialised per read: fade rejects anything above 10 (analysis.d:69);
+                              n_ops always holds the full count */
 
 typedef enum {
     FADEGPU_OK = 0,
@@ -81,6 +82,8 @@ typedef struct fadegpu_params {
 #define FADEGPU_R_ART_RIGHT 4u  /* status.art_right (analysis.d:106) */
 #define FADEGPU_R_OPS_TRUNC 8u  /* n_ops > FADEGPU_MAX_OPS, only the first ones are materialised */
 #define FADEGPU_R_GENERIC 16u   /* served by the generic kernel (wildcard letters / odd sizes) */
+#define FADEGPU_R_OVERSIZE 32u  /* NOT aligned: the read's window exceeds 2^31 DP cells (a spliced record spanning
+                                   megabases); counted in fadegpu_stats.n_oversize, the batch goes on */
 
 /* Struct-of-arrays view of a batch.  Inputs are filled by the caller before fadegpu_submit;
  * outputs are valid after fadegpu_wait until the next submit of the same batch. */
@@ -107,7 +110,23 @@ typedef struct fadegpu_batch_view {
     int64_t *win_start;   /* [n] `start` of analysis.d:45-51; am POS = win_start + beg_ref */
     int32_t *n_ops;       /* [n] res.cigar.length including the S padding */
     uint32_t *ops;        /* [n * FADEGPU_MAX_OPS] BAM-encoded (len<<4|op), forward order */
+    /* ---- compact inputs (fadegpu_submit_compact): an alternative to the seven input arrays above ---- */
+    uint8_t *gate;                 /* [n] min(255, max(clip_left, clip_right)): the one byte per read that is copied
+                                      to the device for EVERY read; it decides the length floor (analysis.d:34) there */
+    struct fadegpu_read_meta *meta; /* [n] everything else about a read; the GPU fetches only the records it aligns */
 } fadegpu_batch_view;
+
+/* One read of the compact layout: 32 bytes, fetched by the GPU over PCIe as one sector, and only for
+ * the reads whose gate byte passes the length floor (about one in six in fade's workload). */
+typedef struct fadegpu_read_meta {
+    int64_t pos;          /* rec.pos, 0-based */
+    uint32_t seq_off;     /* byte offset of the read's bases inside seq4 (compact batches hold < 4 GiB of bases) */
+    int32_t l_qseq;       /* rec.length */
+    int32_t tid;          /* rec.tid */
+    int32_t aligned_len;  /* rec.cigar.alignedLength, analysis.d:53 */
+    uint32_t clip_left;   /* parse_clips(rec.cigar)[0].length, 0 = none */
+    uint32_t clip_right;  /* parse_clips(rec.cigar)[1].length */
+} fadegpu_read_meta;
 
 typedef struct fadegpu_stats {
     int64_t n_reads;          /* reads in the last submit */
@@ -124,6 +143,8 @@ typedef struct fadegpu_stats {
     float host_wait_ms;       /* wall clock of the host part of fadegpu_wait after the stream finished (scatter) */
     float host_classify_ms, host_sort_ms, host_gather_ms;   /* parts of host_submit_ms */
     int32_t host_threads;     /* threads actually used */
+    int32_t reserved;
+    int64_t n_oversize;       /* reads left unaligned because their window exceeds 2^31 DP cells (FADEGPU_R_OVERSIZE) */
 } fadegpu_stats;
 
 int fadegpu_abi_version(void);
@@ -155,6 +176,12 @@ void fadegpu_free_batch(fadegpu_batch *b);
  * of the one before.  The view's input arrays must stay untouched until fadegpu_wait, which also
  * reports any error of the batch (inconsistent seq_off, window too large, CUDA failure). */
 int fadegpu_submit(fadegpu_ctx *ctx, fadegpu_batch *b, int64_t n_reads);
+
+/* Same, for a batch whose view holds the COMPACT layout (gate[], meta[], seq4; seq_bytes = bytes of seq4 in use):
+ * one byte per read is copied to the device; the 32-byte records and the bases of the reads that pass the
+ * length floor are fetched by the GPU from the pinned view.  About 22 bytes per read cross PCIe on fade's workload
+ * instead of 51 (and 18 instead of 22 come back: 72-byte result records of the aligned reads, flags[] and the index). */
+int fadegpu_submit_compact(fadegpu_ctx *ctx, fadegpu_batch *b, int64_t n_reads, int64_t seq_bytes);
 
 /* Same, reading the inputs from caller-owned host arrays (pageable is fine: the library gathers
  * the reads that need SW into its own pinned staging before the H2D copy).  The arrays are only
@@ -196,6 +223,10 @@ int fadegpu_get_results(const fadegpu_batch *b, fadegpu_results_view *r);
  * the inputs already resident in HBM (no host work, no copies), timed with CUDA events on the ctx
  * stream.  ms_out receives the device milliseconds of `iters` passes. */
 int fadegpu_get_stats(const fadegpu_batch *b, fadegpu_stats *s);
+/* Device timeline of the batch's last submit relative to the start of `origin`'s last submit (both of the same ctx,
+ * both waited for): ms[0] start of the uploads, ms[1] inputs ready (first fill may start), ms[2] end of its kernels,
+ * ms[3] results on the host.  For pipeline diagnostics (tools/e2e_timeline.py). */
+int fadegpu_get_timeline(const fadegpu_batch *b, const fadegpu_batch *origin, float ms[4]);
 int fadegpu_replay_kernels(fadegpu_ctx *ctx, fadegpu_batch *b, int32_t iters, float *ms_out);
 /* The same over several resident batches of the ctx, queued back to back the way consecutive submits
  * queue them (the traceback rounds of one batch run under the fill of the next): device

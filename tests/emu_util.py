@@ -12,7 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU_DIR = os.path.join(ROOT, "fade_b200", "csrc", "emu")
 EMU_SO = os.path.join(EMU_DIR, "libfadeemu.so")
-OPS_CAP = 16
+OPS_CAP = 10
 
 CODE = {"A": 0, "C": 1, "T": 2, "G": 3, "N": 4}
 

@@ -28,14 +28,16 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
     assert sorted(names) == sorted(_lib.ABI_SYMBOLS)
-    assert L.fadegpu_abi_version() == 1
+    assert L.fadegpu_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Params) == 48
     assert C.sizeof(_lib.Inputs) == 8 * 8
-    assert C.sizeof(_lib.BatchView) == 8 * 19
-    assert C.sizeof(_lib.Result) == 32 + 4 * 16                      # fadegpu_result, FADEGPU_MAX_OPS == 16
+    assert C.sizeof(_lib.BatchView) == 8 * 21
+    assert api.META_DTYPE.itemsize == 32                              # fadegpu_read_meta
+    assert C.sizeof(_lib.Stats) == 120
+    assert C.sizeof(_lib.Result) == 32 + 4 * 10                      # fadegpu_result, FADEGPU_MAX_OPS == 10
     p = api.default_params()
     assert (p.window_size, p.min_length, p.gap_open, p.gap_extend, p.match, p.mismatch) == (300, 5, 10, 2, 2, -3)
 

@@ -287,9 +287,10 @@ def test_share_reference_and_concurrent_contexts():
     assert not errs, errs
 
 
-def test_long_windows_use_generic_kernel_and_absurd_ones_are_refused():
+def test_long_windows_use_generic_kernel_and_absurd_ones_are_reported():
     """spliced-style records (huge aligned_len): windows beyond the packed kernels' 4000 columns go
-    to the generic kernel on the device; a window of > 2^31 DP cells is refused with an error."""
+    to the generic kernel on the device; a window of > 2^31 DP cells leaves THAT read unaligned with
+    FADEGPU_R_OVERSIZE (counted in the stats) and the rest of the batch is served as usual."""
     rng = random.Random(31)
     contigs = [readsets.random_ref(rng, 60_000)]
     reads = readsets.ragged_reads(rng, contigs, 40, min_len=100, max_len=150)
@@ -304,15 +305,65 @@ def test_long_windows_use_generic_kernel_and_absurd_ones_are_refused():
         assert b.stats().n_generic >= 5
         b.close()
     big = [bytes(40_000_000)]
-    rd2 = readsets.build([dict(seq="ACGT" * 30, tid=0, pos=100, aligned_len=39_000_000, clip_left=20, clip_right=0)])
-    with _ctx() as ctx:
-        ctx.load_reference(["z"], big)
-        b = ctx.alloc_batch(1, 64)
-        b.fill(rd2.seq4, rd2.seq_off, rd2.l_qseq, rd2.tid, rd2.pos, rd2.aligned_len, rd2.clip_left, rd2.clip_right)
-        with pytest.raises(Exception) as e:
-            b.run()
-        assert "2^31" in str(e.value)
-        b.close()
+    rnd = random.Random(32)
+    small = [dict(seq="".join(rnd.choice("ACGT") for _ in range(120)), tid=0, pos=5000 + 10 * k, aligned_len=100, clip_left=20, clip_right=0)
+             for k in range(30)]
+    absurd = dict(seq="ACGT" * 30, tid=0, pos=100, aligned_len=39_000_000, clip_left=20, clip_right=0)
+    rd2 = readsets.build(small[:10] + [absurd] + small[10:])
+    for flags in (0, api.F_HOST_BINNING):
+        with _ctx(flags=flags) as ctx:
+            ctx.load_reference(["z"], big)
+            b = ctx.alloc_batch(rd2.n, int(rd2.seq_off[rd2.n]))
+            for path in ("view", "compact"):
+                if path == "view":
+                    b.fill(rd2.seq4, rd2.seq_off, rd2.l_qseq, rd2.tid, rd2.pos, rd2.aligned_len, rd2.clip_left, rd2.clip_right).run()
+                else:
+                    b.fill_compact(rd2.seq4, rd2.seq_off, rd2.l_qseq, rd2.tid, rd2.pos, rd2.aligned_len, rd2.clip_left, rd2.clip_right)
+                    b.submit_compact()
+                    b.wait()
+                st = b.stats()
+                assert st.n_oversize == 1 and st.n_aligned == 30
+                assert b.flags[10] == api.R_OVERSIZE and (b.flags[:10] & 1).all() and (b.flags[11:31] & 1).all()
+            b.close()
+
+
+def test_compact_inputs_equal_view_inputs_and_oracle():
+    """fadegpu_submit_compact (one gate byte per read uploaded, the 32-byte records and the bases of the reads
+    past the length floor fetched by the GPU) against fadegpu_submit and the oracle: ragged lengths, several
+    contigs, clips at / below / far above the floor (gate saturation at 255), several floors."""
+    rng = random.Random(43)
+    contigs = [readsets.random_ref(rng, n) for n in (9000, 2500, 600)]
+    reads = readsets.ragged_reads(rng, contigs, 4000, max_len=320)
+    for r in reads[:60]:          # clips beyond the gate's 8 bits
+        r["clip_left"] = rng.choice([254, 255, 256, 300])
+    rd = readsets.build(reads)
+    for min_length in (5, 0, 254, 255, 290, -1):
+        with _ctx(min_length=min_length) as ctx:
+            ctx.load_reference(["a", "b", "c"], contigs)
+            b = run_gpu(ctx, rd)
+            rec1 = b.results()[0]
+            rec1 = rec1[np.argsort(rec1["read"])].copy()
+            fl1 = b.flags[: rd.n].copy()
+            h2d_view = b.stats().h2d_bytes
+            b.fill_compact(rd.seq4, rd.seq_off, rd.l_qseq, rd.tid, rd.pos, rd.aligned_len, rd.clip_left, rd.clip_right)
+            b.submit_compact()
+            b.wait()
+            n_al = compare(b, rd, contigs, oracle_params(ctx.params))
+            rec2 = b.results()[0]
+            assert np.array_equal(rec1, rec2[np.argsort(rec2["read"])]) and np.array_equal(fl1, b.flags[: rd.n])
+            st = b.stats()
+            assert st.n_aligned == n_al
+            if min_length == 5:
+                assert n_al > 800 and st.h2d_bytes < h2d_view - 14 * rd.n      # half of the reads here pass the floor
+            if min_length == -1:
+                assert n_al == 0      # the floor compare is unsigned (analysis.d:34)
+            ms = b.replay_kernels(1)  # replays run from the device mirrors of the fetched records
+            assert ms > 0
+            b.submit_compact()
+            b.wait()
+            rec3 = b.results()[0]
+            assert np.array_equal(rec1, rec3[np.argsort(rec3["read"])])
+            b.close()
 
 
 @pytest.mark.parametrize("flags", [0, api.F_HOST_BINNING, api.F_SYNC_SUBMIT])
