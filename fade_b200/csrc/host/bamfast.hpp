@@ -363,6 +363,31 @@ inline void write_eof_marker()
     fwrite(eof, 1, sizeof(eof), stdout);   // SAMv1 4.1.2
 }
 
+// `fade-b200 view --count`: number of records (parallel inflate, nothing decoded), for checks at scale
+inline int count_records(FILE *fin, const std::string &pre, bool is_bam, int threads)
+{
+    RecordInput in(fin, pre, is_bam, threads);
+    if (!in.read_header()) return 1;
+    long long n = 0;
+    for (;;) {
+        while (in.spos + 4 <= in.stream.size()) {
+            const uint32_t bs = get_u32(&in.stream[in.spos]);
+            if (in.spos + 4 + (size_t)bs > in.stream.size()) break;
+            in.spos += 4 + (size_t)bs;
+            ++n;
+        }
+        in.stream.erase(in.stream.begin(), in.stream.begin() + (long)in.spos);
+        in.spos = 0;
+        const size_t have = in.stream.size();
+        if (!in.need(have + 1)) {
+            if (in.bad() || have) { fprintf(stderr, "fade-b200: damaged or truncated input\n"); return 1; }
+            break;
+        }
+    }
+    printf("%lld\n", n);
+    return 0;
+}
+
 // `fade-b200 view --bulk`: every record through the parallel readers and writers of the annotate loop
 // (format conversion only; exercises this file's I/O without a GPU)
 inline int copy_records(FILE *fin, const std::string &pre, bool is_bam, int con, int threads)
@@ -392,7 +417,7 @@ inline int copy_records(FILE *fin, const std::string &pre, bool is_bam, int con,
             in.stream.erase(in.stream.begin(), in.stream.begin() + (long)end);
             in.spos = 0;
         }
-        const size_t have = in.stream.size();
+        const size_t have = in.stream.size() - in.spos;   // bytes of an incomplete record (none at the end of a good file)
         if (!in.need(have + 1)) {   // nothing more to read
             if (in.bad()) { if (is_bam) fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
             if (have) { fprintf(stderr, "fade-b200: truncated BAM record\n"); return 1; }

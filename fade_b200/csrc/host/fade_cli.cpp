@@ -806,7 +806,7 @@ int cmd_fasta_digest(int argc, char **argv)
 // format conversion only: every header line and record, unchanged (SAM <-> BAM)
 int cmd_view(int argc, char **argv)
 {
-    const Options opt = parse_options(argc, argv, 2, { { 0, "bulk", false }, { 't', "threads", true }, { 'h', "help", false },
+    const Options opt = parse_options(argc, argv, 2, { { 0, "bulk", false }, { 0, "count", false }, { 't', "threads", true }, { 'h', "help", false },
                                                       { 'b', "bam", false }, { 'u', "ubam", false } });
     if (!opt.ok || opt.pos.size() > 1) { usage(); return 1; }
     if (opt.has("help") || opt.pos.empty()) return usage();
@@ -815,12 +815,13 @@ int cmd_view(int argc, char **argv)
     const bool bulk = opt.has("bulk");      // through the parallel readers / writers of the annotate loop
     int con = 0;
     if (!output_container(opt, con)) return 1;
-    if (bulk) {
+    if (bulk || opt.has("count")) {
         FILE *f = path == "-" ? stdin : fopen(path.c_str(), "rb");
         if (!f) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
         std::string pre(2, '\0');
         pre.resize(fread(&pre[0], 1, 2, f));
         const bool is_bam = pre.size() == 2 && (uint8_t)pre[0] == 0x1f && (uint8_t)pre[1] == 0x8b;
+        if (opt.has("count")) return bamfast::count_records(f, pre, is_bam, threads > 0 ? threads : omp_get_max_threads());
         return bamfast::copy_records(f, pre, is_bam, con, threads > 0 ? threads : omp_get_max_threads());
     }
     open_output(con);

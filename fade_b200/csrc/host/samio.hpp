@@ -59,46 +59,68 @@ private:
         if (got < n) got += fread(d + got, 1, n - got, f_);
         return got == n;
     }
+    // Refills blk_ with the payload of the next group of blocks (up to kGroup): the raw blocks are read in order and
+    // inflated side by side.  Empty blocks (the EOF marker) contribute nothing.
     bool next_block()
     {
-        for (;;) {   // skips empty blocks (the EOF marker)
-            uint8_t h[12];
-            if (!raw_read(h, 12)) return false;
-            if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { bad_ = true; return false; }
-            const uint32_t xlen = get_u16(h + 10);
-            std::vector<uint8_t> extra(xlen);
-            if (!raw_read(extra.data(), xlen)) { bad_ = true; return false; }
-            int64_t bsize = -1;
-            for (size_t i = 0; i + 4 <= xlen;) {
-                const uint32_t sl = get_u16(&extra[i + 2]);
-                if (extra[i] == 'B' && extra[i + 1] == 'C' && sl == 2 && i + 6 <= xlen) bsize = get_u16(&extra[i + 4]);
-                i += 4 + sl;
+        struct Raw { std::vector<uint8_t> c; uint32_t isize, crc; size_t off; };
+        for (;;) {
+            std::vector<Raw> grp;
+            size_t total = 0;
+            bool eof = false;
+            while (grp.size() < kGroup) {
+                uint8_t h[12];
+                if (!raw_read(h, 12)) { eof = true; break; }
+                if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { bad_ = true; return false; }
+                const uint32_t xlen = get_u16(h + 10);
+                std::vector<uint8_t> extra(xlen);
+                if (!raw_read(extra.data(), xlen)) { bad_ = true; return false; }
+                int64_t bsize = -1;
+                for (size_t i = 0; i + 4 <= xlen;) {
+                    const uint32_t sl = get_u16(&extra[i + 2]);
+                    if (extra[i] == 'B' && extra[i + 1] == 'C' && sl == 2 && i + 6 <= xlen) bsize = get_u16(&extra[i + 4]);
+                    i += 4 + sl;
+                }
+                if (bsize < 0) { bad_ = true; return false; }
+                const int64_t clen = bsize - xlen - 19;
+                if (clen < 0 || clen > 0x10000) { bad_ = true; return false; }
+                Raw r;
+                r.c.resize((size_t)clen + 8);
+                if (!raw_read(r.c.data(), (size_t)clen + 8)) { bad_ = true; return false; }
+                r.crc = get_u32(&r.c[(size_t)clen]);
+                r.isize = get_u32(&r.c[(size_t)clen + 4]);
+                if (r.isize > 0x10000) { bad_ = true; return false; }   // SAMv1 4.1: a block inflates to at most 64 KiB
+                r.off = total;
+                total += r.isize;
+                grp.push_back(std::move(r));
+                if (first_) break;    // the first block alone: a caller sniffing the magic should not wait for a group
             }
-            if (bsize < 0) { bad_ = true; return false; }
-            const int64_t clen = bsize - xlen - 19;
-            if (clen < 0) { bad_ = true; return false; }
-            std::vector<uint8_t> cdata((size_t)clen + 8);
-            if (!raw_read(cdata.data(), (size_t)clen + 8)) { bad_ = true; return false; }
-            const uint32_t crc = get_u32(&cdata[(size_t)clen]), isize = get_u32(&cdata[(size_t)clen + 4]);
-            if (isize > 0x10000) { bad_ = true; return false; }   // SAMv1 4.1: a block inflates to at most 64 KiB
-            blk_.resize(isize);
+            first_ = false;
+            if (grp.empty()) return false;
+            blk_.resize(total);
             pos_ = 0;
-            if (isize) {
+            int bad = 0;
+            const long ng = (long)grp.size();
+#pragma omp parallel for schedule(dynamic, 4) reduction(| : bad) if (ng > 8)
+            for (long k = 0; k < ng; ++k) {
+                const Raw &r = grp[(size_t)k];
+                if (!r.isize) continue;
                 z_stream zs;
                 memset(&zs, 0, sizeof(zs));
-                if (inflateInit2(&zs, -15) != Z_OK) { bad_ = true; return false; }
-                zs.next_in = cdata.data(); zs.avail_in = (uInt)clen;
-                zs.next_out = blk_.data(); zs.avail_out = isize;
+                if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; continue; }
+                zs.next_in = const_cast<uint8_t *>(r.c.data()); zs.avail_in = (uInt)(r.c.size() - 8);
+                zs.next_out = blk_.data() + r.off; zs.avail_out = r.isize;
                 const int rc = inflate(&zs, Z_FINISH);
                 inflateEnd(&zs);
-                if (rc != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0, nullptr, 0), blk_.data(), isize) != crc) {
-                    bad_ = true;
-                    return false;
-                }
-                return true;
+                if (rc != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0, nullptr, 0), blk_.data() + r.off, r.isize) != r.crc) bad = 1;
             }
+            if (bad) { bad_ = true; return false; }
+            if (total) return true;
+            if (eof) return false;
         }
     }
+    static constexpr size_t kGroup = 256;
+    bool first_ = true;
     FILE *f_;
     std::string raw_;
     size_t raw_pos_ = 0;
@@ -120,15 +142,18 @@ public:
             if (buf_.size() == kBlock) flush();
         }
     }
-    void flush()
+    void flush()   // closes the current block; blocks are deflated side by side, kPending at a time, and written in order
     {
         if (buf_.empty()) return;
-        emit(buf_.data(), buf_.size());
-        buf_.clear();
+        pend_.emplace_back();
+        pend_.back().swap(buf_);
+        buf_.reserve(kBlock);
+        if (pend_.size() >= kPending) drain();
     }
     void finish()   // remaining data + the 28-byte EOF marker block
     {
         flush();
+        drain();
         static const uint8_t eof[28] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
         fwrite(eof, 1, sizeof(eof), f_);   // SAMv1 4.1.2
         fflush(f_);
@@ -136,29 +161,40 @@ public:
 
 private:
     static constexpr size_t kBlock = 0xff00;
-    void emit(const uint8_t *data, size_t n)
+    static constexpr size_t kPending = 256;
+    void drain()
     {
-        uint8_t out[0x10000 + 64];
-        z_stream zs;
-        memset(&zs, 0, sizeof(zs));
-        deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
-        zs.next_in = const_cast<uint8_t *>(data); zs.avail_in = (uInt)n;
-        zs.next_out = out + 18; zs.avail_out = sizeof(out) - 18 - 8;
-        deflate(&zs, Z_FINISH);
-        const size_t clen = zs.total_out;
-        deflateEnd(&zs);
-        static const uint8_t head[16] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0 };
-        memcpy(out, head, 16);
-        const uint32_t bsize = (uint32_t)(clen + 18 + 8 - 1);
-        out[16] = (uint8_t)(bsize & 0xff); out[17] = (uint8_t)(bsize >> 8);
-        const uint32_t crc = (uint32_t)crc32(crc32(0, nullptr, 0), data, (uInt)n);
-        uint8_t *t = out + 18 + clen;
-        for (int i = 0; i < 4; ++i) { t[i] = (uint8_t)(crc >> (8 * i)); t[4 + i] = (uint8_t)((uint32_t)n >> (8 * i)); }
-        fwrite(out, 1, 18 + clen + 8, f_);
+        const long nb = (long)pend_.size();
+        if (!nb) return;
+        std::vector<std::string> out((size_t)nb);
+#pragma omp parallel for schedule(dynamic, 4) if (nb > 8)
+        for (long k = 0; k < nb; ++k) {
+            const std::vector<uint8_t> &in = pend_[(size_t)k];
+            std::string &o = out[(size_t)k];
+            o.resize(0x10000 + 64);
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+            zs.next_in = const_cast<uint8_t *>(in.data()); zs.avail_in = (uInt)in.size();
+            zs.next_out = reinterpret_cast<uint8_t *>(&o[18]); zs.avail_out = (uInt)(o.size() - 18 - 8);
+            deflate(&zs, Z_FINISH);
+            const size_t clen = zs.total_out;
+            deflateEnd(&zs);
+            static const uint8_t head[16] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0 };
+            memcpy(&o[0], head, 16);
+            const uint32_t bsize = (uint32_t)(clen + 18 + 8 - 1);
+            o[16] = (char)(bsize & 0xff); o[17] = (char)(bsize >> 8);
+            const uint32_t crc = (uint32_t)crc32(crc32(0, nullptr, 0), in.data(), (uInt)in.size());
+            for (int i = 0; i < 4; ++i) { o[18 + clen + (size_t)i] = (char)(crc >> (8 * i)); o[22 + clen + (size_t)i] = (char)((uint32_t)in.size() >> (8 * i)); }
+            o.resize(18 + clen + 8);
+        }
+        for (const auto &o : out) fwrite(o.data(), 1, o.size(), f_);
+        pend_.clear();
     }
     FILE *f_;
     int level_;
     std::vector<uint8_t> buf_;
+    std::vector<std::vector<uint8_t>> pend_;
 };
 
 // ---- header ---------------------------------------------------------------------------------

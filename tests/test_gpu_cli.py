@@ -153,3 +153,33 @@ def test_binary_bam_path_equals_text_path_on_rich_records(tmp_path):
     assert len(recs) == 3000 and all("\trs:i:" in ln for ln in recs)
     assert sum("\trs:i:1" in ln or "\trs:i:33" in ln for ln in recs) > 300          # soft-clipped reads went to the GPU
     assert not any(ln.count("\tam:Z:") > 1 or ln.count("\trs:i:") > 1 for ln in recs)   # old tags were replaced
+
+
+def test_cli_multi_gpu_equals_single_gpu(tmp_path):
+    """`fade-b200 annotate --gpus N` (one ctx per GPU, the packed reference copied GPU to GPU, batches dealt round-robin,
+    one writer emitting in input order -- the reference's merge is its mutex-guarded writer, anno.d:47-49): the same
+    records as a single GPU, in the same order."""
+    from fade_b200 import api
+    n_dev = api.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs")
+    names, contigs, cfg, _ = sim.config_c1()
+    contigs = [contigs[0][:300_000]]
+    rd = sim.make_reads(cfg, 0, 6000, contigs)
+    fa, bam = tmp_path / "ref.fa", tmp_path / "in.bam"
+    sim.write_fasta(str(fa), names, contigs)
+    sim.write_bam(str(bam), names, contigs, rd)
+
+    def run(*flags):
+        p = subprocess.run([BIN, "annotate", *flags, str(bam), str(fa)], capture_output=True)
+        assert p.returncode == 0, p.stderr.decode()
+        return [ln for ln in p.stdout.decode().splitlines() if not ln.startswith("@PG\tID:fade-annotate")]
+
+    one = run("--batch", "500")
+    assert sum("\tam:Z:" in ln for ln in one) > 200
+    for g in sorted({2, min(n_dev, 4), n_dev}):
+        assert run("--batch", "500", "--gpus", str(g)) == one, g          # 12 batches over g GPUs
+    assert run("--gpus=2") == one                                           # one batch only: the second GPU stays idle
+    assert run("--batch", "700", "--gpus", "2", "--device", str(n_dev - 2)) == one
+    p = subprocess.run([BIN, "annotate", "--gpus", str(n_dev + 1), str(bam), str(fa)], capture_output=True)
+    assert p.returncode == 1 and b"does not have" in p.stderr
