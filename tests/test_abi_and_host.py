@@ -134,3 +134,25 @@ def test_finish_reports_small_buffers():
     rc = L.fadehost_finish(C.byref(hr), b"chr1", 1, 30, 0, 120, 1 | 2, 700, 10, 2,
                            ops.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(rs_out), *bufs, 8)
     assert rc == -1 and rs_out.value == 3
+
+
+def test_d_binding_matches_the_c_abi():
+    """integration/fadegpu.d (the extern(C) binding the D host links with) cannot be compiled here; at least every
+    function it declares must be exported by the library, and the struct sizes it pins must be the C ones."""
+    import re
+    txt = open(os.path.join(ROOT, "integration", "fadegpu.d")).read()
+    L = _lib.lib()
+    fns = set(re.findall(r"\b(fade(?:gpu|host)_\w+)\s*\(", txt))
+    assert len(fns) >= 20
+    missing = [f for f in fns if not hasattr(L, f)]
+    assert not missing, missing
+    sizes = dict(re.findall(r"static assert\((\w+)\.sizeof == (\d+)\);", txt))
+    c_sizes = {"fadegpu_params": C.sizeof(_lib.Params), "fadegpu_read_meta": api.META_DTYPE.itemsize,
+               "fadegpu_batch_view": C.sizeof(_lib.BatchView), "fadegpu_result": C.sizeof(_lib.Result),
+               "fadegpu_stats": C.sizeof(_lib.Stats)}
+    assert {k: int(v) for k, v in sizes.items()} == c_sizes
+    assert f"enum FADEGPU_ABI_VERSION = {L.fadegpu_abi_version()};" in txt and f"enum FADEGPU_MAX_OPS = {api.MAX_OPS};" in txt
+    # the loop calls only what the binding declares
+    loop = open(os.path.join(ROOT, "integration", "anno.d")).read()
+    used = set(re.findall(r"\b(fade(?:gpu|host)_[a-z_]+)\s*\(", loop))
+    assert used and used <= fns, used - fns
