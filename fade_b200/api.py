@@ -258,8 +258,8 @@ class Batch:
         return s
 
     def timeline(self, origin: "Batch"):
-        """device ms of (uploads start, inputs ready, kernels done, results on the host) relative to origin's start"""
-        ms = (C.c_float * 4)()
+        """device ms of (uploads start, first fill starts, kernels done, results home, inputs ready, last fill done) relative to origin's start"""
+        ms = (C.c_float * 6)()
         self.ctx._check(lib().fadegpu_get_timeline(self._h, origin._h, ms))
         return [float(x) for x in ms]
 

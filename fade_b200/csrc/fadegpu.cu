@@ -122,7 +122,9 @@ struct fadegpu_batch {
     int64_t n_reads = 0, n_aln = 0, n_items = 0, seq_bytes = 0;
     int qmax_all = 0, tmax_all = 0;
     fadegpu_stats st{};
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };  // start, after H2D, after kernels, after D2H
+    // start of the uploads, first fill may start (compute stream), end of the kernels, results home,
+    // inputs ready (upload stream), end of the last fill
+    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     bool in_flight = false;
     // scratch for the host binning
     std::vector<std::vector<AlnTmp>> tl_aln;   // per host thread
@@ -239,7 +241,7 @@ int cls_rank(int cls)
 int class_of(const fadegpu_ctx *c, int qlen, int tlen)
 {
     if (c->p.flags & FADEGPU_F_FORCE_GENERIC) return 0;
-    if (qlen > QMAX_FAST || tlen > TMAX_FAST) return 0;
+    if (qlen > QMAX_FAST || tlen > TMAX_PACKED) return 0;
     for (int k = 0; k < N_ROW_CLASSES; ++k) if (qlen <= FG * ROW_CLASSES[k]) return ROW_CLASSES[k];
     return 0;
 }
@@ -457,6 +459,7 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
         }
     }
     if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
+    CU(c, cudaEventRecord(b->ev[5], sf));          // end of the batch's last fill (timeline diagnostics)
     // every launch ends on tstream, in launch order: its tail is the batch's
     CU(c, cudaEventRecord(b->ev_kernels, b->plan.empty() ? sf : st));
     if (launches) *launches = nl;
@@ -905,8 +908,8 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
             const int tlen = (int)(end - start);
             const int cls = class_of(c, ql, tlen);
             const int rk = cls_rank(cls);
-            // key = class rank (13, 19, 32, generic) then descending window length (generic: input order)
-            const int key = rk * (TMAX_FAST + 2) + (rk == N_ROW_CLASSES ? 0 : TMAX_FAST - tlen);
+            // key = class rank (row classes, then the generic list) then descending window length (generic: input order)
+            const int key = bin_key(rk, tlen);
             loc.push_back(AlnTmp{ start, so, (int32_t)r, tlen, cls, ql, tid, key, cl, cr });
             cells += (int64_t)ql * tlen;
         }
@@ -926,7 +929,7 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     order.resize((size_t)n_aln);
     // parallel, stable counting sort of the INDICES: per-thread histograms over the thread's own
     // (read-ordered) slice, one prefix pass over (key, thread), per-thread scatter
-    const int KEYS = (N_ROW_CLASSES + 1) * (TMAX_FAST + 2);
+    const int KEYS = BIN_KEYS;
     std::vector<int32_t> &hist = b->cnt;
     hist.resize((size_t)nthr * (size_t)(KEYS + 1));
     std::vector<int64_t> toff((size_t)nthr + 1, 0);
@@ -955,7 +958,7 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
         for (int t = 0; t < nthr; ++t) { klo = std::min(klo, kmin[(size_t)t]); khi = std::max(khi, kmax[(size_t)t]); }
         for (int rk = 0; rk <= N_ROW_CLASSES; ++rk) cls_first[rk] = -1;
         for (int key = std::max(klo, 0); key <= khi; ++key) {
-            const int rk = key / (TMAX_FAST + 2);
+            const int rk = key / KEYS_PER_CLASS;
             if (cls_first[rk] < 0) cls_first[rk] = run;   // first key seen of this class
             for (int t = 0; t < nthr; ++t) {
                 int32_t &hv = hist[(size_t)t * (size_t)(KEYS + 1) + (size_t)key];
@@ -1025,7 +1028,10 @@ int fadegpu_submit_inputs(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_reads, con
     // ---- 4. launch plan ----
     std::vector<int32_t> &stl = b->sorted_tlen;
     stl.resize((size_t)n_aln);
-    for (int64_t kx = 0; kx < n_aln; ++kx) stl[(size_t)kx] = b->h_aln[kx].tlen;
+    for (int64_t kx = 0; kx < n_aln; ++kx) {   // long windows share keys: the plan uses the key's upper end for all of them
+        const AlnTmp &t = all[order[(size_t)kx]];
+        stl[(size_t)kx] = (t.cls != 0 && t.tlen > TMAX_FAST) ? key_tlen(t.key % KEYS_PER_CLASS) : t.tlen;
+    }
     int gq = 1, gt = 1;
     for (int64_t kx = cls_first[N_ROW_CLASSES]; kx < n_aln; ++kx) { gq = std::max(gq, b->h_aln[kx].qlen); gt = std::max(gt, b->h_aln[kx].tlen); }
     b->seq_bytes = seq_bytes;
@@ -1218,12 +1224,12 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
         int64_t run = 0;
         for (int rk = 0; rk <= N_ROW_CLASSES; ++rk) {
             cls_first[rk] = run;
-            const int k0 = rk * (TMAX_FAST + 2), k1 = k0 + (TMAX_FAST + 2);
+            const int k0 = rk * KEYS_PER_CLASS, k1 = k0 + KEYS_PER_CLASS;
             for (int key = k0; key < k1; ++key) {
                 const int32_t cnt = b->h_hist[key];
                 b->h_keybase[key] = (int32_t)run;
                 if (!cnt) continue;
-                const int tl = rk == N_ROW_CLASSES ? (int)b->h_stats[5] : TMAX_FAST - (key - k0);
+                const int tl = rk == N_ROW_CLASSES ? (int)b->h_stats[5] : key_tlen(key - k0);
                 std::fill(stl.begin() + run, stl.begin() + run + cnt, tl);
                 run += cnt;
             }
@@ -1248,6 +1254,7 @@ static int submit_device_binning(fadegpu_ctx *c, fadegpu_batch *b, int64_t n_rea
         CU(c, cudaMemsetAsync(b->d_ridx, 0xff, (size_t)n_reads * 4, s2));
     }
     CU(c, cudaEventRecord(b->ev_ready, s2));
+    CU(c, cudaEventRecord(b->ev[4], s2));
     // ---- compute stream ----
     CU(c, cudaStreamWaitEvent(c->stream, b->ev_ready, 0));
     CU(c, cudaEventRecord(b->ev[1], c->stream));
@@ -1480,10 +1487,10 @@ int fadegpu_get_stats(const fadegpu_batch *b, fadegpu_stats *s)
     return FADEGPU_OK;
 }
 
-int fadegpu_get_timeline(const fadegpu_batch *b, const fadegpu_batch *origin, float ms[4])
+int fadegpu_get_timeline(const fadegpu_batch *b, const fadegpu_batch *origin, float ms[6])
 {
     if (!b || !origin || !ms || b->ctx != origin->ctx) return fail(b ? b->ctx : nullptr, FADEGPU_E_ARG, "fadegpu_get_timeline: bad arguments");
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 6; ++k)
         if (cudaEventElapsedTime(&ms[k], origin->ev[0], b->ev[k]) != cudaSuccess) { cudaGetLastError(); ms[k] = -1.f; }
     return FADEGPU_OK;
 }

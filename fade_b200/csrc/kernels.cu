@@ -22,21 +22,30 @@ constexpr unsigned FULL = 0xffffffffu;
 // source/analysis.d:45-64) into shared memory, query selector words (reverse complement of the
 // BAM 4-bit bases, source/util.d:18-34) into registers.  `wild` gets bit0/bit1 when alignment
 // a/b contains a letter outside ACGTN (those go to the generic kernel).
-template <int R>
-__device__ __forceinline__ void stage_pair(const KernelArgs &a, const AlnDesc &da, const AlnDesc &db,
-                                           int g, int nblk, uint16_t *tw, uint32_t (&qs)[R],
-                                           uint8_t *qc, uint32_t &wild)
+// Target selector words of the steps [step0, step0 + nsteps) of one pair: columns step0 - FG .. step0 + nsteps - 1 at
+// tw[0 ..], i.e. column j at tw[j - step0 + FG].  Windows longer than FILL_CHUNK_STEPS are staged chunk by chunk.
+__device__ __forceinline__ uint32_t stage_targets(const KernelArgs &a, const AlnDesc &da, const AlnDesc &db, int g,
+                                                  int step0, int nsteps, uint16_t *tw)
 {
-    const int TW = FBLK * nblk + FG + 1;
+    const int TW = nsteps + FG + 1;
     uint32_t w = 0;
     for (int idx = g; idx < TW; idx += FG) {
-        const int j = idx - FG;
+        const int j = step0 + idx - FG;
         int ca = C_TPAD, cb = C_TPAD;
         if (j >= 0 && j < da.tlen) ca = ref_code(a.ref.planes, da.gstart + j);
         if (j >= 0 && j < db.tlen) cb = ref_code(a.ref.planes, db.gstart + j);
         w |= (ca == C_WILD ? 1u : 0u) | (cb == C_WILD ? 2u : 0u);
         tw[idx] = (uint16_t)t_sel(ca, cb);
     }
+    return w;
+}
+
+template <int R>
+__device__ __forceinline__ void stage_pair(const KernelArgs &a, const AlnDesc &da, const AlnDesc &db,
+                                           int g, int nblk, uint16_t *tw, uint32_t (&qs)[R],
+                                           uint8_t *qc, uint32_t &wild)
+{
+    uint32_t w = stage_targets(a, da, db, g, 0, FBLK * min(nblk, FILL_CHUNK_BLOCKS), tw);
     const uint8_t *sa = a.seq + da.seq_off, *sb = a.seq + db.seq_off;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -91,6 +100,13 @@ __global__ void __launch_bounds__(FILL_THREADS, (R <= 19 ? 5 : 1)) sw_fill_kerne
     const uint16_t *twp = tw + (FG - g);
     const int nsteps = item.nsteps;   // tmax + FG - 1: the last block may be partial
     for (int c = 0; c < nblk; ++c) {
+        if (c > 0 && (c % FILL_CHUNK_BLOCKS) == 0) {
+            // a window longer than the staged chunk: the group replaces its target words by the next chunk's
+            __syncwarp();
+            wild |= stage_targets(a, da, db, g, c * FBLK, FBLK * min(nblk - c, FILL_CHUNK_BLOCKS), tw);
+            twp = tw + (FG - g) - c * FBLK;
+            __syncwarp();
+        }
         const int ulim = min(FBLK, nsteps - c * FBLK);
 #pragma unroll 2
         for (int u = 0; u < ulim; ++u) {
@@ -876,7 +892,7 @@ __global__ void __launch_bounds__(256) alu_peak_kernel(uint32_t *out, int iters)
 
 }  // namespace
 
-int tw_stride_for(int nblk_max) { return (FBLK * nblk_max + FG + 1 + 7) & ~7; }
+int tw_stride_for(int nblk_max) { return (FBLK * std::min(nblk_max, FILL_CHUNK_BLOCKS) + FG + 1 + 7) & ~7; }
 
 size_t fill_smem_bytes(int tw_stride) { return (size_t)(FILL_THREADS / FG) * tw_stride * 2; }
 

@@ -126,18 +126,37 @@ constexpr int N_ROW_CLASSES = 5;
 __host__ __device__ constexpr int row_class(int k) { return k == 0 ? 13 : k == 1 ? 19 : k == 2 ? 25 : k == 3 ? 32 : 38; }
 constexpr int ROW_CLASSES[N_ROW_CLASSES] = { row_class(0), row_class(1), row_class(2), row_class(3), row_class(4) };
 constexpr int QMAX_FAST = FG * 38;   // rows covered by the largest packed instantiation
-constexpr int TMAX_FAST = 4000;      // window length covered by the packed kernels
+// Window lengths: up to TMAX_FAST every length is its own sort key; longer windows (spliced records: alignedLength
+// spans the introns, analysis.d:53) share keys of TLONG_STEP columns up to TMAX_PACKED, beyond which only the generic
+// kernel serves them.  TMAX_PACKED keeps block numbers (32 steps each) within 16 bits.
+constexpr int TMAX_FAST = 4000;
+constexpr int TLONG_STEP = 1024;
+constexpr int TMAX_PACKED = 1000000;
+constexpr int N_LONG_KEYS = (TMAX_PACKED - TMAX_FAST + TLONG_STEP - 1) / TLONG_STEP;
+constexpr int KEYS_PER_CLASS = N_LONG_KEYS + TMAX_FAST + 2;
+// The fill kernel keeps the target words of FILL_CHUNK_BLOCKS * 32 steps per pair in shared memory (2 KB) and
+// restages them for longer windows, so that its occupancy does not depend on the longest window of a launch.
+constexpr int FILL_CHUNK_BLOCKS = 32;
 
 size_t fill_smem_bytes(int tw_stride);
 size_t trace_tile_bytes(int R);
 int tw_stride_for(int nblk_max);
 
-constexpr int BIN_KEYS = (N_ROW_CLASSES + 1) * (TMAX_FAST + 2);
+constexpr int BIN_KEYS = (N_ROW_CLASSES + 1) * KEYS_PER_CLASS;
 // sort key: class rank (ROW_CLASSES order, then the generic list) and descending window length
-__host__ __device__ inline int bin_key(int rank, int tlen) { return rank * (TMAX_FAST + 2) + (rank == N_ROW_CLASSES ? 0 : TMAX_FAST - tlen); }
+__host__ __device__ inline int bin_key(int rank, int tlen)
+{
+    if (rank == N_ROW_CLASSES) return rank * KEYS_PER_CLASS;
+    return rank * KEYS_PER_CLASS + (tlen > TMAX_FAST ? (TMAX_PACKED - tlen) / TLONG_STEP : N_LONG_KEYS + TMAX_FAST - tlen);
+}
+// the window length a key stands for in the launch plan: exact up to TMAX_FAST, the upper end of the key's range beyond
+__host__ __device__ inline int key_tlen(int key_in_class)
+{
+    return key_in_class < N_LONG_KEYS ? TMAX_PACKED - key_in_class * TLONG_STEP : TMAX_FAST - (key_in_class - N_LONG_KEYS);
+}
 __host__ __device__ inline int bin_rank(int qlen, int tlen, bool force_generic)
 {
-    if (force_generic || qlen > QMAX_FAST || tlen > TMAX_FAST) return N_ROW_CLASSES;
+    if (force_generic || qlen > QMAX_FAST || tlen > TMAX_PACKED) return N_ROW_CLASSES;
     for (int k = 0; k < N_ROW_CLASSES; ++k) if (qlen <= FG * row_class(k)) return k;
     return N_ROW_CLASSES;
 }

@@ -224,9 +224,10 @@ int fadegpu_get_results(const fadegpu_batch *b, fadegpu_results_view *r);
  * stream.  ms_out receives the device milliseconds of `iters` passes. */
 int fadegpu_get_stats(const fadegpu_batch *b, fadegpu_stats *s);
 /* Device timeline of the batch's last submit relative to the start of `origin`'s last submit (both of the same ctx,
- * both waited for): ms[0] start of the uploads, ms[1] inputs ready (first fill may start), ms[2] end of its kernels,
- * ms[3] results on the host.  For pipeline diagnostics (tools/e2e_timeline.py). */
-int fadegpu_get_timeline(const fadegpu_batch *b, const fadegpu_batch *origin, float ms[4]);
+ * both waited for): ms[0] start of the uploads, ms[1] the compute stream reaches the batch (first fill starts), ms[2] end
+ * of its kernels, ms[3] results on the host, ms[4] inputs ready on the upload stream, ms[5] end of its last fill; -1 where
+ * the last submit did not record the event.  For pipeline diagnostics (tools/e2e_timeline.py). */
+int fadegpu_get_timeline(const fadegpu_batch *b, const fadegpu_batch *origin, float ms[6]);
 int fadegpu_replay_kernels(fadegpu_ctx *ctx, fadegpu_batch *b, int32_t iters, float *ms_out);
 /* The same over several resident batches of the ctx, queued back to back the way consecutive submits
  * queue them (the traceback rounds of one batch run under the fill of the next): device

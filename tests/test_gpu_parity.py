@@ -288,8 +288,8 @@ def test_share_reference_and_concurrent_contexts():
 
 
 def test_long_windows_use_generic_kernel_and_absurd_ones_are_reported():
-    """spliced-style records (huge aligned_len): windows beyond the packed kernels' 4000 columns go
-    to the generic kernel on the device; a window of > 2^31 DP cells leaves THAT read unaligned with
+    """spliced-style records (huge aligned_len): windows of thousands of columns stay on the packed kernels, those
+    beyond a million columns go to the generic kernel on the device; a window of > 2^31 DP cells leaves THAT read unaligned with
     FADEGPU_R_OVERSIZE (counted in the stats) and the rest of the batch is served as usual."""
     rng = random.Random(31)
     contigs = [readsets.random_ref(rng, 60_000)]
@@ -298,11 +298,24 @@ def test_long_windows_use_generic_kernel_and_absurd_ones_are_reported():
         r["aligned_len"] = rng.randint(5_000, 12_000)      # an N-spanning CIGAR
         r["pos"] = rng.randint(0, 40_000)
     rd = readsets.build(reads)
+    for flags in (0, api.F_HOST_BINNING):
+        with _ctx(flags=flags) as ctx:
+            ctx.load_reference(["c"], contigs)
+            b = run_gpu(ctx, rd)
+            compare(b, rd, contigs, oracle_params(ctx.params))
+            assert b.stats().n_generic == 0      # the packed kernels restage the target chunk by chunk (1024 steps at a time)
+            b.close()
+    # windows beyond the packed kernels' million columns: the generic kernel on the device
+    huge = [readsets.random_ref(rng, 1_300_000)]
+    far = [dict(seq="".join(rng.choice("ACGT") for _ in range(60)), tid=0, pos=1000 + 50 * k, aligned_len=1_100_000 + 1000 * k,
+                clip_left=10 + k, clip_right=0) for k in range(2)]
+    near = readsets.ragged_reads(rng, huge, 30, min_len=100, max_len=150)
+    rd3 = readsets.build(near[:15] + far + near[15:])
     with _ctx() as ctx:
-        ctx.load_reference(["c"], contigs)
-        b = run_gpu(ctx, rd)
-        compare(b, rd, contigs, oracle_params(ctx.params))
-        assert b.stats().n_generic >= 5
+        ctx.load_reference(["h"], huge)
+        b = run_gpu(ctx, rd3)
+        compare(b, rd3, huge, oracle_params(ctx.params))
+        assert b.stats().n_generic == 2
         b.close()
     big = [bytes(40_000_000)]
     rnd = random.Random(32)

@@ -67,8 +67,9 @@ def main():
         if ev[0] == "wait":
             tl = bs[ev[1]].timeline(bs[0])
             st = bs[ev[1]].stats()
-            print(f"chunk {ev[1]:2d}: wait called {ev[2] * 1e3:7.2f} returned {ev[3] * 1e3:7.2f} consumed {ev[4] * 1e3:7.2f} | device: up {tl[0]:7.2f} ready {tl[1]:7.2f} "
-                  f"kernels done {tl[2]:7.2f} home {tl[3]:7.2f} | host submit {st.host_submit_ms:.2f} (classify wait {st.host_classify_ms:.2f}) wait-scatter {st.host_wait_ms:.2f}")
+            print(f"chunk {ev[1]:2d}: wait called {ev[2] * 1e3:7.2f} returned {ev[3] * 1e3:7.2f} consumed {ev[4] * 1e3:7.2f} | device: up {tl[0]:7.2f} inputs {tl[4]:7.2f} "
+                  f"fill {tl[1]:7.2f} - {tl[5]:7.2f} kernels done {tl[2]:7.2f} home {tl[3]:7.2f} | host submit {st.host_submit_ms:.2f} "
+                  f"(classify wait {st.host_classify_ms:.2f}) wait-scatter {st.host_wait_ms:.2f}")
         else:
             print(f"   submit {ev[1]:2d} at {ev[2] * 1e3:7.2f} ({(ev[3] - ev[2]) * 1e3:.3f} ms)")
     for b in bs:
