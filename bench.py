@@ -106,7 +106,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -300,6 +300,11 @@ def file_level_e2e(wl: Workload, n_reads: int, threads: int, device: int):
 def main():
     args = parse_args()
     out = claim_stdout()
+    # A ctx drives four streams (fills, traceback, uploads + binning, results) that must overlap.  With the default of 8
+    # hardware queues per device they can end up sharing a queue with each other once NCCL has added its own streams
+    # (N > 1), which serialises the binning of the next batch behind the running fill.  Must be set before the CUDA
+    # context exists; fadegpu_create sets the same default for processes that have not created one yet.
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     from fade_b200 import shard as _shard
     rank, local_rank, world = _shard.world()
     # torchrun exports OMP_NUM_THREADS=1; the host side of the path (gather / scatter) and the generators are
@@ -390,8 +395,12 @@ def main():
         return int(b.flags[:m8].view(np.uint64).sum(dtype=np.uint64) & 0xffff) + int(b.flags[m8: b.n].sum()) \
             + int(rec["score"].sum()) + len(ws)
 
+    # rank 0 prints the line, so rank 0 samples its GPU; eight pollers of the driver on one box would only disturb
+    # the other ranks' launches
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
+    e2e_steps = []      # wall seconds of every e2e pass of this rank
     k_ms = 0.0          # device ms of the kernel-only passes, all groups, all steps
     e_s = 0.0           # wall seconds of the e2e passes
     cb = None
@@ -471,10 +480,18 @@ def main():
         barrier()
         # ---- timed: end to end through the C ABI ----
         for s in range(args.steps):
-            barrier()
+            # The K timed passes are bracketed by a barrier + synchronize on both sides; no barrier BETWEEN passes: it
+            # phase-locks the ranks, and eight GPUs pulling their bases over PCIe in the same microseconds cost every
+            # pass 1.3 ms on the 8-GPU box (FADE_BENCH_STEP_BARRIER=1 restores it; with the ranks 0.7 ms out of phase,
+            # FADE_BENCH_STAGGER_MS=0.7, a pass is another 1.3 ms shorter -- profiles/README.md).
+            if s == 0 or os.environ.get("FADE_BENCH_STEP_BARRIER"):
+                barrier()
+            if os.environ.get("FADE_BENCH_STAGGER_MS"):      # diagnostics: ranks out of phase by a fixed offset
+                time.sleep(1e-3 * float(os.environ["FADE_BENCH_STAGGER_MS"]) * rank)
             copies["h2d"] = copies["d2h"] = 0
             dt, _ = e2e_step()
             e_s += dt
+            e2e_steps.append(dt)
             copies_total = dict(copies)
             if s == 0:
                 agg.setdefault("h2d", 0); agg.setdefault("d2h", 0)
@@ -487,8 +504,14 @@ def main():
             cb = cpu_baseline(wl.contigs, rd, args.cpu_sample, host_threads, wl.window)
             if args.scalar_sample > 0:
                 scalar = cpu_baseline(wl.contigs, rd, args.scalar_sample, host_threads, wl.window, simd=False)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
 
+    per_rank = None
+    if world > 1:       # every rank's e2e passes (diagnostics of the scaling curve): mean and worst pass in ms
+        mine = [1e3 * statistics.mean(e2e_steps), 1e3 * max(e2e_steps), 1e3 * min(e2e_steps)]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = [[round(x, 2) for x in g] for g in gathered]
     k_ms_max = max_over_ranks(k_ms)
     e_s_max = max_over_ranks(e_s)
     total_reads = sum_over_ranks(float(wl.n))
@@ -528,6 +551,7 @@ def main():
                     "d2h_bytes_per_step": agg.get("d2h", 0), "ms_per_step": 1e3 * e_s_max / args.steps,
                     "bytes_per_read": round((agg.get("h2d", 0) + agg.get("d2h", 0)) / max(wl.n, 1), 2),
                     "host_threads_per_rank": host_threads, "path": path,
+                    "pass_ms_mean_max_min_per_rank": per_rank,
                     "host_ms_last_pass": {kx: round(v, 3) for kx, v in host_ms.items()}},
             "gpu_launches": agg["launches"] * args.steps,
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak9, "unit": "GCUPS",
@@ -563,7 +587,7 @@ def main():
         dist.destroy_process_group()
 
 
-FILL_TRAFFIC = 2.466e9   # profiles/r01_prof_fill_5blk_raw.csv: 0.173 GB read + 2.293 GB written per launch
+FILL_TRAFFIC = 2.455e9   # profiles/r02_prof_fill_raw.csv: 0.160 GB read + 2.295 GB written per launch (ncu --set full)
 
 
 def peak_hbm():

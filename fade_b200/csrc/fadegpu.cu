@@ -524,6 +524,9 @@ int fadegpu_create(int device, const fadegpu_params *p, fadegpu_ctx **out)
     if (pp.gap_open < pp.gap_extend || pp.gap_extend <= 0 || pp.match <= 0 || pp.mismatch > 0 ||
         pp.match > 100 || pp.mismatch < -100 || pp.gap_open > 1000 || pp.window_size < 0)
         return fail(nullptr, FADEGPU_E_ARG, "fadegpu_create: unsupported scoring / window parameters");
+    // the four streams of a ctx must be able to overlap: ask for more hardware queues than the default 8 unless the
+    // process has chosen a value (only effective if no CUDA context exists yet)
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0)

@@ -96,6 +96,40 @@ def test_force_generic_equals_packed():
         b.close()
 
 
+def test_both_kernel_families_against_the_striped_restatement():
+    """The generic kernel and the scalar oracle are written alike, so agreeing with each other says little.  Here the
+    packed kernels AND the generic kernel are compared with the structurally different restatement of parasail's
+    striped lazy-F kernel (oracle/parasail_striped.c, 16 and 8 lanes) on every aligned read of a ragged read set."""
+    rng = random.Random(91)
+    contigs = [readsets.random_ref(rng, n) for n in (6000, 1500)]
+    reads = readsets.ragged_reads(rng, contigs, 700, max_len=200)
+    rd = readsets.build(reads)
+    for flags in (0, api.F_FORCE_GENERIC):
+        with _ctx(flags=flags) as ctx:
+            ctx.load_reference(["a", "b"], contigs)
+            b = run_gpu(ctx, rd)
+            W = ctx.params.window_size
+            n_checked = 0
+            for k in np.flatnonzero(b.flags[: rd.n] & 1):
+                r = reads[k]
+                ref = contigs[r["tid"]].decode().upper()
+                start = max(0, r["pos"] - W)
+                end = min(len(ref), r["pos"] + r["aligned_len"] + W)
+                assert int(b.win_start[k]) == start
+                q = readsets.revcomp(r["seq"])
+                for lanes in (16, 8):
+                    s = orc.sw_trace_striped(q, ref[start:end], lanes)
+                    assert (s.score, s.n_ops) == (int(b.score[k]), int(b.n_ops[k])), (k, lanes)
+                    if s.score > 0:
+                        assert (s.end_query, s.end_ref, s.beg_query, s.beg_ref) == \
+                            (int(b.end_query[k]), int(b.end_ref[k]), int(b.beg_query[k]), int(b.beg_ref[k])), (k, lanes)
+                        assert s.ops[: api.MAX_OPS] == [int(x) for x in b.ops[k, : min(s.n_ops, api.MAX_OPS)]], (k, lanes, s.cigar)
+                n_checked += 1
+            assert n_checked > 200
+            assert (b.stats().n_generic > 0) == bool(flags)
+            b.close()
+
+
 def test_stress_config_long_windows_short_clips():
     """BASELINE.json configs[3]: --window-size 1000, --min-length 5, 2x250 reads, clip law U{1..40}."""
     ref = sim.make_contig(1002, 0, 400_000, 50_000, 300, 0.02)

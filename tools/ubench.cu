@@ -23,17 +23,19 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, int iters, uint32_t c1, 
             for (int i = 0; i < 8; ++i) {
                 if (KIND == 0) x[i] = __viaddmax_s16x2(x[i], c1, c2);
                 if (KIND == 1) x[i] = __vimax3_s16x2(x[i], c1, c2);
-                if (KIND == 2) x[i] = __vmaxs2(x[i], c1);
+                // max / logic chains with loop-invariant operands collapse at compile time (max is idempotent, two LOP3 of the
+                // same three inputs fuse into one): the second operand changes every iteration instead
+                if (KIND == 2) { x[i] = __vmaxs2(x[i], y[i]); y[i] = __vadd2(y[i], c1); }            // VIMNMX + VIADD
                 if (KIND == 3) x[i] = __vadd2(x[i], c1);
                 if (KIND == 4) x[i] = __byte_perm(x[i], c1, c2);
-                if (KIND == 5) x[i] = (x[i] ^ c1) & c2;
+                if (KIND == 5) { x[i] = (x[i] ^ y[i]) & c1; y[i] = (y[i] | x[i]) ^ c2; }             // 2 LOP3 of four inputs
                 if (KIND == 6) x[i] = x[i] * one + c1;                       // IMAD
                 if (KIND == 7) { x[i] = __viaddmax_s16x2(x[i], c1, c2); y[i] = y[i] * one + c1; }   // ALU + FMA pipes
                 if (KIND == 8) { x[i] = __viaddmax_s16x2(x[i], c1, c2); y[i] = __vmaxs2(y[i], c1); } // 2 ALU
                 if (KIND == 9) x[i] = __viaddmax_s16x2_relu(x[i], c1, c2);
-                if (KIND == 10) { x[i] = __viaddmax_s16x2(x[i], c1, c2); y[i] = (y[i] ^ c1) & c2; }
+                if (KIND == 10) { x[i] = __viaddmax_s16x2(x[i], c1, y[i]); y[i] = (y[i] ^ x[i]) & c2; }
                 if (KIND == 11) { x[i] = __viaddmax_s16x2(x[i], c1, y[i]); y[i] = __viaddmax_s16x2(y[i], c2, x[i]); } // 3 register operands
-                if (KIND == 12) { x[i] = __vmaxs2(x[i], c1); y[i] = y[i] * one + c1; }
+                if (KIND == 12) { x[i] = __vmaxs2(x[i], y[i]); y[i] = y[i] * one + c1; }
                 if (KIND == 13) x[i] = __vimax3_s16x2_relu(x[i], c1, c2);
             }
         }
@@ -79,10 +81,10 @@ int main()
     run<9>("VIADDMNMX.S16x2.RELU", 1, s, mhz);
     run<1>("VIMNMX3.S16x2", 1, s, mhz);
     run<13>("VIMNMX3.S16x2.RELU", 1, s, mhz);
-    run<2>("VIMNMX.S16x2", 1, s, mhz);
+    run<2>("VIMNMX.S16x2 + VIADD.16x2 (2 per iter)", 2, s, mhz);
     run<3>("VIADD.16x2", 1, s, mhz);
     run<4>("PRMT", 1, s, mhz);
-    run<5>("LOP3", 1, s, mhz);
+    run<5>("LOP3 (2 per iter)", 2, s, mhz);
     run<6>("IMAD", 1, s, mhz);
     run<7>("VIADDMNMX + IMAD (2 per iter)", 2, s, mhz);
     run<8>("VIADDMNMX + VIMNMX (2 per iter)", 2, s, mhz);
