@@ -83,6 +83,9 @@ def parse_args():
                     help="compact = fadegpu_submit_compact (gate byte + 32-byte record per read in the pinned view); "
                          "view = fadegpu_submit (seven arrays); arrays = fadegpu_submit_inputs from pageable arrays")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--tags-only", action="store_true",
+                    help="FADEGPU_F_TAGS_ONLY: no traceback for alignments whose score already fails both accept predicates "
+                         "(what the file drivers use; NOT the default bench line, which produces every record in full)")
     ap.add_argument("--file-reads", type=int, default=1_000_000,
                     help="records of the e2e_file leg (fade-b200 annotate BAM -> BAM on the first reads of the workload; 0 = skip)")
     a = ap.parse_args()
@@ -199,6 +202,8 @@ class Workload:
         else:
             desc = (f"{a.reads} simulated 2x150 paired reads (seed {READ_SEED}) vs synthetic "
                     f"{a.ref_len} bp chromosome (seed {REF_SEED}), window-size 300, min-length 5, per GPU")
+        if a.tags_only:
+            desc += "; FADEGPU_F_TAGS_ONLY (no traceback where the score rules out both accept predicates)"
         return {"workload": desc, "chunk_reads": a.chunk, "resident_chunks": a.group,
                 "l2": "inputs + checkpoint scratch per chunk (>2 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -341,7 +346,8 @@ def main():
     from fade_b200 import default_params
     from fade_b200 import api as _api
     # compact results (fadegpu_get_results): fadegpu_wait rebuilds only flags[] and the result index
-    ctx = Context(local_rank, default_params(host_threads=host_threads, flags=_api.F_NO_SCATTER, window_size=wl.window))
+    ctx = Context(local_rank, default_params(host_threads=host_threads, window_size=wl.window,
+                                             flags=_api.F_NO_SCATTER | (_api.F_TAGS_ONLY if args.tags_only else 0)))
     ctx.load_reference(wl.names, wl.contigs)
     alu_ops, max_mhz = ctx.measure_alu_peak()
 

@@ -11,9 +11,10 @@ import numpy as np
 from ._lib import BatchView, FadeGpuError, HostRecord, Inputs, Params, Result, ResultsView, Stats, lib
 
 MAX_OPS = 10
-R_ALIGNED, R_ART_LEFT, R_ART_RIGHT, R_OPS_TRUNC, R_GENERIC, R_OVERSIZE = 1, 2, 4, 8, 16, 32
+R_ALIGNED, R_ART_LEFT, R_ART_RIGHT, R_OPS_TRUNC, R_GENERIC, R_OVERSIZE, R_SCORE_ONLY = 1, 2, 4, 8, 16, 32, 64
 F_FORCE_GENERIC = 1
 F_NO_SCATTER = 2
+F_TAGS_ONLY = 4
 F_NO_SHORTCUT = 8
 F_HOST_BINNING = 16
 F_SYNC_SUBMIT = 32

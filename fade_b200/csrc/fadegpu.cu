@@ -396,6 +396,7 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
                 a.qcount = ln.d_qcount;
                 a.round = 0;
                 a.max_rounds = L.nblk_max + FG;   // each round scans one candidate block or walks one block
+                a.tags_only = (c->p.flags & FADEGPU_F_TAGS_ONLY) ? 1 : 0;
             }
             CU(c, cudaMemsetAsync(a.aln_flags, 0, (size_t)L.n_aln * sizeof(uint32_t), sf));
             CU(c, cudaMemsetAsync(ln.d_qcount, 0, 2 * sizeof(unsigned int), sf));
@@ -415,7 +416,7 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
             ga.n_slots = (int)std::max<size_t>(1, std::min<size_t>(GEN_SLOTS_MAX, ln.gen_bytes / (size_t)ga.slot_bytes));
             ga.chunk = 64;
             ga.open = c->p.gap_open; ga.extend = c->p.gap_extend; ga.match = c->p.match; ga.mismatch = c->p.mismatch;
-            ga.min_length = c->p.min_length;
+            ga.min_length = c->p.min_length; ga.tags_only = (c->p.flags & FADEGPU_F_TAGS_ONLY) ? 1 : 0;
             if (timed) CU(c, cudaEventRecord(e2, st));
             CU(c, cudaMemsetAsync(ln.d_cursor, 0, sizeof(unsigned int), st));
             CU(c, launch_generic(ga, ga.n_slots, st));
@@ -442,7 +443,7 @@ int run_plan(fadegpu_ctx *c, fadegpu_batch *b, float *fill_ms, float *trace_ms, 
             ga.n_slots = std::min(ga.n_slots, std::max(L.n_aln, 1));
             ga.chunk = 1;
             ga.open = c->p.gap_open; ga.extend = c->p.gap_extend; ga.match = c->p.match; ga.mismatch = c->p.mismatch;
-            ga.min_length = c->p.min_length;
+            ga.min_length = c->p.min_length; ga.tags_only = (c->p.flags & FADEGPU_F_TAGS_ONLY) ? 1 : 0;
             CU(c, cudaEventRecord(ln.ev_fill, sf));        // (orders tstream after dep and the set's previous traceback)
             CU(c, cudaStreamWaitEvent(st, ln.ev_fill, 0));
             if (timed) CU(c, cudaEventRecord(e0, st));

@@ -468,7 +468,7 @@ inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, cons
         cseqs.push_back(it->second.data());
     }
     fadegpu_params prm = job.prm;
-    prm.flags |= FADEGPU_F_NO_SCATTER;
+    prm.flags |= FADEGPU_F_NO_SCATTER | FADEGPU_F_TAGS_ONLY;   // only rs / am / as / ar / ab leave this loop
     // One ctx (and its submit thread) per GPU; the reference is packed and uploaded once and copied GPU to GPU
     // (NVLink peer copy) to the others: every GPU holds its own copy, reads are independent, nothing is exchanged
     // on the data path.  The reference's merge is its mutex-guarded writer (anno.d:47-49); here the one writer

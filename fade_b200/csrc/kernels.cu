@@ -181,7 +181,15 @@ __global__ void FADE_SMALL_KERNEL trace_init_kernel(const KernelArgs a)
             c.blk[g] = half ? (int)(v.y >> 16) : (int)(v.y & 0xffffu);
         }
         ctl_init(c, d.qlen, d.tlen);
-        if (c.phase == 2) {
+        if (c.phase != 2 && a.tags_only && !score_may_accept(c.S, d.clip_left, d.clip_right, a.min_length)) {
+            // FADEGPU_F_TAGS_ONLY: the score already rules out both accept predicates (analysis.d:76,100): no end cell, no
+            // traceback; the record carries the score and FADEGPU_R_SCORE_ONLY
+            AlnOut o;
+            o.score = c.S; o.end_query = o.end_ref = o.beg_query = o.beg_ref = 0; o.n_ops = 0;
+            o.flags = R_ALIGNED | R_SCORE_ONLY; o.read = d.read;
+            for (int k = 0; k < OPS_CAP; ++k) o.ops[k] = 0;
+            a.out[aln] = o;
+        } else if (c.phase == 2) {
             AlnOut o;
             finalize_result(c, o, d.read, d.clip_left, d.clip_right, a.min_length);
             a.out[aln] = o;
@@ -655,6 +663,12 @@ __global__ void __launch_bounds__(128) sw_generic_kernel(const GenericArgs a)
             }
         }
         out.score = best;
+        if (best > 0 && a.tags_only && !score_may_accept(best, d.clip_left, d.clip_right, a.min_length)) {
+            out.end_query = out.end_ref = out.beg_query = out.beg_ref = out.n_ops = 0;
+            out.flags = R_ALIGNED | R_GENERIC | R_SCORE_ONLY;
+            a.out[cur_idx] = out;
+            continue;
+        }
         if (best <= 0) {
             out.end_query = out.end_ref = out.beg_query = out.beg_ref = out.n_ops = 0;
             out.flags = R_ALIGNED | R_GENERIC;

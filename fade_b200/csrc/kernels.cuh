@@ -64,6 +64,7 @@ struct KernelArgs {
     unsigned int *qcount;      // [2]
     uint32_t *tiles;           // [ceil(n_aln/2)] trace tiles of the current round
     int32_t round, max_rounds;
+    int32_t tags_only;         // FADEGPU_F_TAGS_ONLY
 };
 
 struct GenericArgs {
@@ -80,6 +81,7 @@ struct GenericArgs {
     int32_t n_slots;           // threads that own a scratch slot
     int32_t chunk;             // work items claimed per atomic
     int32_t open, extend, match, mismatch, min_length;
+    int32_t tags_only;         // FADEGPU_F_TAGS_ONLY
 };
 
 // ---- binning on the device (pinned-view submits): classify reads, histogram by (class, window

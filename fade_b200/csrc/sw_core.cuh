@@ -499,7 +499,7 @@ struct AlnOut {
     uint32_t ops[OPS_CAP];
 };
 
-constexpr uint32_t R_ALIGNED = 1u, R_ART_LEFT = 2u, R_ART_RIGHT = 4u, R_OPS_TRUNC = 8u, R_GENERIC = 16u;
+constexpr uint32_t R_ALIGNED = 1u, R_ART_LEFT = 2u, R_ART_RIGHT = 4u, R_OPS_TRUNC = 8u, R_GENERIC = 16u, R_SCORE_ONLY = 64u;
 
 // accept predicate for one side, source/analysis.d:69-80 (left) / :98-104 (right)
 FD bool accept_side(bool left, int score, int n_ops, uint32_t first_op, uint32_t last_op,
@@ -513,6 +513,20 @@ FD bool accept_side(bool left, int score, int n_ops, uint32_t first_op, uint32_t
     if (!((float)score > cutoff)) return false;                          // analysis.d:76 / :100
     if (left) return !(trail_s != 0 || lead_s == 0);                     // analysis.d:78-80
     return !(lead_s != 0 || trail_s == 0);                               // analysis.d:102-104
+}
+
+// Can an alignment of this score be accepted on either side at all?  The score test of accept_side (analysis.d:43,
+// 76 / 100, same float arithmetic) is the only predicate that needs nothing but the fill's result; when it fails for
+// both clips no traceback can change the read's tags (FADEGPU_F_TAGS_ONLY).
+FD bool score_may_accept(int score, uint32_t clip_left, uint32_t clip_right, int32_t min_length)
+{
+    for (int side = 0; side < 2; ++side) {
+        const uint32_t clip_len = side == 0 ? clip_left : clip_right;
+        if (clip_len == 0 || clip_len <= (uint32_t)min_length) continue;
+        const float cutoff = (float)((double)clip_len * 0.9 * 2);
+        if ((float)score > cutoff) return true;
+    }
+    return false;
 }
 
 // P5 (dparasail wrapper): forward CIGAR = [S lead] + reversed ring + [S trail]; then predicates.

@@ -73,6 +73,10 @@ typedef struct fadegpu_params {
                                       implementation, kept as an A/B switch) instead of binning them on the device */
 #define FADEGPU_F_SYNC_SUBMIT 32u   /* fadegpu_submit: plan and launch on the calling thread (errors of the batch
                                       are then returned by fadegpu_submit itself instead of fadegpu_wait) */
+#define FADEGPU_F_TAGS_ONLY 4u     /* the caller only needs what fade writes into the tags: an alignment whose score already
+                                      fails `score > clip_len*0.9*2` (analysis.d:43,76,100) for both clips gets no end cell and
+                                      no traceback -- its record carries the score, n_ops = 0 and FADEGPU_R_SCORE_ONLY; flags[]
+                                      (art_left / art_right) and the records of every other read are unchanged */
 #define FADEGPU_F_NO_SCATTER 2u    /* fadegpu_wait fills only flags[] and the compact results
                                       (fadegpu_get_results), not the other per-read output arrays */
 
@@ -82,6 +86,7 @@ typedef struct fadegpu_params {
 #define FADEGPU_R_ART_RIGHT 4u  /* status.art_right (analysis.d:106) */
 #define FADEGPU_R_OPS_TRUNC 8u  /* n_ops > FADEGPU_MAX_OPS, only the first ones are materialised */
 #define FADEGPU_R_GENERIC 16u   /* served by the generic kernel (wildcard letters / odd sizes) */
+#define FADEGPU_R_SCORE_ONLY 64u /* FADEGPU_F_TAGS_ONLY: only `score` is valid in this read's record (no artifact possible) */
 #define FADEGPU_R_OVERSIZE 32u  /* NOT aligned: the read's window exceeds 2^31 DP cells (a spliced record spanning
                                    megabases); counted in fadegpu_stats.n_oversize, the batch goes on */
 

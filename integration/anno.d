@@ -77,7 +77,7 @@ int annotate(string cl, string[] args, ubyte con, int artifact_floor_length, int
     fadegpu_default_params(&prm);                       // open 10, extend 2, match 2, mismatch -3 = Parasail("ACTGN",10,2,2,-3)
     prm.window_size = align_buffer_size;
     prm.min_length = artifact_floor_length;
-    prm.flags = FADEGPU_F_NO_SCATTER;
+    prm.flags = FADEGPU_F_NO_SCATTER | FADEGPU_F_TAGS_ONLY;   // only rs / am / as / ar / ab leave this loop
     int nGpus = environment.get("FADE_GPUS", "1").to!int;
     int nDev;
     enforce(fadegpu_device_count(&nDev) == 0 && nDev >= nGpus && nGpus >= 1, "fade annotate: " ~ lastError(null));

@@ -45,6 +45,7 @@ enum : uint
 {
     FADEGPU_F_FORCE_GENERIC = 1,
     FADEGPU_F_NO_SCATTER = 2,
+    FADEGPU_F_TAGS_ONLY = 4,
     FADEGPU_F_NO_SHORTCUT = 8,
     FADEGPU_F_HOST_BINNING = 16,
     FADEGPU_F_SYNC_SUBMIT = 32
@@ -58,7 +59,8 @@ enum : uint
     FADEGPU_R_ART_RIGHT = 4,  /// status.art_right, analysis.d:106
     FADEGPU_R_OPS_TRUNC = 8,
     FADEGPU_R_GENERIC = 16,
-    FADEGPU_R_OVERSIZE = 32
+    FADEGPU_R_OVERSIZE = 32,
+    FADEGPU_R_SCORE_ONLY = 64
 }
 
 /// one read of the compact input layout (32 bytes)

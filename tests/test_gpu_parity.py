@@ -130,6 +130,40 @@ def test_both_kernel_families_against_the_striped_restatement():
             b.close()
 
 
+@pytest.mark.parametrize("extra", [0, api.F_FORCE_GENERIC, api.F_HOST_BINNING])
+def test_tags_only_skips_hopeless_tracebacks_and_changes_no_tag(extra):
+    """FADEGPU_F_TAGS_ONLY: an alignment whose score fails `score > clip_len*0.9*2` (analysis.d:43,76,100) for both
+    clips gets no traceback (record: score, FADEGPU_R_SCORE_ONLY); art_left / art_right of every read and the full
+    record of every other alignment equal the oracle."""
+    names, contigs, cfg, n = sim.config_c1()
+    rd = sim.make_reads(cfg, 0, 6000, contigs)
+    with _ctx(flags=api.F_TAGS_ONLY | extra) as ctx:
+        ctx.load_reference(names, contigs)
+        b = run_gpu(ctx, rd)
+        res, ops = orc.align_batch(rd.seq4, rd.seq_off, rd.l_qseq, rd.tid, rd.pos, rd.aligned_len, rd.clip_left, rd.clip_right,
+                                   contigs, params=oracle_params(ctx.params), ops_cap=api.MAX_OPS)
+        fl = b.flags[: rd.n]
+        assert np.array_equal((fl & 1).astype(np.int32), res["aligned"])
+        assert np.array_equal(((fl >> 1) & 1).astype(np.int32), res["art_left"])
+        assert np.array_equal(((fl >> 2) & 1).astype(np.int32), res["art_right"])
+        al = res["aligned"] == 1
+        so = (fl & api.R_SCORE_ONLY) != 0
+        assert 0.15 < so[al].mean() < 0.6 and not so[~al].any()
+        assert np.array_equal(b.score[: rd.n][al], res["score"][al])
+        # a skipped alignment can indeed not be accepted: 5 * score <= 9 * clip for both clips past the floor
+        S, cl, cr = res["score"], rd.clip_left, rd.clip_right
+        may = ((cl > 5) & (5 * S > 9 * cl)) | ((cr > 5) & (5 * S > 9 * cr))
+        assert np.array_equal(so[al], ~may[al])
+        full = al & ~so
+        for f in ("beg_query", "end_query", "beg_ref", "end_ref", "n_ops"):
+            assert np.array_equal(getattr(b, f)[: rd.n][full], res[f][full]), f
+        k = np.minimum(res["n_ops"], api.MAX_OPS)
+        m = np.arange(api.MAX_OPS)[None, :] < k[:, None]
+        assert np.array_equal(np.where(m, b.ops[: rd.n], 0)[full], np.where(m, ops, 0)[full])
+        assert (b.n_ops[: rd.n][al & so] == 0).all()
+        b.close()
+
+
 def test_stress_config_long_windows_short_clips():
     """BASELINE.json configs[3]: --window-size 1000, --min-length 5, 2x250 reads, clip law U{1..40}."""
     ref = sim.make_contig(1002, 0, 400_000, 50_000, 300, 0.02)
