@@ -273,6 +273,7 @@ struct Job {
     int device = 0;             // first device
     int n_gpus = 1;             // devices device .. device + n_gpus - 1, batches dealt round-robin
     int64_t batch_n = 1 << 20;
+    int level = 6;              // zlib level of -b output (htslib's default is zlib's default, 6)
     int con = 0;                // util.d:65-76: 0 SAM, 1 uBAM, 2 BAM
     std::string cl, version;
     std::string fasta_path;
@@ -338,7 +339,7 @@ struct RecordInput {
 };
 
 // the header as SAM text (con 0) or as the first BGZF block(s) of a BAM file (util.d:65-76)
-inline void write_header(const samio::Header &hdr, int con, int threads)
+inline void write_header(const samio::Header &hdr, int con, int threads, int bam_level = 6)
 {
     if (con == 0) {
         for (const auto &l : hdr.lines) { fwrite(l.data(), 1, l.size(), stdout); fputc('\n', stdout); }
@@ -354,7 +355,7 @@ inline void write_header(const samio::Header &hdr, int con, int threads)
         o += hdr.names[r]; o.push_back('\0');
         samio::put_u32(o, (uint32_t)hdr.lens[r]);
     }
-    write_blocks(stdout, reinterpret_cast<const uint8_t *>(o.data()), o.size(), con == 1 ? 0 : 6, threads);
+    write_blocks(stdout, reinterpret_cast<const uint8_t *>(o.data()), o.size(), con == 1 ? 0 : bam_level, threads);
 }
 
 inline void write_eof_marker()
@@ -451,8 +452,8 @@ inline int annotate_records(FILE *fin, const std::string &pre, bool is_bam, cons
     if (!last_pg.empty()) pg += "\tPP:" + last_pg;
     pg += "\tCL:" + job.cl;
     hdr.add_line(pg);
-    const int level = job.con == 1 ? 0 : 6;
-    write_header(hdr, job.con, threads);
+    const int level = job.con == 1 ? 0 : job.level;
+    write_header(hdr, job.con, threads, job.level);
 
     // ---- reference (anno.d:23) ----
     std::map<std::string, std::string> fasta;

@@ -224,6 +224,7 @@ int usage()
             "      --min-length N   minimum soft-clip length considered (default 5)\n"
             "  -w, --window-size N  bases considered outside of the read region (default 300)\n"
             "      --batch N        records per GPU batch (default 1048576)\n"
+            "      --level N        zlib level of -b output, 0-9 (default 6, as htslib)\n"
             "      --device N       first CUDA device (default 0)\n"
             "      --gpus N         GPUs: batches are dealt round-robin to devices N0..N0+N-1, every GPU holds the reference\n"
             "                       (packed once, copied GPU to GPU), the records keep their input order (default 1)\n"
@@ -238,7 +239,7 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
     fadegpu_params prm;
     fadegpu_default_params(&prm);
     const Options opt = parse_options(argc, argv, 2, { { 't', "threads", true }, { 0, "min-length", true }, { 'w', "window-size", true },
-                                                      { 0, "batch", true }, { 0, "device", true }, { 0, "gpus", true }, { 0, "text-path", false },
+                                                      { 0, "batch", true }, { 0, "device", true }, { 0, "gpus", true }, { 0, "level", true }, { 0, "text-path", false },
                                                       { 'h', "help", false }, { 'b', "bam", false }, { 'u', "ubam", false } });
     if (!opt.ok) { usage(); return 1; }
     if (opt.has("help")) return usage();
@@ -246,13 +247,13 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
     prm.min_length = (int32_t)opt.num("min-length", prm.min_length);
     prm.window_size = (int32_t)opt.num("window-size", prm.window_size);
     const int64_t batch_n = opt.num("batch", 1 << 20);
-    const int device = (int)opt.num("device", 0), n_gpus = (int)opt.num("gpus", 1);
+    const int device = (int)opt.num("device", 0), n_gpus = (int)opt.num("gpus", 1), level = (int)opt.num("level", 6);
     const bool text_path = opt.has("text-path");   // the line-by-line SAM text loop (A/B check of bamfast.hpp)
     const std::vector<std::string> &pos_args = opt.pos;
     int con = 0;
     if (pos_args.size() != 2) { usage(); return pos_args.empty() ? 0 : 1; }
     if (!output_container(opt, con)) return 1;
-    if (batch_n <= 0 || n_gpus < 1 || (text_path && n_gpus != 1)) { fprintf(stderr, "fade-b200: bad --batch / --gpus\n"); return 1; }
+    if (batch_n <= 0 || n_gpus < 1 || (text_path && n_gpus != 1) || level < 0 || level > 9) { fprintf(stderr, "fade-b200: bad --batch / --gpus / --level\n"); return 1; }
     fprintf(stderr, "[W::fade annotate] Output will keep the input order\n");
 
     FILE *fin_raw = pos_args[0] == "-" ? stdin : fopen(pos_args[0].c_str(), "rb");
@@ -264,7 +265,7 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
         // --text-path keeps the first, line-by-line implementation below (A/B check)
         const bool is_bam = pre.size() == 2 && (uint8_t)pre[0] == 0x1f && (uint8_t)pre[1] == 0x8b;
         bamfast::Job job;
-        job.prm = prm; job.device = device; job.n_gpus = n_gpus; job.batch_n = batch_n; job.con = con; job.cl = cl; job.version = kVersion;
+        job.prm = prm; job.device = device; job.n_gpus = n_gpus; job.batch_n = batch_n; job.level = level; job.con = con; job.cl = cl; job.version = kVersion;
         job.fasta_path = pos_args[1];
         return bamfast::annotate_records(fin_raw, pre, is_bam, job, read_fasta);
     }

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """File-level throughput of `fade-b200 annotate` (C++ driver, fade_b200/csrc/host): simulated reads ->
-SAM / BAM files -> annotate -> SAM / uBAM / BAM, records per second of wall clock per combination.
-    python tools/cli_bench.py [--reads N] [--ref-len L]"""
+SAM / BAM files -> annotate -> SAM / uBAM / BAM, records per second of wall clock per combination, and
+BAM -> BAM over 1, 2, 4, 8 GPUs when the box has them (--gpus 1,2,4,8).
+    python tools/cli_bench.py [--reads N] [--ref-len L] [--gpus 1,2]"""
 import argparse
 import os
 import subprocess
@@ -10,10 +11,6 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np  # noqa: E402
-
-import samio  # noqa: E402
 from fade_b200 import sim  # noqa: E402
 
 BIN = os.path.join(ROOT, "fade_b200", "bin", "fade-b200")
@@ -24,6 +21,8 @@ def main():
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--ref-len", type=int, default=20_000_000)
     ap.add_argument("--dir", default="/tmp/fade_cli_bench")
+    ap.add_argument("--gpus", default="1")
+    ap.add_argument("--combos", default="all", help="all = every input / output container; bam = BAM -> BAM only")
     a = ap.parse_args()
     os.makedirs(a.dir, exist_ok=True)
     cfg = sim.default_cfg(read_seed=2002)
@@ -31,23 +30,27 @@ def main():
     rd = sim.make_reads(cfg, 0, a.reads, [ref])
     fa, sam, bam = (os.path.join(a.dir, x) for x in ("ref.fa", "in.sam", "in.bam"))
     t = time.time()
-    samio.write_fasta(fa, ["chrS"], [ref])
-    samio.write_sam(sam, ["chrS"], [ref], rd)
-    with open(bam, "wb") as f:
-        subprocess.run([BIN, "view", "-b", sam], stdout=f, check=True)
+    sim.write_fasta(fa, ["chrS"], [ref])
+    sim.write_bam(bam, ["chrS"], [ref], rd)
+    with open(sam, "wb") as f:
+        subprocess.run([BIN, "view", bam], stdout=f, check=True)
     print(f"inputs: {a.reads} reads, SAM {os.path.getsize(sam) >> 20} MiB, BAM {os.path.getsize(bam) >> 20} MiB ({time.time() - t:.0f} s to write)",
           flush=True)
     env = dict(os.environ, FADE_TIMING="1")
-    for src, flags in ((bam, ["-b"]), (bam, ["-b"]), (bam, ["-u"]), (bam, []), (sam, []), (sam, ["-b"])):
-        t = time.time()
-        with open(os.path.join(a.dir, "out.bin"), "wb") as f:
-            p = subprocess.run([BIN, "annotate", *flags, src, fa], stdout=f, stderr=subprocess.PIPE, text=True, env=env)
-        dt = time.time() - t
-        assert p.returncode == 0, p.stderr
-        print(f"{os.path.basename(src)} -> {flags or ['sam']}: {dt:.2f} s wall, {a.reads / dt / 1e6:.2f} M records/s (incl. FASTA load + upload)")
-        for ln in p.stderr.splitlines():
-            if "threads" in ln or "records," in ln:
-                print("   ", ln)
+    combos = [(bam, ["-b"]), (bam, ["-b"]), (bam, ["-b", "--level", "1"]), (bam, ["-u"]), (bam, []), (sam, []), (sam, ["-b"])]
+    if a.combos == "bam":
+        combos = combos[:2]
+    for g in [int(x) for x in a.gpus.split(",")]:
+        for src, flags in combos:
+            t = time.time()
+            with open(os.path.join(a.dir, "out.bin"), "wb") as f:
+                p = subprocess.run([BIN, "annotate", "--gpus", str(g), *flags, src, fa], stdout=f, stderr=subprocess.PIPE, text=True, env=env)
+            dt = time.time() - t
+            assert p.returncode == 0, p.stderr
+            print(f"{g} GPU(s) {os.path.basename(src)} -> {flags or ['sam']}: {dt:.2f} s wall, {a.reads / dt / 1e6:.2f} M records/s (incl. FASTA load + upload)")
+            for ln in p.stderr.splitlines():
+                if "threads" in ln or "records," in ln:
+                    print("   ", ln)
 
 
 if __name__ == "__main__":
