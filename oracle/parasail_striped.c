@@ -17,7 +17,10 @@
  * -open, the lazy-F loop that re-derives the H source and the E / F trace bits of every cell it
  * touches, the H-column triple buffering that keeps the column of the best score, the per-column
  * `vMaxH > vMaxHUnit` test, the end_query scan in striped order -- and tests/test_striped_parity.py
- * fuzzes it against fo_sw_trace at 8 lanes (SSE2/SSE4.1/NEON builds) and 16 lanes (AVX2 builds).
+ * fuzzes it against fo_sw_trace at 8 lanes (SSE2/SSE4.1/NEON builds), 16 lanes (AVX2 builds) and 32 lanes (the
+ * lane count of the 8-bit AVX2 kernel: U10 -- dparasail's sw_striped may be parasail's saturating dispatcher, which
+ * tries the 8-bit kernel first and keeps its answer when the score stays below 127 - match; without saturation the
+ * 8-bit kernels compute the same recurrence, so only their lane count could matter).
  *
  * PROVENANCE / LIMIT: parasail's source is not in /root/reference nor installable here (no
  * network); this is restated from the author's knowledge of upstream src/sw_trace_striped.c,
@@ -357,9 +360,10 @@ int ps_sw_trace_striped(const char *s1, int s1Len, const char *s2, int s2Len, in
                         int match, int mismatch, int lanes, ps_result *res, uint32_t *ops, int ops_cap)
 {
     if (!s1 || !s2 || s1Len <= 0 || s2Len <= 0 || lanes < 1 || lanes > PS_MAX_LANES || !res) return -1;
-    switch (lanes) {   /* the two widths upstream ships get a specialised (vectorisable) copy */
+    switch (lanes) {   /* the widths upstream ships get a specialised (vectorisable) copy */
     case 8: return ps_core(s1, s1Len, s2, s2Len, open, gap, match, mismatch, 8, res, ops, ops_cap);
     case 16: return ps_core(s1, s1Len, s2, s2Len, open, gap, match, mismatch, 16, res, ops, ops_cap);
+    case 32: return ps_core(s1, s1Len, s2, s2Len, open, gap, match, mismatch, 32, res, ops, ops_cap);
     default: return ps_core(s1, s1Len, s2, s2Len, open, gap, match, mismatch, lanes, res, ops, ops_cap);
     }
 }
