@@ -203,14 +203,7 @@ inline void write_blocks(FILE *f, const uint8_t *data, size_t n, int level, int 
         const size_t len = std::min(kBlock, n - (size_t)k * kBlock);
         std::string &o = out[(size_t)k];
         o.resize(0x10000 + 64);
-        z_stream zs;
-        memset(&zs, 0, sizeof(zs));
-        deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
-        zs.next_in = const_cast<uint8_t *>(src); zs.avail_in = (uInt)len;
-        zs.next_out = reinterpret_cast<uint8_t *>(&o[18]); zs.avail_out = (uInt)(o.size() - 26);
-        deflate(&zs, Z_FINISH);
-        const size_t clen = zs.total_out;
-        deflateEnd(&zs);
+        const size_t clen = samio::deflate_block(src, len, reinterpret_cast<uint8_t *>(&o[18]), o.size() - 26, level);
         static const uint8_t head[16] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0 };
         memcpy(&o[0], head, 16);
         const uint32_t bsize = (uint32_t)(clen + 25);
@@ -273,7 +266,7 @@ struct Job {
     int device = 0;             // first device
     int n_gpus = 1;             // devices device .. device + n_gpus - 1, batches dealt round-robin
     int64_t batch_n = 1 << 20;
-    int level = 6;              // zlib level of -b output (htslib's default is zlib's default, 6)
+    int level = samio::kFastLevel;   // -b output: fastdeflate.hpp by default, --level 1..9 = zlib
     int con = 0;                // util.d:65-76: 0 SAM, 1 uBAM, 2 BAM
     std::string cl, version;
     std::string fasta_path;
@@ -339,7 +332,7 @@ struct RecordInput {
 };
 
 // the header as SAM text (con 0) or as the first BGZF block(s) of a BAM file (util.d:65-76)
-inline void write_header(const samio::Header &hdr, int con, int threads, int bam_level = 6)
+inline void write_header(const samio::Header &hdr, int con, int threads, int bam_level = samio::kFastLevel)
 {
     if (con == 0) {
         for (const auto &l : hdr.lines) { fwrite(l.data(), 1, l.size(), stdout); fputc('\n', stdout); }
@@ -405,7 +398,7 @@ inline int copy_records(FILE *fin, const std::string &pre, bool is_bam, int con,
             end += 4 + (size_t)bs;
         }
         if (end > in.spos) {
-            if (con != 0) write_blocks(stdout, &in.stream[in.spos], end - in.spos, con == 1 ? 0 : 6, threads);
+            if (con != 0) write_blocks(stdout, &in.stream[in.spos], end - in.spos, con == 1 ? 0 : samio::kFastLevel, threads);
             else {
                 std::string line;
                 for (size_t p = in.spos; p < end;) {

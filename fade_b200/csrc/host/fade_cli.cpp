@@ -30,11 +30,22 @@ const char *kVersion = "fade-b200-0.1";
 
 samio::LineSink *g_out = nullptr;   // stdout as SAM text, uBAM or BAM (util.d:65-76)
 
+// BAM output converts its lines in batches, so a line that cannot be encoded is reported by a LATER put() or by the close
+void report_unencodable() { fprintf(stderr, "fade-b200: cannot encode record for BAM output: %s\n", g_out->bad_line().c_str()); }
+
 bool out_line(const std::string &l)
 {
     if (g_out->put(l)) return true;
-    fprintf(stderr, "fade-b200: cannot encode record for BAM output: %s\n", l.c_str());
+    report_unencodable();
     return false;
+}
+
+// flushes and closes stdout; the command's exit code
+int close_output()
+{
+    if (g_out->close()) return 0;
+    report_unencodable();
+    return 1;
 }
 
 // Command-line options the way std.getopt with config.bundling reads them in the reference (app.d:73-107):
@@ -224,7 +235,8 @@ int usage()
             "      --min-length N   minimum soft-clip length considered (default 5)\n"
             "  -w, --window-size N  bases considered outside of the read region (default 300)\n"
             "      --batch N        records per GPU batch (default 1048576)\n"
-            "      --level N        zlib level of -b output, 0-9 (default 6, as htslib)\n"
+            "      --level N        compression of -b output: fast (default: built-in encoder, the size of zlib level 6 on BAM\n"
+            "                       records at several times its speed) or a zlib level 0-9\n"
             "      --device N       first CUDA device (default 0)\n"
             "      --gpus N         GPUs: batches are dealt round-robin to devices N0..N0+N-1, every GPU holds the reference\n"
             "                       (packed once, copied GPU to GPU), the records keep their input order (default 1)\n"
@@ -247,13 +259,14 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
     prm.min_length = (int32_t)opt.num("min-length", prm.min_length);
     prm.window_size = (int32_t)opt.num("window-size", prm.window_size);
     const int64_t batch_n = opt.num("batch", 1 << 20);
-    const int device = (int)opt.num("device", 0), n_gpus = (int)opt.num("gpus", 1), level = (int)opt.num("level", 6);
+    const int device = (int)opt.num("device", 0), n_gpus = (int)opt.num("gpus", 1);
+    const int level = (!opt.has("level") || opt.val.at("level") == "fast") ? samio::kFastLevel : (int)opt.num("level", 6);
     const bool text_path = opt.has("text-path");   // the line-by-line SAM text loop (A/B check of bamfast.hpp)
     const std::vector<std::string> &pos_args = opt.pos;
     int con = 0;
     if (pos_args.size() != 2) { usage(); return pos_args.empty() ? 0 : 1; }
     if (!output_container(opt, con)) return 1;
-    if (batch_n <= 0 || n_gpus < 1 || (text_path && n_gpus != 1) || level < 0 || level > 9) { fprintf(stderr, "fade-b200: bad --batch / --gpus / --level\n"); return 1; }
+    if (batch_n <= 0 || n_gpus < 1 || (text_path && n_gpus != 1) || level < samio::kFastLevel || level > 9) { fprintf(stderr, "fade-b200: bad --batch / --gpus / --level\n"); return 1; }
     fprintf(stderr, "[W::fade annotate] Output will keep the input order\n");
 
     FILE *fin_raw = pos_args[0] == "-" ? stdin : fopen(pos_args[0].c_str(), "rb");
@@ -427,7 +440,7 @@ static int cmd_annotate(int argc, char **argv, const std::string &cl)
     }
     if (src.failed()) { fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
     if (flush()) return 1;
-    g_out->close();
+    if (close_output()) return 1;
     fprintf(stderr, "[fade-b200 annotate] %lld records, %lld soft-clipped, %lld with artifact tags\n", (long long)n_total,
             (long long)n_sc, (long long)n_art);
     fadegpu_free_batch(bt);
@@ -699,8 +712,7 @@ int cmd_out(int argc, char **argv, const std::string &cl)
     }
     if (rc < 0) { fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str()); return 1; }
     st.print();
-    g_out->close();
-    return put_failed ? 1 : 0;   // a record that cannot be encoded for the chosen container is an error, not a silent drop
+    return (close_output() || put_failed) ? 1 : 0;   // a record that cannot be encoded for the chosen container is an error, not a silent drop
 }
 
 int cmd_extract(int argc, char **argv, const std::string &cl)
@@ -743,8 +755,7 @@ int cmd_extract(int argc, char **argv, const std::string &cl)
         }
     }
     if (rc < 0) { fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str()); return 1; }
-    g_out->close();
-    return 0;
+    return close_output();
 }
 
 // `fade-b200 sort -n`: name-sorted copy of the input (what config 5 of BASELINE.json uses `samtools sort -n`
@@ -785,8 +796,7 @@ int cmd_sort(int argc, char **argv)
     if (!have_hd) out_line("@HD\tVN:1.6\tSO:queryname");
     for (auto &h : sam.header) out_line(h);
     for (auto &x : recs) if (!out_line(x.line())) return 1;
-    g_out->close();
-    return 0;
+    return close_output();
 }
 
 // `fade-b200 fasta-digest <FASTA>`: name, length and FNV-1a hash of every contig as the loader sees it
@@ -801,6 +811,24 @@ int cmd_fasta_digest(int argc, char **argv)
         for (unsigned char ch : kv.second) { h ^= ch; h *= 1099511628211ull; }
         printf("%s\t%zu\t%016llx\n", kv.first.c_str(), kv.second.size(), (unsigned long long)h);
     }
+    return 0;
+}
+
+// `fade-b200 bgzf [--level fast|0..9] <file or ->`: the bytes of the file as a BGZF stream (the block compressor of the
+// BAM writers on arbitrary data; used by the tests to check the built-in DEFLATE encoder against zlib's inflate)
+int cmd_bgzf(int argc, char **argv)
+{
+    const Options opt = parse_options(argc, argv, 2, { { 0, "level", true }, { 't', "threads", true } });
+    if (!opt.ok || opt.pos.size() != 1) { usage(); return 1; }
+    const int level = (!opt.has("level") || opt.val.at("level") == "fast") ? samio::kFastLevel : (int)opt.num("level", 6);
+    if (level < samio::kFastLevel || level > 9) { fprintf(stderr, "fade-b200: bad --level\n"); return 1; }
+    FILE *f = opt.pos[0] == "-" ? stdin : fopen(opt.pos[0].c_str(), "rb");
+    if (!f) { fprintf(stderr, "fade-b200: cannot read %s\n", opt.pos[0].c_str()); return 1; }
+    samio::BgzfWriter bz(stdout, level);
+    std::vector<uint8_t> buf(1 << 20);
+    size_t got;
+    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) bz.write(buf.data(), got);
+    bz.finish();
     return 0;
 }
 
@@ -834,8 +862,7 @@ int cmd_view(int argc, char **argv)
         if (!line.empty() && !out_line(line)) return 1;
     }
     if (in.failed()) { fprintf(stderr, "fade-b200: damaged BAM input\n"); return 1; }
-    g_out->close();
-    return 0;
+    return close_output();
 }
 
 }  // namespace
@@ -851,6 +878,7 @@ int main(int argc, char **argv)
     if (strcmp(argv[1], "view") == 0) return cmd_view(argc, argv);
     if (strcmp(argv[1], "sort") == 0) return cmd_sort(argc, argv);
     if (strcmp(argv[1], "fasta-digest") == 0) return cmd_fasta_digest(argc, argv);
+    if (strcmp(argv[1], "bgzf") == 0) return cmd_bgzf(argc, argv);
     usage();
     return 1;
 }

@@ -13,6 +13,7 @@
 // RNEXT prints "=" when it equals RNAME; a missing quality string is 0xff bytes.
 #pragma once
 #include <zlib.h>
+#include "fastdeflate.hpp"
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -129,6 +130,25 @@ private:
     bool bad_ = false;
 };
 
+// Compression levels of BAM output: kFastLevel = the encoder of fastdeflate.hpp (the default of -b: the size of zlib
+// level 6 on BAM records at six times its speed), 0 = stored, 1..9 = zlib.
+constexpr int kFastLevel = -1;
+
+// raw DEFLATE stream of src[0, n) (n <= 0xff00) into dst (capacity >= n + 1024); returns its size
+inline size_t deflate_block(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, int level)
+{
+    if (level < 0) return fastdeflate::compress(src, n, dst, cap);
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+    zs.next_in = const_cast<uint8_t *>(src); zs.avail_in = (uInt)n;
+    zs.next_out = dst; zs.avail_out = (uInt)cap;
+    deflate(&zs, Z_FINISH);
+    const size_t clen = zs.total_out;
+    deflateEnd(&zs);
+    return clen;
+}
+
 class BgzfWriter {
 public:
     BgzfWriter(FILE *f, int level) : f_(f), level_(level) { buf_.reserve(kBlock); }
@@ -172,14 +192,7 @@ private:
             const std::vector<uint8_t> &in = pend_[(size_t)k];
             std::string &o = out[(size_t)k];
             o.resize(0x10000 + 64);
-            z_stream zs;
-            memset(&zs, 0, sizeof(zs));
-            deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
-            zs.next_in = const_cast<uint8_t *>(in.data()); zs.avail_in = (uInt)in.size();
-            zs.next_out = reinterpret_cast<uint8_t *>(&o[18]); zs.avail_out = (uInt)(o.size() - 18 - 8);
-            deflate(&zs, Z_FINISH);
-            const size_t clen = zs.total_out;
-            deflateEnd(&zs);
+            const size_t clen = deflate_block(in.data(), in.size(), reinterpret_cast<uint8_t *>(&o[18]), o.size() - 18 - 8, level_);
             static const uint8_t head[16] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0 };
             memcpy(&o[0], head, 16);
             const uint32_t bsize = (uint32_t)(clen + 18 + 8 - 1);
@@ -481,15 +494,53 @@ public:
     {
         if (!bam_) return text_line(line);
         if (hdr_pos_ < hdr_.lines.size()) { line = hdr_.lines[hdr_pos_++]; return true; }
-        uint8_t b4[4];
-        if (!bz_->read(b4, 4)) return false;
-        const uint32_t bs = get_u32(b4);
-        rec_.resize(bs);
-        if (!bz_->read(rec_.data(), bs) || !bam_to_sam(rec_.data(), bs, hdr_, line)) { fail_ = true; return false; }
+        if (q_pos_ == q_.size() && !refill()) return false;
+        line.swap(q_[q_pos_++]);
         return true;
     }
 
 private:
+    // BAM input: the records of the next stretch of the file are read in order and converted to SAM text side by side
+    bool refill()
+    {
+        q_.clear();
+        q_pos_ = 0;
+        if (fail_) return false;
+        raw_.clear();
+        off_.clear();
+        while (off_.size() < kBatch) {
+            uint8_t b4[4];
+            if (!bz_->read(b4, 4)) break;
+            const uint32_t bs = get_u32(b4);
+            if (bs > (1u << 29)) { fail_ = true; break; }
+            const size_t at = raw_.size();
+            raw_.resize(at + bs);
+            if (!bz_->read(raw_.data() + at, bs)) { fail_ = true; break; }
+            off_.push_back(at);
+        }
+        off_.push_back(raw_.size());
+        const long n = (long)off_.size() - 1;
+        if (n <= 0) return false;
+        q_.resize((size_t)n);
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad) if (n > 256)
+        for (long k = 0; k < n; ++k)
+            if (!bam_to_sam(raw_.data() + off_[(size_t)k], off_[(size_t)k + 1] - off_[(size_t)k], hdr_, q_[(size_t)k])) bad |= 1;
+        if (bad) {   // serve the records before the first damaged one, then fail
+            fail_ = true;
+            std::string tmp;
+            size_t good = 0;
+            while (good < (size_t)n && bam_to_sam(raw_.data() + off_[good], off_[good + 1] - off_[good], hdr_, tmp)) ++good;
+            q_.resize(good);
+        }
+        return !q_.empty();
+    }
+    static constexpr size_t kBatch = 1 << 15;
+    std::vector<std::string> q_;
+    size_t q_pos_ = 0;
+    std::vector<uint8_t> raw_;
+    std::vector<size_t> off_;
+
     bool text_line(std::string &line)
     {
         line.clear();
@@ -559,29 +610,54 @@ public:
         if (mode_ == SAM) { fwrite(line.data(), 1, line.size(), f_); fputc('\n', f_); return true; }
         if (!line.empty() && line[0] == '@' && !started_) { hdr_.add_line(line); return true; }
         if (!started_) start();
-        if (!sam_to_bam(line, hdr_, rec_)) return false;
-        std::string bs;
-        put_u32(bs, (uint32_t)rec_.size());
-        bz_->write(bs.data(), 4);
-        bz_->write(rec_.data(), rec_.size());
-        return true;
+        if (failed_) return false;
+        // lines are converted to binary records side by side, kBatch at a time; a line that cannot be encoded makes
+        // this and every later put() fail (the caller stops: the output would lack a record)
+        pend_.push_back(line);
+        if (pend_.size() >= kBatch) flush_lines();
+        return !failed_;
     }
-    void close()
+    bool close()
     {
-        if (closed_) return;
+        if (closed_) return !failed_;
         closed_ = true;
-        if (mode_ == SAM) { fflush(f_); return; }
+        if (mode_ == SAM) { fflush(f_); return true; }
         if (!started_) start();
+        flush_lines();
         bz_->finish();
         delete bz_;
         bz_ = nullptr;
+        return !failed_;
     }
+    const std::string &bad_line() const { return bad_line_; }
 
 private:
+    void flush_lines()
+    {
+        const long n = (long)pend_.size();
+        if (!n) return;
+        recs_.resize((size_t)n);
+        long first_bad = n;
+#pragma omp parallel for schedule(static) reduction(min : first_bad) if (n > 256)
+        for (long k = 0; k < n; ++k)
+            if (!sam_to_bam(pend_[(size_t)k], hdr_, recs_[(size_t)k])) first_bad = std::min(first_bad, k);
+        for (long k = 0; k < first_bad; ++k) {
+            std::string bs;
+            put_u32(bs, (uint32_t)recs_[(size_t)k].size());
+            bz_->write(bs.data(), 4);
+            bz_->write(recs_[(size_t)k].data(), recs_[(size_t)k].size());
+        }
+        if (first_bad < n) { failed_ = true; bad_line_ = pend_[(size_t)first_bad]; }
+        pend_.clear();
+    }
+    static constexpr size_t kBatch = 1 << 15;
+    std::vector<std::string> pend_, recs_;
+    bool failed_ = false;
+    std::string bad_line_;
     void start()
     {
         started_ = true;
-        bz_ = new BgzfWriter(f_, mode_ == UBAM ? 0 : 6);
+        bz_ = new BgzfWriter(f_, mode_ == UBAM ? 0 : kFastLevel);
         std::string text;
         for (const auto &l : hdr_.lines) { text += l; text += '\n'; }
         std::string o("BAM\1", 4);
