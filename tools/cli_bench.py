@@ -37,7 +37,7 @@ def main():
     print(f"inputs: {a.reads} reads, SAM {os.path.getsize(sam) >> 20} MiB, BAM {os.path.getsize(bam) >> 20} MiB ({time.time() - t:.0f} s to write)",
           flush=True)
     env = dict(os.environ, FADE_TIMING="1")
-    combos = [(bam, ["-b"]), (bam, ["-b"]), (bam, ["-b", "--level", "1"]), (bam, ["-u"]), (bam, []), (sam, []), (sam, ["-b"])]
+    combos = [(bam, ["-b"]), (bam, ["-b"]), (bam, ["-b", "--level", "6"]), (bam, ["-b", "--level", "1"]), (bam, ["-u"]), (bam, []), (sam, []), (sam, ["-b"])]
     if a.combos == "bam":
         combos = combos[:2]
     for g in [int(x) for x in a.gpus.split(",")]:
