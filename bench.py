@@ -513,10 +513,9 @@ def main():
             dt, _ = e2e_step()
             e_s += dt
             e2e_steps.append(dt)
-            copies_total = dict(copies)
-            if s == 0:
-                agg.setdefault("h2d", 0); agg.setdefault("d2h", 0)
-                agg["h2d"] += copies_total["h2d"]; agg["d2h"] += copies_total["d2h"]
+            if s == 0:          # bytes over PCIe of ONE pass over this group
+                agg["h2d"] = agg.get("h2d", 0) + copies["h2d"]
+                agg["d2h"] = agg.get("d2h", 0) + copies["d2h"]
         barrier()
         sampler.window(t_w0, time.time())
         for b in (live if path != "arrays" else batches):
