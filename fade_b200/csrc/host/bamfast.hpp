@@ -51,8 +51,8 @@ public:
             const int64_t clen = bsize - xlen - 19;
             if (bsize < 0 || clen < 0 || clen > 0x10000) { bad_ = true; return false; }
             Blk b;
-            b.c.resize((size_t)clen + 8);
-            if (raw(b.c.data(), b.c.size()) != b.c.size()) { bad_ = true; return false; }
+            b.c.resize((size_t)clen + 16);     // trailer + the read slack of the built-in decoder
+            if (raw(b.c.data(), (size_t)clen + 8) != (size_t)clen + 8) { bad_ = true; return false; }
             b.crc = get_u32(&b.c[(size_t)clen]);
             b.isize = get_u32(&b.c[(size_t)clen + 4]);
             if (b.isize > 0x10000) { bad_ = true; return false; }   // SAMv1 4.1: a block inflates to at most 64 KiB
@@ -67,16 +67,7 @@ public:
 #pragma omp parallel for schedule(dynamic, 4) reduction(| : bad) num_threads(threads_)
         for (long k = 0; k < (long)blks.size(); ++k) {
             const Blk &b = blks[(size_t)k];
-            if (!b.isize) continue;
-            z_stream zs;
-            memset(&zs, 0, sizeof(zs));
-            if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; continue; }
-            zs.next_in = const_cast<uint8_t *>(b.c.data()); zs.avail_in = (uInt)(b.c.size() - 8);
-            zs.next_out = out.data() + base + b.off; zs.avail_out = b.isize;
-            const int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END || zs.avail_out != 0 ||
-                crc32(crc32(0, nullptr, 0), out.data() + base + b.off, b.isize) != b.crc) bad = 1;
+            if (!samio::inflate_block(b.c.data(), b.c.size() - 16, out.data() + base + b.off, b.isize, b.crc)) bad = 1;
         }
         if (bad) bad_ = true;
         return !bad;

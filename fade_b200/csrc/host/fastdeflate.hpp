@@ -165,7 +165,7 @@ inline size_t stored_block(const uint8_t *src, size_t n, uint8_t *dst)
     dst[0] = 1;   // BFINAL = 1, BTYPE = 00
     dst[1] = (uint8_t)(n & 0xff); dst[2] = (uint8_t)(n >> 8);
     dst[3] = (uint8_t)(~n & 0xff); dst[4] = (uint8_t)((~n >> 8) & 0xff);
-    memcpy(dst + 5, src, n);
+    if (n) memcpy(dst + 5, src, n);
     return n + 5;
 }
 

@@ -14,6 +14,7 @@
 #pragma once
 #include <zlib.h>
 #include "fastdeflate.hpp"
+#include "fastinflate.hpp"
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -31,6 +32,23 @@ inline uint32_t get_u32(const uint8_t *p) { return get_u16(p) | (get_u16(p + 2) 
 inline int32_t get_i32(const uint8_t *p) { return (int32_t)get_u32(p); }
 
 // ---- BGZF -----------------------------------------------------------------------------------
+// Payload of one BGZF block: cdata[0, clen) is the raw DEFLATE stream and cdata must be readable up to clen + 16 (the
+// block's 8-byte trailer follows it in the file; callers allocate 8 bytes more).  The built-in decoder runs first; its
+// result is accepted only if size and CRC-32 match, otherwise zlib decides (a damaged block fails there as well).
+inline bool inflate_block(const uint8_t *cdata, size_t clen, uint8_t *out, uint32_t isize, uint32_t crc)
+{
+    if (isize == 0) return true;
+    if (fastinflate::inflate(cdata, clen, out, isize) && (uint32_t)crc32(crc32(0, nullptr, 0), out, isize) == crc) return true;
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<uint8_t *>(cdata); zs.avail_in = (uInt)clen;
+    zs.next_out = out; zs.avail_out = isize;
+    const int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    return rc == Z_STREAM_END && zs.avail_out == 0 && (uint32_t)crc32(crc32(0, nullptr, 0), out, isize) == crc;
+}
+
 class BgzfReader {
 public:
     explicit BgzfReader(FILE *f, const std::string &prefetched) : f_(f), raw_(prefetched) {}
@@ -86,7 +104,7 @@ private:
                 const int64_t clen = bsize - xlen - 19;
                 if (clen < 0 || clen > 0x10000) { bad_ = true; return false; }
                 Raw r;
-                r.c.resize((size_t)clen + 8);
+                r.c.resize((size_t)clen + 16);     // trailer + the read slack of the built-in decoder
                 if (!raw_read(r.c.data(), (size_t)clen + 8)) { bad_ = true; return false; }
                 r.crc = get_u32(&r.c[(size_t)clen]);
                 r.isize = get_u32(&r.c[(size_t)clen + 4]);
@@ -105,15 +123,7 @@ private:
 #pragma omp parallel for schedule(dynamic, 4) reduction(| : bad) if (ng > 8)
             for (long k = 0; k < ng; ++k) {
                 const Raw &r = grp[(size_t)k];
-                if (!r.isize) continue;
-                z_stream zs;
-                memset(&zs, 0, sizeof(zs));
-                if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; continue; }
-                zs.next_in = const_cast<uint8_t *>(r.c.data()); zs.avail_in = (uInt)(r.c.size() - 8);
-                zs.next_out = blk_.data() + r.off; zs.avail_out = r.isize;
-                const int rc = inflate(&zs, Z_FINISH);
-                inflateEnd(&zs);
-                if (rc != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0, nullptr, 0), blk_.data() + r.off, r.isize) != r.crc) bad = 1;
+                if (!inflate_block(r.c.data(), r.c.size() - 16, blk_.data() + r.off, r.isize, r.crc)) bad = 1;
             }
             if (bad) { bad_ = true; return false; }
             if (total) return true;

@@ -139,3 +139,42 @@ def test_builtin_deflate_encoder_is_read_back_by_zlib(tmp_path):
     a = run("bgzf", "-", input=cases["acgt"]).stdout
     b = run("bgzf", "-t", "1", "-", input=cases["acgt"]).stdout
     assert a == b and bamcodec.bgzf_decode(a) == cases["acgt"]
+
+
+def test_reader_decodes_every_kind_of_deflate_block(sam, tmp_path):
+    """BGZF blocks as other writers may produce them -- stored, fixed-Huffman, Huffman-only, several DEFLATE blocks per BGZF
+    block -- are read identically by both readers (built-in decoder first, zlib behind it); a block whose CRC does not match
+    its payload is damaged input."""
+    import bamcodec
+    ref = run("view", sam).stdout
+    payload = bamcodec.bgzf_decode(run("view", "-u", sam).stdout)
+
+    def block(data, level, strategy, split=False):
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+        c = b""
+        if split and len(data) > 100:
+            c += co.compress(data[: len(data) // 3]) + co.flush(zlib.Z_FULL_FLUSH)
+            c += co.compress(data[len(data) // 3:]) + co.flush(zlib.Z_SYNC_FLUSH)
+            c += co.flush()
+        else:
+            c = co.compress(data) + co.flush()
+        head = b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(c) + 25)
+        return head + c + struct.pack("<II", zlib.crc32(data), len(data))
+
+    eof = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    for name, (level, strategy, split, size) in {"stored": (0, zlib.Z_DEFAULT_STRATEGY, False, 60000), "fixed": (6, zlib.Z_FIXED, False, 30000),
+                                                 "huffman": (6, zlib.Z_HUFFMAN_ONLY, False, 65000), "rle": (9, zlib.Z_RLE, False, 1000),
+                                                 "multi": (6, zlib.Z_DEFAULT_STRATEGY, True, 50000), "tiny": (1, zlib.Z_DEFAULT_STRATEGY, False, 7)}.items():
+        f = tmp_path / f"{name}.bam"
+        f.write_bytes(b"".join(block(payload[a:a + size], level, strategy, split) for a in range(0, len(payload), size)) + eof)
+        for bulk in ([], ["--bulk"]):
+            p = run("view", *bulk, str(f))
+            assert p.returncode == 0 and p.stdout == ref, (name, bulk, p.stderr)
+        assert run("view", "--count", str(f)).stdout.strip() == b"400"
+    bad = bytearray(block(payload[:40000], 6, zlib.Z_DEFAULT_STRATEGY) + eof)
+    bad[-28 - 8] ^= 0x01                                   # the CRC of the first block
+    g = tmp_path / "crc.bam"
+    g.write_bytes(bytes(bad))
+    for bulk in ([], ["--bulk"]):
+        p = run("view", *bulk, str(g))
+        assert p.returncode == 1 and p.stdout == b"" and (b"damaged" in p.stderr or b"cannot read" in p.stderr)
