@@ -21,6 +21,7 @@
 #include <vector>
 #include "../../../include/fadegpu.h"
 #include "../../../include/fadehost.h"
+#include <parallel/algorithm>
 #include "samio.hpp"
 #include "bamfast.hpp"
 
@@ -601,22 +602,33 @@ SamRec clip_read(const SamRec &rec, int rs, const Sam &sam)
 }
 
 // source/filter.d:127-165
-int natural_compare(std::string a, std::string b)
+// numericallyAwareStringComparison of source/filter.d:127-165, on the strings in place: while both have characters
+// left -- two non-digits are compared as characters; otherwise each side's leading digits are read as a number (-1 when
+// there are none, which consumes nothing) and compared; when everything compared equal the shorter string comes first.
+int natural_compare(const char *a, size_t na, const char *b, size_t nb)
 {
     auto isd = [](char c) { return c >= '0' && c <= '9'; };
-    while (!a.empty() && !b.empty()) {
-        if (!isd(a[0]) && !isd(b[0])) {
-            if (a[0] == b[0]) { a.erase(0, 1); b.erase(0, 1); continue; }
-            return a[0] < b[0] ? -1 : 1;
+    const char *const ae = a + na, *const be = b + nb;
+    while (a < ae && b < be) {
+        if (!isd(*a) && !isd(*b)) {
+            if (*a == *b) { ++a; ++b; continue; }
+            return *a < *b ? -1 : 1;
         }
-        auto take = [&](std::string &s) { long v = -1; size_t k = 0; while (k < s.size() && isd(s[k])) ++k; if (k) { v = atol(s.substr(0, k).c_str()); s.erase(0, k); } return v; };
-        const std::string a0 = a, b0 = b;
-        const long ai = take(a), bi = take(b);
+        auto take = [&](const char *&p, const char *e) {
+            if (p == e || !isd(*p)) return -1L;
+            unsigned long long v = 0;
+            while (p < e && isd(*p)) { if (v < (1ull << 62) / 10) v = v * 10 + (unsigned)(*p - '0'); else v = (1ull << 62); ++p; }
+            return (long)v;
+        };
+        const char *a0 = a, *b0 = b;
+        const long ai = take(a, ae), bi = take(b, be);
         if (ai == bi) { if (a == a0 && b == b0) return 0; continue; }
         return ai < bi ? -1 : 1;
     }
-    return a.size() == b.size() ? 0 : (a.size() < b.size() ? -1 : 1);
+    const size_t ra = (size_t)(ae - a), rb = (size_t)(be - b);
+    return ra == rb ? 0 : (ra < rb ? -1 : 1);
 }
+int natural_compare(const std::string &a, const std::string &b) { return natural_compare(a.data(), a.size(), b.data(), b.size()); }
 
 struct OutStats {   // source/stats.d:16-72
     long read_count = 0, clipped = 0, sup = 0, art_sup = 0, art = 0, aln_l = 0, aln_r = 0;
@@ -772,31 +784,84 @@ int cmd_sort(int argc, char **argv)
     const std::string path = opt.pos[0];
     int con = 0;
     if (!output_container(opt, con)) return 1;
-    open_output(con);
-    Sam sam;
-    if (!sam.open(path)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
-    std::vector<SamRec> recs;
-    SamRec r;
-    int rc;
-    while ((rc = sam.next(r)) == 1) recs.push_back(r);
-    if (rc < 0) { fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str()); return 1; }
-    std::stable_sort(recs.begin(), recs.end(), [](const SamRec &a, const SamRec &b) {
-        const int c = natural_compare(a.f[0], b.f[0]);
+    const int threads = (int)opt.num("threads", 0) > 0 ? (int)opt.num("threads", 0) : omp_get_max_threads();
+    FILE *f = path == "-" ? stdin : fopen(path.c_str(), "rb");
+    if (!f) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
+    std::string pre(2, '\0');
+    pre.resize(fread(&pre[0], 1, 2, f));
+    const bool is_bam = pre.size() == 2 && (uint8_t)pre[0] == 0x1f && (uint8_t)pre[1] == 0x8b;
+    // every record as BAM bytes in one buffer (SAM lines are converted on the way in); only a 16-byte key per record
+    // is sorted, and the records are gathered in that order on the way out
+    bamfast::RecordInput in(f, pre, is_bam, threads);
+    if (!in.read_header()) return 1;
+    for (;;) {
+        const size_t have = in.stream.size() - in.spos;
+        if (!in.need(have + 1)) break;
+    }
+    if (in.bad()) { fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str()); return 1; }
+    struct Key { uint64_t off; uint32_t name; uint8_t len, pair; };
+    std::vector<Key> keys;
+    std::vector<char> names;
+    const std::vector<uint8_t> &st = in.stream;
+    for (size_t p2 = in.spos; p2 < st.size();) {
+        const size_t left = st.size() - p2;
+        const uint32_t bs = left >= 4 ? bamfast::get_u32(&st[p2]) : 0;
+        const uint32_t ln = left >= 36 ? st[p2 + 4 + 8] : 0;
+        if (left < 36 || bs < 32 || (size_t)bs + 4 > left || ln < 1 || 32 + ln > bs || names.size() > 0xffffff00u) {
+            fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str());
+            return 1;
+        }
+        const char *nm = reinterpret_cast<const char *>(&st[p2 + 36]);
+        const size_t nl = strnlen(nm, ln);
+        keys.push_back({ (uint64_t)p2, (uint32_t)names.size(), (uint8_t)nl, (uint8_t)(bamfast::get_u16(&st[p2 + 4 + 14]) & 0xc0) });
+        names.insert(names.end(), nm, nm + nl);
+        p2 += 4 + (size_t)bs;
+    }
+    // name, then first / second of the pair, input order among equals
+    omp_set_num_threads(threads);
+    __gnu_parallel::stable_sort(keys.begin(), keys.end(), [&](const Key &x, const Key &y) {
+        const int c = natural_compare(&names[x.name], x.len, &names[y.name], y.len);
         if (c) return c < 0;
-        return (atoi(a.f[1].c_str()) & 0xc0) < (atoi(b.f[1].c_str()) & 0xc0);
+        return x.pair < y.pair;
     });
     bool have_hd = false;
-    for (auto &h : sam.header) {   // @HD SO:queryname, as samtools sort -n writes it
+    for (auto &h : in.hdr.lines) {   // @HD SO:queryname, as samtools sort -n writes it
         if (h.compare(0, 3, "@HD") != 0) continue;
         have_hd = true;
         const size_t a = h.find("\tSO:");
         if (a == std::string::npos) h += "\tSO:queryname";
         else { const size_t e = h.find('\t', a + 1); h.replace(a, (e == std::string::npos ? h.size() : e) - a, "\tSO:queryname"); }
     }
-    if (!have_hd) out_line("@HD\tVN:1.6\tSO:queryname");
-    for (auto &h : sam.header) out_line(h);
-    for (auto &x : recs) if (!out_line(x.line())) return 1;
-    return close_output();
+    if (!have_hd) in.hdr.lines.insert(in.hdr.lines.begin(), "@HD\tVN:1.6\tSO:queryname");
+    bamfast::write_header(in.hdr, con, threads);
+    constexpr size_t kBatch = 1 << 17;   // records gathered (BAM) or converted to text (SAM) side by side per write
+    std::vector<uint8_t> gathered;
+    std::vector<size_t> at(kBatch + 1);
+    std::vector<std::string> lines(con == 0 ? kBatch : 0);
+    for (size_t k0 = 0; k0 < keys.size(); k0 += kBatch) {
+        const size_t nk = std::min(kBatch, keys.size() - k0);
+        if (con != 0) {
+            at[0] = 0;
+            for (size_t k = 0; k < nk; ++k) at[k + 1] = at[k] + 4 + bamfast::get_u32(&st[keys[k0 + k].off]);
+            gathered.resize(at[nk]);
+#pragma omp parallel for schedule(static) num_threads(threads)
+            for (long k = 0; k < (long)nk; ++k) memcpy(&gathered[at[(size_t)k]], &st[keys[k0 + (size_t)k].off], at[(size_t)k + 1] - at[(size_t)k]);
+            bamfast::write_blocks(stdout, gathered.data(), gathered.size(), con == 1 ? 0 : samio::kFastLevel, threads);
+        } else {
+            int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad) num_threads(threads)
+            for (long k = 0; k < (long)nk; ++k) {
+                const size_t o = (size_t)keys[k0 + (size_t)k].off;
+                if (!samio::bam_to_sam(&st[o + 4], bamfast::get_u32(&st[o]), in.hdr, lines[(size_t)k])) bad = 1;
+                else lines[(size_t)k].push_back('\n');
+            }
+            if (bad) { fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str()); return 1; }
+            for (size_t k = 0; k < nk; ++k) fwrite(lines[k].data(), 1, lines[k].size(), stdout);
+        }
+    }
+    if (con != 0) bamfast::write_eof_marker();
+    if (fflush(stdout) != 0 || ferror(stdout)) { fprintf(stderr, "fade-b200: write error\n"); return 1; }
+    return 0;
 }
 
 // `fade-b200 fasta-digest <FASTA>`: name, length and FNV-1a hash of every contig as the loader sees it

@@ -174,3 +174,48 @@ def test_sort_by_name_feeds_out(tmp_path):
     assert p2.returncode == 0
     dec = bamcodec.decode(p2.stdout)
     assert dec[0] == "@HD\tVN:1.6\tSO:queryname" and [ln for ln in dec if not ln.startswith("@")] == body
+
+
+def test_sort_by_name_order_is_the_reference_comparison_on_awkward_names(tmp_path):
+    """The sort works on binary records with its own in-place restatement of filter.d:127-165: names mixing
+    letters, digit runs, leading zeros and shared prefixes must come out in the order of the Python restatement,
+    names that compare equal ("a01" / "a1") keep their input order, first of pair precedes second, and the SAM and
+    BAM routes agree."""
+    import functools
+    import random
+    import bamcodec
+    rng = random.Random(5)
+    alphabet = ["a", "b", ":", "_", "0", "1", "9", "10", "007"]
+    names = ["".join(rng.choice(alphabet) for _ in range(rng.randint(1, 7))) for _ in range(1500)]
+    names += ["a1", "a01", "a001", "x", "x", "9", "09"]
+    head = ["@HD\tVN:1.6\tSO:unsorted", "@SQ\tSN:c\tLN:1000"]
+    recs = []
+    for k, nm in enumerate(names):
+        flag = rng.choice([0x41, 0x81, 0])
+        recs.append(f"{nm}\t{flag}\tc\t{1 + k % 900}\t60\t4M\t*\t0\t0\tACGT\tIIII\tXI:i:{k}")
+    path = tmp_path / "in.sam"
+    path.write_text("\n".join(head + recs) + "\n")
+    p = subprocess.run([BIN, "sort", "-n", str(path)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    body = [ln for ln in p.stdout.splitlines() if not ln.startswith("@")]
+
+    def key_cmp(x, y):
+        fx, fy = x.split("\t"), y.split("\t")
+        c = cons.natural_compare(fx[0], fy[0])
+        return c if c else ((int(fx[1]) & 0xc0) > (int(fy[1]) & 0xc0)) - ((int(fx[1]) & 0xc0) < (int(fy[1]) & 0xc0))
+    assert body == sorted(recs, key=functools.cmp_to_key(key_cmp))     # sorted() is stable, like the tool
+    p2 = subprocess.run([BIN, "sort", "-nb", "-"], input=bamcodec.encode(head + recs), capture_output=True)
+    assert p2.returncode == 0 and [ln for ln in bamcodec.decode(p2.stdout) if not ln.startswith("@")] == body
+
+
+def test_sort_refuses_damaged_input(tmp_path):
+    import bamcodec
+    head = ["@HD\tVN:1.6", "@SQ\tSN:c\tLN:1000"]
+    recs = [f"r{k}\t0\tc\t{1 + k}\t60\t4M\t*\t0\t0\tACGT\tIIII" for k in range(50)]
+    bad = tmp_path / "bad.sam"
+    bad.write_text("\n".join(head + recs[:20] + ["only\tthree\tfields"] + recs[20:]) + "\n")
+    p = subprocess.run([BIN, "sort", "-n", str(bad)], capture_output=True)
+    assert p.returncode == 1 and b"malformed" in p.stderr and b"r0" not in p.stdout
+    raw = bamcodec.encode(head + recs)
+    cut = subprocess.run([BIN, "sort", "-n", "-"], input=raw[: len(raw) - 60], capture_output=True)
+    assert cut.returncode == 1 and b"r0" not in cut.stdout
