@@ -26,7 +26,7 @@ through the C ABI (libfadegpu.so).  Workloads (BASELINE.json `configs`):
          --e2e-path arrays: fadegpu_submit_inputs on pageable caller arrays.
   roofline  INT16x2 ALU roofline: cells/s against 2*R_alu/9 and against 2*R_alu/7.5 (the
          fill kernel's own instruction mix), R_alu measured live by fadegpu_measure_alu_peak.
-  cpu_baseline  a CPU port of the path (oracle/fade_oracle_simd.c: AVX2, 16 alignments per vector, trace
+  cpu_baseline  a CPU port of the path (oracle/fade_oracle_simd.c: AVX-512BW / AVX2, 32 / 16 alignments per vector, trace
          table + traceback, OpenMP on the host cores; validated against the scalar oracle) timed on a
          bounded sample of the same reads, and the scalar oracle beside it.  `--impl reference` prints
          that arm alone.
@@ -75,7 +75,7 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=CHUNK)
     ap.add_argument("--group", type=int, default=10, help="chunks resident (pinned host + HBM) at a time")
     ap.add_argument("--cpu-sample", type=int, default=4_000_000,
-                    help="reads in the cpu_baseline sample (4 M reads = about 30 core-seconds of the AVX2 port)")
+                    help="reads in the cpu_baseline sample (4 M reads = about 30 core-seconds of the SIMD port)")
     ap.add_argument("--scalar-sample", type=int, default=200_000, help="reads in the scalar-oracle sample (0 = skip)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
     ap.add_argument("--depth", type=int, default=3, help="chunks in flight in the e2e loop")
@@ -208,7 +208,13 @@ class Workload:
                 "l2": "inputs + checkpoint scratch per chunk (>2 GB) exceed the 126 MB L2; no explicit flush"}
 
 
-CPU_KIND = ("AVX2 16-lane inter-sequence port of the path (oracle/fade_oracle_simd.c: SW fill with trace table, "
+def cpu_kind() -> str:
+    """What the SIMD arm is on this host: the widest of AVX-512BW (32 int16 lanes) and AVX2 (16) the CPU runs."""
+    from oracle import oracle as orc
+    lanes = orc.simd_lanes()
+    isa = {32: "AVX-512BW 32-lane (AVX2 16-lane where a 32-lane trace table would pass 8 MB per thread)",
+           16: "AVX2 16-lane"}.get(lanes, "scalar (no AVX2 on this host)")
+    return (f"{isa} inter-sequence port of the path (oracle/fade_oracle_simd.c: SW fill with trace table, "
             "traceback, predicates; in-memory reference), validated against the scalar oracle")
 
 
@@ -246,7 +252,7 @@ def run_reference(args, rank: int, world: int):
         if i >= args.warmup:
             vals.append(v); gc.append(g)
     v = statistics.mean(vals)
-    sample = f"first {rd.n} reads of the workload per step; {CPU_KIND}; OpenMP {threads} threads"
+    sample = f"first {rd.n} reads of the workload per step; {cpu_kind()}; OpenMP {threads} threads"
     line = {
         "impl": "reference", "metric": "annotate_reads_per_sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * rd.n / v,
@@ -557,7 +563,7 @@ def main():
         hbm_bytes = agg.get("h2d", 0) + agg.get("d2h", 0) + n_al * 270
         cb_v, cb_g, cb_n, cb_dt = cb
         cpu = {"value": cb_v, "unit": "reads/s", "cores": host_threads, "kind": "port", "gcups": cb_g,
-               "sample": f"first {cb_n} reads of the workload; {CPU_KIND}; OpenMP {host_threads} threads, {cb_dt:.1f} s"}
+               "sample": f"first {cb_n} reads of the workload; {cpu_kind()}; OpenMP {host_threads} threads, {cb_dt:.1f} s"}
         if scalar:
             cpu["scalar"] = {"value": scalar[0], "unit": "reads/s", "gcups": scalar[1], "cores": host_threads,
                              "sample": f"first {scalar[2]} reads; the scalar oracle (oracle/fade_oracle.c, the parity authority), "

@@ -127,8 +127,10 @@ int fo_align_batch(int64_t n, const uint8_t *seq4, const int64_t *seq_off, const
                    const fo_params *p, fo_read_result *res, uint32_t *ops_out, int ops_cap,
                    int n_threads);
 
-/* AVX2 inter-sequence implementation of the same contract (fade_oracle_simd.c): the CPU baseline
- * of bench.py.  Falls back to fo_align_batch on CPUs without AVX2. */
+/* AVX2 / AVX-512BW inter-sequence implementation of the same contract (fade_oracle_simd.c): the CPU baseline
+ * of bench.py.  Uses the widest of the two the host supports (fo_simd_lanes(): 32, 16, or 0 = neither, in which
+ * case it falls back to fo_align_batch); FADE_ORACLE_SIMD=avx2 in the environment forces 16 lanes. */
+int fo_simd_lanes(void);
 int fo_align_batch_simd(int64_t n, const uint8_t *seq4, const int64_t *seq_off, const int32_t *l_qseq,
                         const int32_t *tid, const int64_t *pos, const int32_t *aligned_len,
                         const int32_t *clip_left, const int32_t *clip_right,

@@ -1,6 +1,6 @@
 /*
- * fade_oracle_simd.c -- AVX2 (16 x int16 lanes, one alignment per lane) CPU implementation of the
- * same path, used ONLY as the reported CPU baseline of bench.py (cpu_baseline / --impl reference)
+ * fade_oracle_simd.c -- AVX2 (16 x int16 lanes) / AVX-512BW (32 lanes), one alignment per lane: CPU implementation
+ * of the same path (the widest the host supports is chosen at run time; FADE_ORACLE_SIMD=avx2 forces 16 lanes), used ONLY as the reported CPU baseline of bench.py (cpu_baseline / --impl reference)
  * and validated against the scalar oracle in tests/.  TEST / MEASUREMENT INFRASTRUCTURE, not
  * product code.  PARITY UNPINNED like the scalar oracle it mirrors (see fade_oracle.h).
  *
@@ -20,7 +20,7 @@
 #include <omp.h>
 #endif
 
-#define LANES 16
+#define MAX_LANES 32
 enum { T_ZERO = 0, T_DIAG = 1, T_F = 2, T_E = 3, T_EOPEN = 4, T_FOPEN = 8 };
 
 static inline int map5(unsigned char c)
@@ -32,41 +32,36 @@ static inline int map5(unsigned char c)
 }
 
 typedef struct {
-    int read[LANES];
-    int qlen[LANES], tlen[LANES];
-    int64_t start[LANES];
-    int n;
-} simd_batch;
-
-typedef struct {
-    int16_t *q;      /* [qmax][16] query codes (pad = 100+lane-independent mismatch code) */
-    int16_t *t;      /* [tmax][16] target codes */
-    __m256i *H, *E;  /* [qmax] */
-    uint8_t *tr;     /* [qmax*tmax][16] */
+    int16_t *q;      /* [qmax][lanes] query codes (pad = 100+lane-independent mismatch code) */
+    int16_t *t;      /* [tmax][lanes] target codes */
+    int16_t *H, *E;  /* [qmax][lanes] */
+    uint8_t *tr;     /* [qmax*tmax][lanes] */
     size_t cap_q, cap_t, cap_tr;
 } simd_ws;
 
-static void ws_reserve(simd_ws *w, int qmax, int tmax)
+static void ws_reserve(simd_ws *w, int qmax, int tmax, int lanes)
 {
     if ((size_t)qmax > w->cap_q) {
         free(w->q); free(w->H); free(w->E);
         w->cap_q = (size_t)qmax + 64;
-        w->q = (int16_t *)aligned_alloc(32, w->cap_q * LANES * 2);
-        w->H = (__m256i *)aligned_alloc(32, w->cap_q * 32);
-        w->E = (__m256i *)aligned_alloc(32, w->cap_q * 32);
+        w->q = (int16_t *)aligned_alloc(64, w->cap_q * lanes * 2);
+        w->H = (int16_t *)aligned_alloc(64, w->cap_q * lanes * 2);
+        w->E = (int16_t *)aligned_alloc(64, w->cap_q * lanes * 2);
     }
     if ((size_t)tmax > w->cap_t) {
         free(w->t);
         w->cap_t = (size_t)tmax + 256;
-        w->t = (int16_t *)aligned_alloc(32, w->cap_t * LANES * 2);
+        w->t = (int16_t *)aligned_alloc(64, w->cap_t * lanes * 2);
     }
-    const size_t need = (size_t)qmax * tmax * LANES;
+    const size_t need = (size_t)qmax * tmax * lanes;
     if (need > w->cap_tr) {
         free(w->tr);
         w->cap_tr = need + need / 4;
-        w->tr = (uint8_t *)aligned_alloc(32, (w->cap_tr + 31) & ~(size_t)31);
+        w->tr = (uint8_t *)aligned_alloc(64, (w->cap_tr + 63) & ~(size_t)63);
     }
 }
+
+typedef void (*simd_kernel)(simd_ws *w, int qmax, int tmax, const fo_params *p, int *score, int *end_q, int *end_r);
 
 __attribute__((target("avx2")))
 static void simd_sw16(simd_ws *w, int qmax, int tmax, const fo_params *p,
@@ -78,8 +73,10 @@ static void simd_sw16(simd_ws *w, int qmax, int tmax, const fo_params *p,
     const __m256i neg = _mm256_set1_epi16(-20000);
     const __m256i c1 = _mm256_set1_epi16(1), c2 = _mm256_set1_epi16(2), c3 = _mm256_set1_epi16(3);
     const __m256i c4 = _mm256_set1_epi16(4), c8 = _mm256_set1_epi16(8);
+    enum { LANES = 16 };
+    __m256i *const H = (__m256i *)w->H, *const E = (__m256i *)w->E;
     __m256i best = zero, bi = zero, bj = zero;
-    for (int i = 0; i < qmax; ++i) { w->H[i] = zero; w->E[i] = neg; }
+    for (int i = 0; i < qmax; ++i) { H[i] = zero; E[i] = neg; }
     for (int j = 0; j < tmax; ++j) {
         const __m256i tv = _mm256_load_si256((const __m256i *)(w->t + (size_t)j * LANES));
         const __m256i vj = _mm256_set1_epi16((short)j);
@@ -87,9 +84,9 @@ static void simd_sw16(simd_ws *w, int qmax, int tmax, const fo_params *p,
         uint8_t *trj = w->tr + (size_t)j * LANES;
         for (int i = 0; i < qmax; ++i) {
             const __m256i qv = _mm256_load_si256((const __m256i *)(w->q + (size_t)i * LANES));
-            const __m256i hleft = w->H[i];
+            const __m256i hleft = H[i];
             /* E[i][j] = max(H[i][j-1]-o, E[i][j-1]-e); open iff strictly greater */
-            const __m256i e_opn = _mm256_subs_epi16(hleft, vo), e_ext = _mm256_subs_epi16(w->E[i], ve);
+            const __m256i e_opn = _mm256_subs_epi16(hleft, vo), e_ext = _mm256_subs_epi16(E[i], ve);
             const __m256i eo = _mm256_cmpgt_epi16(e_opn, e_ext);
             const __m256i ev = _mm256_max_epi16(e_opn, e_ext);
             const __m256i f_opn = _mm256_subs_epi16(hup, vo), f_ext = _mm256_subs_epi16(f, ve);
@@ -114,12 +111,74 @@ static void simd_sw16(simd_ws *w, int qmax, int tmax, const fo_params *p,
             bi = _mm256_blendv_epi8(bi, _mm256_set1_epi16((short)i), gt);
             bj = _mm256_blendv_epi8(bj, vj, gt);
             hdiag = hleft; hup = h; f = fv;
-            w->E[i] = ev; w->H[i] = h;
+            E[i] = ev; H[i] = h;
         }
     }
     int16_t b[LANES], xi[LANES], xj[LANES];
     _mm256_storeu_si256((__m256i *)b, best); _mm256_storeu_si256((__m256i *)xi, bi); _mm256_storeu_si256((__m256i *)xj, bj);
     for (int l = 0; l < LANES; ++l) { score[l] = b[l]; end_q[l] = xi[l]; end_r[l] = xj[l]; }
+}
+
+/* the same recurrence on 32 lanes; comparisons land in mask registers and the trace byte is assembled in the byte domain */
+__attribute__((target("avx512f,avx512bw,avx512vl")))
+static void simd_sw32(simd_ws *w, int qmax, int tmax, const fo_params *p,
+                      int *score, int *end_q, int *end_r)
+{
+    enum { LANES = 32 };
+    const __m512i vo = _mm512_set1_epi16((short)p->gap_open), ve = _mm512_set1_epi16((short)p->gap_extend);
+    const __m512i vmatch = _mm512_set1_epi16((short)p->match), vmis = _mm512_set1_epi16((short)p->mismatch);
+    const __m512i zero = _mm512_setzero_si512();
+    const __m512i neg = _mm512_set1_epi16(-20000);
+    const __m256i b1 = _mm256_set1_epi8(1), b2 = _mm256_set1_epi8(2), b3 = _mm256_set1_epi8(3);
+    const __m256i b4 = _mm256_set1_epi8(4), b8 = _mm256_set1_epi8(8);
+    __m512i *const H = (__m512i *)w->H, *const E = (__m512i *)w->E;
+    __m512i best = zero, bi = zero, bj = zero;
+    for (int i = 0; i < qmax; ++i) { H[i] = zero; E[i] = neg; }
+    for (int j = 0; j < tmax; ++j) {
+        const __m512i tv = _mm512_load_si512((const void *)(w->t + (size_t)j * LANES));
+        const __m512i vj = _mm512_set1_epi16((short)j);
+        __m512i hdiag = zero, hup = zero, f = neg;
+        uint8_t *trj = w->tr + (size_t)j * LANES;
+        for (int i = 0; i < qmax; ++i) {
+            const __m512i qv = _mm512_load_si512((const void *)(w->q + (size_t)i * LANES));
+            const __m512i hleft = H[i];
+            const __m512i e_opn = _mm512_subs_epi16(hleft, vo), e_ext = _mm512_subs_epi16(E[i], ve);
+            const __mmask32 eo = _mm512_cmpgt_epi16_mask(e_opn, e_ext);
+            const __m512i ev = _mm512_max_epi16(e_opn, e_ext);
+            const __m512i f_opn = _mm512_subs_epi16(hup, vo), f_ext = _mm512_subs_epi16(f, ve);
+            const __mmask32 fo = _mm512_cmpgt_epi16_mask(f_opn, f_ext);
+            const __m512i fv = _mm512_max_epi16(f_opn, f_ext);
+            const __m512i s = _mm512_mask_blend_epi16(_mm512_cmpeq_epi16_mask(qv, tv), vmis, vmatch);
+            const __m512i hd = _mm512_max_epi16(_mm512_adds_epi16(hdiag, s), zero);
+            const __m512i h = _mm512_max_epi16(_mm512_max_epi16(hd, ev), fv);
+            /* source priority DIAG/ZERO > F > E */
+            const __mmask32 is_d = _mm512_cmpeq_epi16_mask(h, hd), is_f = _mm512_cmpeq_epi16_mask(h, fv);
+            const __mmask32 is_nz = _mm512_cmpneq_epi16_mask(h, zero);
+            __m256i tb = _mm256_mask_blend_epi8(is_f, b3, b2);
+            tb = _mm256_mask_mov_epi8(tb, is_d, _mm256_maskz_mov_epi8(is_nz, b1));
+            tb = _mm256_or_si256(tb, _mm256_or_si256(_mm256_maskz_mov_epi8(eo, b4), _mm256_maskz_mov_epi8(fo, b8)));
+            _mm256_storeu_si256((__m256i *)(trj + (size_t)i * tmax * LANES), tb);
+            /* end cell: first column, then first row (strictly greater only) */
+            const __mmask32 gt = _mm512_cmpgt_epi16_mask(h, best);
+            best = _mm512_max_epi16(best, h);
+            bi = _mm512_mask_mov_epi16(bi, gt, _mm512_set1_epi16((short)i));
+            bj = _mm512_mask_mov_epi16(bj, gt, vj);
+            hdiag = hleft; hup = h; f = fv;
+            E[i] = ev; H[i] = h;
+        }
+    }
+    int16_t b[LANES], xi[LANES], xj[LANES];
+    _mm512_storeu_si512((void *)b, best); _mm512_storeu_si512((void *)xi, bi); _mm512_storeu_si512((void *)xj, bj);
+    for (int l = 0; l < LANES; ++l) { score[l] = b[l]; end_q[l] = xi[l]; end_r[l] = xj[l]; }
+}
+
+/* lanes of the widest kernel this host runs (16 or 32; 0 = no AVX2) */
+int fo_simd_lanes(void)
+{
+    if (!__builtin_cpu_supports("avx2")) return 0;
+    const char *force = getenv("FADE_ORACLE_SIMD");
+    if (force && strcmp(force, "avx2") == 0) return 16;
+    return (__builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl")) ? 32 : 16;
 }
 
 static int accept_side(int left, int score, int n_ops, const uint32_t *ops, int n_have, uint32_t clip_len)
@@ -143,7 +202,8 @@ int fo_align_batch_simd(int64_t n, const uint8_t *seq4, const int64_t *seq_off, 
                         const fo_params *p, fo_read_result *res, uint32_t *ops_out, int ops_cap,
                         int n_threads)
 {
-    if (!__builtin_cpu_supports("avx2"))
+    int LANES = fo_simd_lanes();
+    if (LANES == 0)
         return fo_align_batch(n, seq4, seq_off, l_qseq, tid, pos, aligned_len, clip_left, clip_right, n_contigs,
                               contigs, contig_len, p, res, ops_out, ops_cap, n_threads);
 #ifdef _OPENMP
@@ -151,7 +211,7 @@ int fo_align_batch_simd(int64_t n, const uint8_t *seq4, const int64_t *seq_off, 
 #endif
     /* which reads need SW (analysis.d:34) and their windows (analysis.d:45-59) */
     int64_t *list = (int64_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int64_t));
-    int64_t m = 0;
+    int64_t m = 0, max_cells = 0;
     for (int64_t k = 0; k < n; ++k) {
         fo_read_result *r = &res[k];
         memset(r, 0, sizeof(*r));
@@ -168,7 +228,12 @@ int fo_align_batch_simd(int64_t n, const uint8_t *seq4, const int64_t *seq_off, 
         r->tlen = (int)(end - start);
         r->aligned = 1;
         list[m++] = k;
+        if ((int64_t)l_qseq[k] * r->tlen > max_cells) max_cells = (int64_t)l_qseq[k] * r->tlen;
     }
+    /* one trace byte per cell and lane: past 8 MB per thread the 32-lane table falls out of the cache levels the
+     * 16-lane one still fits (2x250 reads with W=1000: 18 MB against 9 MB) and the narrower kernel is the faster one */
+    if (LANES == 32 && max_cells * 32 > (8 << 20)) LANES = 16;
+    const simd_kernel kernel = LANES == 32 ? simd_sw32 : simd_sw16;
     const int64_t nb = (m + LANES - 1) / LANES;
     int err = 0;
 #pragma omp parallel
@@ -186,8 +251,8 @@ int fo_align_batch_simd(int64_t n, const uint8_t *seq4, const int64_t *seq_off, 
                 if (l_qseq[k] > qmax) qmax = l_qseq[k];
                 if (res[k].tlen > tmax) tmax = res[k].tlen;
             }
-            ws_reserve(&w, qmax, tmax);
-            int wild[LANES];
+            ws_reserve(&w, qmax, tmax, LANES);
+            int wild[MAX_LANES];
             for (int l = 0; l < LANES; ++l) wild[l] = 0;
             /* codes: query pad 100, target pad 200 -> never equal */
             for (int i = 0; i < qmax; ++i)
@@ -213,8 +278,8 @@ int fo_align_batch_simd(int64_t n, const uint8_t *seq4, const int64_t *seq_off, 
                     w.t[(size_t)j * LANES + l] = (int16_t)c;
                 }
             }
-            int score[LANES], eq[LANES], er[LANES];
-            simd_sw16(&w, qmax, tmax, p, score, eq, er);
+            int score[MAX_LANES], eq[MAX_LANES], er[MAX_LANES];
+            kernel(&w, qmax, tmax, p, score, eq, er);
             for (int l = 0; l < cnt; ++l) {
                 const int64_t k = list[bx * LANES + l];
                 fo_read_result *r = &res[k];

@@ -96,6 +96,8 @@ def lib():
         L.fo_align_batch.restype = C.c_int
         L.fo_align_batch_simd.argtypes = L.fo_align_batch.argtypes
         L.fo_align_batch_simd.restype = C.c_int
+        L.fo_simd_lanes.argtypes = []
+        L.fo_simd_lanes.restype = C.c_int
         L.ps_sw_trace.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(Params), C.c_int,
                                   C.POINTER(SwResult), C.POINTER(C.c_uint32), C.c_int]
         L.ps_sw_trace.restype = C.c_int
@@ -104,6 +106,11 @@ def lib():
         L.ps_fuzz.restype = C.c_int
         _lib = L
     return _lib
+
+
+def simd_lanes() -> int:
+    """int16 lanes of the SIMD port on this host: 32 (AVX-512BW), 16 (AVX2; also when FADE_ORACLE_SIMD=avx2) or 0."""
+    return int(lib().fo_simd_lanes())
 
 
 def default_params(**kw) -> Params:

@@ -1,5 +1,5 @@
 """BASELINE.json configs at their FULL sizes, bit-exact for every read against the CPU oracle
-(oracle/fade_oracle_simd.c, the AVX2 port validated against the scalar oracle):
+(oracle/fade_oracle_simd.c, the AVX2 / AVX-512BW port validated against the scalar oracle):
 
   C2  configs[1]  10 M 2x150 reads vs a 100 Mbp chromosome, defaults
   C3  configs[2]  3.1 Gbp / 24 contigs resident in HBM (global offsets > 2^31); 2 M of the 100 M reads

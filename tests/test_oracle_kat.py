@@ -143,10 +143,18 @@ def test_golden_fixture_c1_head():
         assert got == e, (int(k), got, e)
 
 
-def test_simd_cpu_baseline_equals_scalar_oracle():
-    """oracle/fade_oracle_simd.c (the AVX2 CPU baseline timed by bench.py) must reproduce the scalar
-    oracle bit for bit: simulated reads, ragged lengths / contig ends, wildcard letters, other flags."""
+@pytest.mark.parametrize("width", ["widest", "avx2"])
+def test_simd_cpu_baseline_equals_scalar_oracle(width, monkeypatch):
+    """oracle/fade_oracle_simd.c (the AVX2 / AVX-512BW CPU baseline timed by bench.py) must reproduce the scalar
+    oracle bit for bit at both lane counts: simulated reads, ragged lengths / contig ends, wildcard letters, other flags."""
     import random as _random
+
+    if width == "avx2":
+        monkeypatch.setenv("FADE_ORACLE_SIMD", "avx2")
+        assert orc.simd_lanes() in (0, 16)
+    else:
+        monkeypatch.delenv("FADE_ORACLE_SIMD", raising=False)
+        assert orc.simd_lanes() in (0, 16, 32)
 
     import readsets
     from fade_b200 import sim
