@@ -807,7 +807,11 @@ int cmd_sort(int argc, char **argv)
         const size_t left = st.size() - p2;
         const uint32_t bs = left >= 4 ? bamfast::get_u32(&st[p2]) : 0;
         const uint32_t ln = left >= 36 ? st[p2 + 4 + 8] : 0;
-        if (left < 36 || bs < 32 || (size_t)bs + 4 > left || ln < 1 || 32 + ln > bs || names.size() > 0xffffff00u) {
+        // the fixed part and the sizes it declares must fit the record (the check samio::bam_to_sam starts with)
+        const uint64_t n_cig = left >= 36 ? bamfast::get_u16(&st[p2 + 4 + 12]) : 0;
+        const int64_t l_seq = left >= 36 ? bamfast::get_i32(&st[p2 + 4 + 16]) : 0;
+        if (left < 36 || bs < 32 || (size_t)bs + 4 > left || ln < 1 || l_seq < 0 ||
+            32 + ln + 4 * n_cig + (uint64_t)(l_seq + 1) / 2 + (uint64_t)l_seq > bs || names.size() > 0xffffff00u) {
             fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str());
             return 1;
         }

@@ -219,3 +219,11 @@ def test_sort_refuses_damaged_input(tmp_path):
     raw = bamcodec.encode(head + recs)
     cut = subprocess.run([BIN, "sort", "-n", "-"], input=raw[: len(raw) - 60], capture_output=True)
     assert cut.returncode == 1 and b"r0" not in cut.stdout
+    # intact BGZF, but one record declares more bases than it holds
+    import struct
+    payload = bytearray(bamcodec.bgzf_decode(raw))
+    at = payload.index(b"r7\0") - 36                       # block_size of record r7
+    struct.pack_into("<i", payload, at + 4 + 16, 5000)      # l_seq
+    for args in (["sort", "-n"], ["sort", "-nb"]):
+        p = subprocess.run([BIN, *args, "-"], input=bamcodec.bgzf_blocks(bytes(payload)) + raw[-28:], capture_output=True)
+        assert p.returncode == 1 and b"malformed" in p.stderr
