@@ -473,6 +473,46 @@ struct SamRec {
     }
 };
 
+// One record line split only as far as `out` needs to decide what happens to it: the name and where the optional
+// fields start.  A record that passes through unchanged is written from `line` as it came in.
+struct LineRec {
+    std::string line;
+    size_t name_len = 0, tags_at = 0;   // tags_at = offset of the first optional field, line.size() when there is none
+    bool index()                        // false: fewer than 11 fields
+    {
+        const char *p = line.data(), *const e = p + line.size();
+        const char *t = p;
+        for (int k = 0; k < 11; ++k) {
+            const char *q = (const char *)memchr(t, '\t', (size_t)(e - t));
+            if (k == 0) name_len = (size_t)((q ? q : e) - p);
+            if (!q) { if (k < 10) return false; t = e; break; }
+            t = q + 1;
+        }
+        tags_at = (size_t)(t - p);
+        return true;
+    }
+    bool same_name(const LineRec &o) const { return name_len == o.name_len && memcmp(line.data(), o.line.data(), name_len) == 0; }
+    // value text of the first optional field whose two-letter name is k (what SamRec::has / SamRec::tag find)
+    bool tag(const char *k, std::string &v) const
+    {
+        for (size_t a = tags_at; a < line.size();) {
+            size_t b = line.find('\t', a);
+            if (b == std::string::npos) b = line.size();
+            if (b - a >= 2 && line[a] == k[0] && line[a + 1] == k[1]) { v = b - a > 5 ? line.substr(a + 5, b - a - 5) : std::string(); return true; }
+            a = b + 1;
+        }
+        return false;
+    }
+    SamRec split() const
+    {
+        SamRec r;
+        auto f = split_tab(line);
+        r.f.assign(f.begin(), f.begin() + 11);
+        r.tags.assign(f.begin() + 11, f.end());
+        return r;
+    }
+};
+
 struct Sam {   // header of the stream; the records are pulled one at a time (inputs need not fit in memory)
     std::vector<std::string> header, contigs;
     std::string last_pg;
@@ -510,6 +550,16 @@ struct Sam {   // header of the stream; the records are pulled one at a time (in
         r.f.assign(f.begin(), f.begin() + 11);
         r.tags.assign(f.begin() + 11, f.end());
         return 1;
+    }
+    int next(LineRec &r)   // the same, without splitting the line
+    {
+        for (;;) {
+            if (have_pending) { r.line.swap(pending); have_pending = false; }
+            else if (!in.getline(r.line)) return in.failed() ? -1 : 0;
+            if (!r.line.empty() && r.line.back() == '\r') r.line.pop_back();
+            if (!r.line.empty()) break;
+        }
+        return r.index() ? 1 : -1;
     }
 };
 
@@ -628,7 +678,6 @@ int natural_compare(const char *a, size_t na, const char *b, size_t nb)
     const size_t ra = (size_t)(ae - a), rb = (size_t)(be - b);
     return ra == rb ? 0 : (ra < rb ? -1 : 1);
 }
-int natural_compare(const std::string &a, const std::string &b) { return natural_compare(a.data(), a.size(), b.data(), b.size()); }
 
 struct OutStats {   // source/stats.d:16-72
     long read_count = 0, clipped = 0, sup = 0, art_sup = 0, art = 0, aln_l = 0, aln_r = 0;
@@ -652,6 +701,13 @@ int rs_of(const SamRec &r, bool &have)
     return have ? (atoi(r.tag("rs").c_str()) & 0xff) : 0;
 }
 
+int rs_of(const LineRec &r, bool &have)
+{
+    std::string v;
+    have = r.tag("rs", v);
+    return have ? (atoi(v.c_str()) & 0xff) : 0;
+}
+
 int cmd_out(int argc, char **argv, const std::string &cl)
 {
     const Options opt = parse_options(argc, argv, 2, { { 'c', "clip", false }, { 't', "threads", true }, { 'h', "help", false },
@@ -668,46 +724,49 @@ int cmd_out(int argc, char **argv, const std::string &cl)
     write_header(sam, "fade-extract", cl);   // sic: filter.d:173 uses the ID of extract
     OutStats st;
     bool put_failed = false;
-    auto put = [&put_failed](const SamRec &r) { if (!out_line(r.line())) put_failed = true; };
+    auto put = [&put_failed](const std::string &l) { if (!out_line(l)) put_failed = true; };
     int rc = 0;
-    SamRec r;
+    LineRec r;
     if (clip) {   // filter.d:182-208
         while ((rc = sam.next(r)) == 1) {
             ++st.read_count;
             bool have;
             const int rs = rs_of(r, have);
-            if (!have) { put(r); continue; }
+            if (!have) { put(r.line); continue; }
             st.parse(rs);
-            if (!(rs & 6)) put(r); else put(clip_read(r, rs, sam));
+            if (!(rs & 6)) put(r.line); else put(clip_read(r.split(), rs, sam).line());
         }
     } else {      // filter.d:209-266: the first ten records decide whether the input is taken as name-sorted
-        std::vector<SamRec> head;
+        std::vector<LineRec> head;
         while (head.size() < 10 && (rc = sam.next(r)) == 1) head.push_back(r);
         bool sorted = true;
         for (size_t k = 0; k + 1 < head.size(); ++k)
-            if (natural_compare(head[k + 1].f[0], head[k].f[0]) < 0) sorted = false;
+            if (natural_compare(head[k + 1].line.data(), head[k + 1].name_len, head[k].line.data(), head[k].name_len) < 0) sorted = false;
         size_t hp = 0;
-        auto next = [&](SamRec &o) -> int {   // the buffered head first, then the rest of the stream
+        auto next = [&](LineRec &o) -> int {   // the buffered head first, then the rest of the stream
             if (hp < head.size()) { o = head[hp++]; return 1; }
             if (rc != 1) return rc;
             return rc = sam.next(o);
         };
         if (sorted) {
             fprintf(stderr, "[W::fade-out] Output looks name-sorted, ejecting all reads with same readname if any have an artifact\n");
-            std::vector<SamRec> group;
+            std::vector<LineRec> group;
+            size_t ng = 0;        // records of the current group (slots of `group` are reused)
             bool art = false;
             auto flush_group = [&]() {
-                if (!art) for (auto &g : group) put(g);
-                group.clear();
+                if (!art) for (size_t g = 0; g < ng; ++g) put(group[g].line);
+                ng = 0;
                 art = false;
             };
             while (next(r) == 1) {
-                if (!group.empty() && group.back().f[0] != r.f[0]) flush_group();
+                if (ng && !group[ng - 1].same_name(r)) flush_group();
                 ++st.read_count;
                 bool have;
                 const int rs = rs_of(r, have);
                 if (have) { st.parse(rs); if (rs & 6) art = true; }
-                group.push_back(r);
+                if (ng == group.size()) group.emplace_back();
+                std::swap(group[ng], r);
+                ++ng;
             }
             flush_group();
         } else {
@@ -718,7 +777,7 @@ int cmd_out(int argc, char **argv, const std::string &cl)
                 const int rs = rs_of(r, have);
                 if (!have) continue;
                 st.parse(rs);
-                if (!(rs & 6)) put(r);
+                if (!(rs & 6)) put(r.line);
             }
         }
     }
