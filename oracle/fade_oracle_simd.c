@@ -35,7 +35,7 @@ typedef struct {
     int16_t *q;      /* [qmax][lanes] query codes (pad = 100+lane-independent mismatch code) */
     int16_t *t;      /* [tmax][lanes] target codes */
     int16_t *H, *E;  /* [qmax][lanes] */
-    uint8_t *tr;     /* [qmax*tmax][lanes] */
+    uint8_t *tr;     /* [tmax][qmax][lanes] */
     size_t cap_q, cap_t, cap_tr;
 } simd_ws;
 
@@ -81,7 +81,7 @@ static void simd_sw16(simd_ws *w, int qmax, int tmax, const fo_params *p,
         const __m256i tv = _mm256_load_si256((const __m256i *)(w->t + (size_t)j * LANES));
         const __m256i vj = _mm256_set1_epi16((short)j);
         __m256i hdiag = zero, hup = zero, f = neg;
-        uint8_t *trj = w->tr + (size_t)j * LANES;
+        uint8_t *trj = w->tr + (size_t)j * qmax * LANES;   /* column after column: the stores are sequential */
         for (int i = 0; i < qmax; ++i) {
             const __m256i qv = _mm256_load_si256((const __m256i *)(w->q + (size_t)i * LANES));
             const __m256i hleft = H[i];
@@ -104,7 +104,7 @@ static void simd_sw16(simd_ws *w, int qmax, int tmax, const fo_params *p,
             /* 16 x int16 -> 16 bytes */
             const __m256i pk = _mm256_packus_epi16(tb, tb);
             const __m128i lo = _mm256_castsi256_si128(pk), hi = _mm256_extracti128_si256(pk, 1);
-            _mm_storeu_si128((__m128i *)(trj + (size_t)i * tmax * LANES), _mm_unpacklo_epi64(lo, hi));
+            _mm_storeu_si128((__m128i *)(trj + (size_t)i * LANES), _mm_unpacklo_epi64(lo, hi));
             /* end cell: first column, then first row (strictly greater only) */
             const __m256i gt = _mm256_cmpgt_epi16(h, best);
             best = _mm256_max_epi16(best, h);
@@ -138,7 +138,7 @@ static void simd_sw32(simd_ws *w, int qmax, int tmax, const fo_params *p,
         const __m512i tv = _mm512_load_si512((const void *)(w->t + (size_t)j * LANES));
         const __m512i vj = _mm512_set1_epi16((short)j);
         __m512i hdiag = zero, hup = zero, f = neg;
-        uint8_t *trj = w->tr + (size_t)j * LANES;
+        uint8_t *trj = w->tr + (size_t)j * qmax * LANES;   /* column after column: the stores are sequential */
         for (int i = 0; i < qmax; ++i) {
             const __m512i qv = _mm512_load_si512((const void *)(w->q + (size_t)i * LANES));
             const __m512i hleft = H[i];
@@ -157,7 +157,7 @@ static void simd_sw32(simd_ws *w, int qmax, int tmax, const fo_params *p,
             __m256i tb = _mm256_mask_blend_epi8(is_f, b3, b2);
             tb = _mm256_mask_mov_epi8(tb, is_d, _mm256_maskz_mov_epi8(is_nz, b1));
             tb = _mm256_or_si256(tb, _mm256_or_si256(_mm256_maskz_mov_epi8(eo, b4), _mm256_maskz_mov_epi8(fo, b8)));
-            _mm256_storeu_si256((__m256i *)(trj + (size_t)i * tmax * LANES), tb);
+            _mm256_storeu_si256((__m256i *)(trj + (size_t)i * LANES), tb);
             /* end cell: first column, then first row (strictly greater only) */
             const __mmask32 gt = _mm512_cmpgt_epi16_mask(h, best);
             best = _mm512_max_epi16(best, h);
@@ -300,7 +300,7 @@ int fo_align_batch_simd(int64_t n, const uint8_t *seq4, const int64_t *seq_off, 
                 if ((size_t)(L + T + 4) > rev_cap) { free(rev); rev_cap = (size_t)(L + T + 64); rev = (uint32_t *)malloc(rev_cap * 4); }
                 int i = eq[l], j = er[l], state = 0, nrev = 0, span = 0;
                 while (i >= 0 && j >= 0) {
-                    const uint8_t tb = w.tr[((size_t)i * tmax + j) * LANES + l];
+                    const uint8_t tb = w.tr[((size_t)j * qmax + i) * LANES + l];
                     uint32_t op;
                     if (state == 0) {
                         const int src = tb & 3;
