@@ -66,3 +66,12 @@ def test_the_fuzz_has_teeth(switch, name):
     scoring = dict(gap_open=4, gap_extend=2) if switch in (orc.FO_SW_E_BEFORE_F, orc.FO_SW_GAP_TIE_OPEN) else {}
     r = orc.fuzz_striped(31, 60_000, 16, params=orc.default_params(switches=switch, **scoring))
     assert r["n_diverged"] > 0 and r["explained_by"].startswith(name), r
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_read_sized_pairs_agree(lanes):
+    """the shapes fade actually aligns (2x150 / 2x250 reads against windows of up to a thousand bases): segLen
+    10..33 instead of the 1..9 of the short pairs above, scores well into the hundreds, long runs of one state"""
+    r = orc.fuzz_striped(41 + lanes, 12_000, lanes, qmax=260, tmax=1000)
+    assert r["n_diverged"] == 0, _report(r, lanes)
+    assert r["n_gapped"] > 1_500 and r["n_multi_max"] > 1_500, r
