@@ -74,16 +74,19 @@ static void simd_sw16(simd_ws *w, int qmax, int tmax, const fo_params *p,
     const __m256i c1 = _mm256_set1_epi16(1), c2 = _mm256_set1_epi16(2), c3 = _mm256_set1_epi16(3);
     const __m256i c4 = _mm256_set1_epi16(4), c8 = _mm256_set1_epi16(8);
     enum { LANES = 16 };
+    /* locals: the byte stores into the trace table may alias *w as far as the compiler knows */
     __m256i *const H = (__m256i *)w->H, *const E = (__m256i *)w->E;
+    const int16_t *const wq = w->q, *const wt = w->t;
+    uint8_t *const wtr = w->tr;
     __m256i best = zero, bi = zero, bj = zero;
     for (int i = 0; i < qmax; ++i) { H[i] = zero; E[i] = neg; }
     for (int j = 0; j < tmax; ++j) {
-        const __m256i tv = _mm256_load_si256((const __m256i *)(w->t + (size_t)j * LANES));
+        const __m256i tv = _mm256_load_si256((const __m256i *)(wt + (size_t)j * LANES));
         const __m256i vj = _mm256_set1_epi16((short)j);
         __m256i hdiag = zero, hup = zero, f = neg;
-        uint8_t *trj = w->tr + (size_t)j * qmax * LANES;   /* column after column: the stores are sequential */
+        uint8_t *trj = wtr + (size_t)j * qmax * LANES;   /* column after column: the stores are sequential */
         for (int i = 0; i < qmax; ++i) {
-            const __m256i qv = _mm256_load_si256((const __m256i *)(w->q + (size_t)i * LANES));
+            const __m256i qv = _mm256_load_si256((const __m256i *)(wq + (size_t)i * LANES));
             const __m256i hleft = H[i];
             /* E[i][j] = max(H[i][j-1]-o, E[i][j-1]-e); open iff strictly greater */
             const __m256i e_opn = _mm256_subs_epi16(hleft, vo), e_ext = _mm256_subs_epi16(E[i], ve);
@@ -132,15 +135,17 @@ static void simd_sw32(simd_ws *w, int qmax, int tmax, const fo_params *p,
     const __m256i b1 = _mm256_set1_epi8(1), b2 = _mm256_set1_epi8(2), b3 = _mm256_set1_epi8(3);
     const __m256i b4 = _mm256_set1_epi8(4), b8 = _mm256_set1_epi8(8);
     __m512i *const H = (__m512i *)w->H, *const E = (__m512i *)w->E;
+    const int16_t *const wq = w->q, *const wt = w->t;
+    uint8_t *const wtr = w->tr;
     __m512i best = zero, bi = zero, bj = zero;
     for (int i = 0; i < qmax; ++i) { H[i] = zero; E[i] = neg; }
     for (int j = 0; j < tmax; ++j) {
-        const __m512i tv = _mm512_load_si512((const void *)(w->t + (size_t)j * LANES));
+        const __m512i tv = _mm512_load_si512((const void *)(wt + (size_t)j * LANES));
         const __m512i vj = _mm512_set1_epi16((short)j);
         __m512i hdiag = zero, hup = zero, f = neg;
-        uint8_t *trj = w->tr + (size_t)j * qmax * LANES;   /* column after column: the stores are sequential */
+        uint8_t *trj = wtr + (size_t)j * qmax * LANES;   /* column after column: the stores are sequential */
         for (int i = 0; i < qmax; ++i) {
-            const __m512i qv = _mm512_load_si512((const void *)(w->q + (size_t)i * LANES));
+            const __m512i qv = _mm512_load_si512((const void *)(wq + (size_t)i * LANES));
             const __m512i hleft = H[i];
             const __m512i e_opn = _mm512_subs_epi16(hleft, vo), e_ext = _mm512_subs_epi16(E[i], ve);
             const __mmask32 eo = _mm512_cmpgt_epi16_mask(e_opn, e_ext);
