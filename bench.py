@@ -212,8 +212,7 @@ def cpu_kind() -> str:
     """What the SIMD arm is on this host: the widest of AVX-512BW (32 int16 lanes) and AVX2 (16) the CPU runs."""
     from oracle import oracle as orc
     lanes = orc.simd_lanes()
-    isa = {32: "AVX-512BW 32-lane (AVX2 16-lane where a 32-lane trace table would pass 8 MB per thread)",
-           16: "AVX2 16-lane"}.get(lanes, "scalar (no AVX2 on this host)")
+    isa = {32: "AVX-512BW 32-lane", 16: "AVX2 16-lane"}.get(lanes, "scalar (no AVX2 on this host)")
     return (f"{isa} inter-sequence port of the path (oracle/fade_oracle_simd.c: SW fill with trace table, "
             "traceback, predicates; in-memory reference), validated against the scalar oracle")
 

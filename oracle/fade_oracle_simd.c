@@ -207,7 +207,7 @@ int fo_align_batch_simd(int64_t n, const uint8_t *seq4, const int64_t *seq_off, 
                         const fo_params *p, fo_read_result *res, uint32_t *ops_out, int ops_cap,
                         int n_threads)
 {
-    int LANES = fo_simd_lanes();
+    const int LANES = fo_simd_lanes();
     if (LANES == 0)
         return fo_align_batch(n, seq4, seq_off, l_qseq, tid, pos, aligned_len, clip_left, clip_right, n_contigs,
                               contigs, contig_len, p, res, ops_out, ops_cap, n_threads);
@@ -216,7 +216,7 @@ int fo_align_batch_simd(int64_t n, const uint8_t *seq4, const int64_t *seq_off, 
 #endif
     /* which reads need SW (analysis.d:34) and their windows (analysis.d:45-59) */
     int64_t *list = (int64_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int64_t));
-    int64_t m = 0, max_cells = 0;
+    int64_t m = 0;
     for (int64_t k = 0; k < n; ++k) {
         fo_read_result *r = &res[k];
         memset(r, 0, sizeof(*r));
@@ -233,11 +233,7 @@ int fo_align_batch_simd(int64_t n, const uint8_t *seq4, const int64_t *seq_off, 
         r->tlen = (int)(end - start);
         r->aligned = 1;
         list[m++] = k;
-        if ((int64_t)l_qseq[k] * r->tlen > max_cells) max_cells = (int64_t)l_qseq[k] * r->tlen;
     }
-    /* one trace byte per cell and lane: past 8 MB per thread the 32-lane table falls out of the cache levels the
-     * 16-lane one still fits (2x250 reads with W=1000: 18 MB against 9 MB) and the narrower kernel is the faster one */
-    if (LANES == 32 && max_cells * 32 > (8 << 20)) LANES = 16;
     const simd_kernel kernel = LANES == 32 ? simd_sw32 : simd_sw16;
     const int64_t nb = (m + LANES - 1) / LANES;
     int err = 0;
