@@ -72,6 +72,6 @@ def test_the_fuzz_has_teeth(switch, name):
 def test_read_sized_pairs_agree(lanes):
     """the shapes fade actually aligns (2x150 / 2x250 reads against windows of up to a thousand bases): segLen
     10..33 instead of the 1..9 of the short pairs above, scores well into the hundreds, long runs of one state"""
-    r = orc.fuzz_striped(41 + lanes, 12_000, lanes, qmax=260, tmax=1000)
+    r = orc.fuzz_striped(41 + lanes, 8_000, lanes, qmax=260, tmax=1000)
     assert r["n_diverged"] == 0, _report(r, lanes)
-    assert r["n_gapped"] > 1_500 and r["n_multi_max"] > 1_500, r
+    assert r["n_gapped"] > 1_000 and r["n_multi_max"] > 1_000, r
