@@ -266,7 +266,11 @@ struct Job {
 // Records of a SAM or BAM input as one byte stream of [block_size][record] entries, plus its header
 struct RecordInput {
     RecordInput(FILE *f, const std::string &pre, bool bam, int threads)
-        : is_bam(bam), rd(f, bam ? pre : std::string(), threads), txt(f, bam ? std::string() : pre, threads) {}
+        : is_bam(bam), rd(f, bam ? pre : std::string(), threads), txt(f, bam ? std::string() : pre, threads)
+    {
+        if (const char *e = getenv("FADE_IO_BLOCKS")) blocks = std::max(1, std::min(4096, atoi(e)));   // tests: small pieces
+    }
+    int blocks = 512;            // BGZF blocks inflated per refill
     bool is_bam;
     BulkReader rd;
     SamTextSource txt;
@@ -277,7 +281,7 @@ struct RecordInput {
     bool need(size_t bytes)   // make stream[spos, spos + bytes) available
     {
         while (stream.size() - spos < bytes)
-            if (!(is_bam ? rd.more(stream, 512) : txt.more(stream, hdr, 1 << 16))) return false;
+            if (!(is_bam ? rd.more(stream, blocks) : txt.more(stream, hdr, 1 << 16))) return false;
         return true;
     }
     bool bad() const { return is_bam ? rd.bad() : txt.bad(); }

@@ -708,6 +708,180 @@ int rs_of(const LineRec &r, bool &have)
     return have ? (atoi(v.c_str()) & 0xff) : 0;
 }
 
+// `out` on BAM input: the records stay binary.  A record that passes through is copied as the bytes it came in as (or
+// converted to text for SAM output), only the records `out -c` clips go through the text form (clip_read); the
+// decisions -- rs of every record, the first ten names, whole read groups when the input looks name-sorted -- are those
+// of the text path below (filter.d:167-269), on which SAM input still runs.
+int out_bam_input(FILE *f, const std::string &path, bool clip, int con, int threads, const std::string &cl)
+{
+    using bamfast::get_u32;
+    auto damaged = [&] { fprintf(stderr, "fade-b200: malformed record or damaged input in %s\n", path.c_str()); return 1; };
+    bamfast::RecordInput in(f, std::string(), true, threads);
+    if (!in.read_header()) return 1;
+    Sam sam;                          // what clip_read and the @PG line need of it
+    sam.contigs = in.hdr.names;
+    for (const auto &h : in.hdr.lines)
+        if (h.compare(0, 3, "@PG") == 0) for (const auto &x : split_tab(h)) if (x.rfind("ID:", 0) == 0) sam.last_pg = x.substr(3);
+    {
+        std::string pg = std::string("@PG\tID:fade-extract\tPN:fade\tVN:") + kVersion;   // sic: filter.d:173 uses the ID of extract
+        if (!sam.last_pg.empty()) pg += "\tPP:" + sam.last_pg;
+        in.hdr.add_line(pg + "\tCL:" + cl);
+    }
+    bamfast::write_header(in.hdr, con, threads);
+    OutStats st;
+    const std::vector<uint8_t> &sb = in.stream;
+    auto name_of = [&](size_t off, size_t &len) { const char *nm = reinterpret_cast<const char *>(&sb[off + 36]); len = strnlen(nm, sb[off + 12]); return nm; };
+    auto same_name = [&](size_t a, size_t b) { size_t la, lb; const char *na = name_of(a, la), *nb = name_of(b, lb); return la == lb && memcmp(na, nb, la) == 0; };
+    bool eof = false, decided = false, sorted = true, unencodable = false;
+    std::vector<size_t> offs;
+    std::vector<uint8_t> have, keep;
+    std::vector<int> rsv;
+    std::vector<std::string> part;
+    std::string all;
+    for (;;) {
+        if (!eof) {
+            const size_t got = in.stream.size() - in.spos;
+            if (!in.need(got + 1)) { eof = true; if (in.bad()) return damaged(); }
+        }
+        // whole records available
+        offs.clear();
+        size_t end = in.spos;
+        while (end + 4 <= sb.size()) {
+            const uint32_t bs = get_u32(&sb[end]);
+            if (bs < 32) return damaged();
+            if (end + 4 + (size_t)bs > sb.size()) break;
+            const uint64_t ln = sb[end + 12], n_cig = bamfast::get_u16(&sb[end + 16]);
+            const int64_t l_seq = bamfast::get_i32(&sb[end + 20]);
+            if (ln < 1 || l_seq < 0 || 32 + ln + 4 * n_cig + (uint64_t)(l_seq + 1) / 2 + (uint64_t)l_seq > bs) return damaged();
+            offs.push_back(end);
+            end += 4 + (size_t)bs;
+        }
+        if (eof && end != sb.size()) return damaged();
+        if (!decided) {   // filter.d:209-266: the first ten records decide whether the input is taken as name-sorted
+            if (offs.size() < 10 && !eof) continue;
+            for (size_t k = 0; k + 1 < offs.size() && k + 1 < 10; ++k) {
+                size_t la, lb;
+                const char *a = name_of(offs[k], la), *b = name_of(offs[k + 1], lb);
+                if (natural_compare(b, lb, a, la) < 0) sorted = false;
+            }
+            decided = true;
+            if (!clip)
+                fprintf(stderr, sorted ? "[W::fade-out] Output looks name-sorted, ejecting all reads with same readname if any have an artifact\n"
+                                       : "[W::fade-out] Output doesn't look name-sorted, ejecting by only reads with an artifact\n");
+        }
+        size_t n = offs.size();
+        if (!clip && sorted && !eof) {   // the last read group may continue in the part of the file not read yet
+            const size_t tail = offs.back();
+            while (n > 0 && same_name(offs[n - 1], tail)) --n;
+            if (n == 0) continue;
+        }
+        // rs of every record (SamRec::has / tag: the first optional field named rs, read as a number)
+        have.assign(n, 0); keep.assign(n, 0); rsv.assign(n, 0);
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad) num_threads(threads)
+        for (long k = 0; k < (long)n; ++k) {
+            const uint8_t *p = &sb[offs[(size_t)k] + 4], *const e = p + get_u32(&sb[offs[(size_t)k]]);
+            const uint8_t *a = p + 32 + p[8] + 4ull * bamfast::get_u16(p + 12) + (size_t)(bamfast::get_i32(p + 16) + 1) / 2 + (size_t)bamfast::get_i32(p + 16);
+            while (a < e) {
+                const size_t sz = bamfast::aux_field_size(a, e);
+                if (!sz) { bad = 1; break; }
+                if (a[0] == 'r' && a[1] == 's') {
+                    have[(size_t)k] = 1;
+                    long long v = 0;
+                    switch (a[2]) {
+                    case 'c': v = (int8_t)a[3]; break;
+                    case 'C': v = a[3]; break;
+                    case 's': v = (int16_t)bamfast::get_u16(a + 3); break;
+                    case 'S': v = bamfast::get_u16(a + 3); break;
+                    case 'i': v = bamfast::get_i32(a + 3); break;
+                    case 'I': v = get_u32(a + 3); break;
+                    default: {   // any other type: through the text form, like the text path
+                        LineRec lr;
+                        if (!samio::bam_to_sam(p, (size_t)(e - p), in.hdr, lr.line) || !lr.index()) { bad = 1; break; }
+                        std::string t;
+                        lr.tag("rs", t);
+                        v = atoi(t.c_str());
+                    }
+                    }
+                    rsv[(size_t)k] = (int)(v & 0xff);
+                    break;
+                }
+                a += sz;
+            }
+        }
+        if (bad) return damaged();
+        // what happens to each record: 0 dropped, 1 as it is, 2 clipped
+        if (clip) {           // filter.d:182-208
+            for (size_t k = 0; k < n; ++k) {
+                ++st.read_count;
+                if (have[k]) st.parse(rsv[k]);
+                keep[k] = (have[k] && (rsv[k] & 6)) ? 2 : 1;
+            }
+        } else if (sorted) {  // whole read groups
+            for (size_t a = 0; a < n;) {
+                size_t b = a + 1;
+                while (b < n && same_name(offs[b], offs[a])) ++b;
+                bool art = false;
+                for (size_t k = a; k < b; ++k) { ++st.read_count; if (have[k]) { st.parse(rsv[k]); if (rsv[k] & 6) art = true; } }
+                for (size_t k = a; k < b; ++k) keep[k] = art ? 0 : 1;
+                a = b;
+            }
+        } else {
+            for (size_t k = 0; k < n; ++k) {
+                ++st.read_count;
+                if (!have[k]) continue;
+                st.parse(rsv[k]);
+                keep[k] = (rsv[k] & 6) ? 0 : 1;
+            }
+        }
+        // the surviving records, converted side by side and written in order
+        const int T = (int)std::max<long>(1, std::min<long>(threads, (long)n / 256));
+        part.assign((size_t)T, std::string());
+        int enc = 0;
+#pragma omp parallel for schedule(static, 1) reduction(| : bad, enc) num_threads(T)
+        for (int t = 0; t < T; ++t) {
+            std::string &o = part[(size_t)t];
+            std::string line, rec;
+            for (size_t k = n * (size_t)t / (size_t)T; k < n * (size_t)(t + 1) / (size_t)T; ++k) {
+                if (!keep[k]) continue;
+                const uint8_t *p = &sb[offs[k]];
+                const uint32_t bs = get_u32(p);
+                if (keep[k] == 1 && con != 0) { o.append(reinterpret_cast<const char *>(p), 4 + (size_t)bs); continue; }
+                LineRec lr;
+                if (!samio::bam_to_sam(p + 4, bs, in.hdr, lr.line)) { bad = 1; continue; }
+                if (keep[k] == 2) {
+                    if (!lr.index()) { bad = 1; continue; }
+                    lr.line = clip_read(lr.split(), rsv[k], sam).line();
+                }
+                if (con == 0) { o += lr.line; o += '\n'; continue; }
+                if (!samio::sam_to_bam(lr.line, in.hdr, rec)) { enc = 1; continue; }
+                samio::put_u32(o, (uint32_t)rec.size());
+                o += rec;
+            }
+        }
+        if (bad) return damaged();
+        if (enc) unencodable = true;
+        if (con == 0) for (const auto &o : part) fwrite(o.data(), 1, o.size(), stdout);
+        else {
+            size_t tot = 0;
+            for (const auto &o : part) tot += o.size();
+            all.clear();
+            all.reserve(tot);
+            for (const auto &o : part) all += o;
+            if (!all.empty()) bamfast::write_blocks(stdout, reinterpret_cast<const uint8_t *>(all.data()), all.size(), con == 1 ? 0 : samio::kFastLevel, threads);
+        }
+        const size_t consumed = n < offs.size() ? offs[n] : end;
+        in.stream.erase(in.stream.begin(), in.stream.begin() + (long)consumed);
+        in.spos = 0;
+        if (eof && n == offs.size()) break;
+    }
+    if (con != 0) bamfast::write_eof_marker();
+    if (fflush(stdout) != 0 || ferror(stdout)) { fprintf(stderr, "fade-b200: write error\n"); return 1; }
+    st.print();
+    if (unencodable) { fprintf(stderr, "fade-b200: a clipped record could not be encoded for BAM output\n"); return 1; }
+    return 0;
+}
+
 int cmd_out(int argc, char **argv, const std::string &cl)
 {
     const Options opt = parse_options(argc, argv, 2, { { 'c', "clip", false }, { 't', "threads", true }, { 'h', "help", false },
@@ -718,6 +892,17 @@ int cmd_out(int argc, char **argv, const std::string &cl)
     const std::string path = opt.pos[0];
     int con = 0;
     if (!output_container(opt, con)) return 1;
+    {   // BAM input (a gzip member starts with 0x1f, SAM text never does) takes the binary route
+        FILE *f = path == "-" ? stdin : fopen(path.c_str(), "rb");
+        if (!f) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
+        const int c0 = fgetc(f);
+        if (c0 != EOF) ungetc(c0, f);
+        if (c0 == 0x1f) {
+            const int threads = (int)opt.num("threads", 0) > 0 ? (int)opt.num("threads", 0) : omp_get_max_threads();
+            return out_bam_input(f, path, clip, con, threads, cl);
+        }
+        if (f != stdin) fclose(f);
+    }
     open_output(con);
     Sam sam;
     if (!sam.open(path)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }

@@ -227,3 +227,48 @@ def test_sort_refuses_damaged_input(tmp_path):
     for args in (["sort", "-n"], ["sort", "-nb"]):
         p = subprocess.run([BIN, *args, "-"], input=bamcodec.bgzf_blocks(bytes(payload)) + raw[-28:], capture_output=True)
         assert p.returncode == 1 and b"malformed" in p.stderr
+
+
+def test_out_on_bam_input_equals_out_on_sam_input(tmp_path, monkeypatch):
+    """BAM input takes a binary route through `out` (records copied as bytes, only clipped ones through text); SAM input
+    the text route.  Both must give the same records, statistics and warnings: name-sorted and unsorted input, -c, all
+    three containers, the file read in pieces of a single BGZF block (read groups then straddle the pieces), a giant
+    read group, fewer than ten records, none at all, and rs tags of unusual types."""
+    import bamcodec
+
+    def both(lines, args):
+        sam = ("\n".join(lines) + "\n").encode()
+        bam = bamcodec.encode(lines)
+        outs = []
+        for src in (sam, bam):
+            p = subprocess.run([BIN, *args, "-"], input=src, capture_output=True)
+            assert p.returncode == 0, p.stderr
+            raw = p.stdout
+            if raw[:2] == b"\x1f\x8b":
+                raw = "\n".join(bamcodec.decode(raw)).encode()
+            outs.append(([ln for ln in raw.decode().splitlines() if not ln.startswith("@PG")], p.stderr))
+        assert outs[0] == outs[1], args
+        return outs[0][0]
+
+    monkeypatch.setenv("FADE_IO_BLOCKS", "1")
+    for name_sorted in (True, False):
+        d = tmp_path / str(name_sorted)
+        d.mkdir()
+        path, _ = annotated_sam(d, n=3000, name_sorted=name_sorted)
+        lines = open(path).read().splitlines()
+        n_in = sum(not ln.startswith("@") for ln in lines)
+        for args in (["out"], ["out", "-c"], ["out", "-b"], ["out", "-cb"], ["out", "-u"]):
+            got = both(lines, args)
+            n_out = sum(not ln.startswith("@") for ln in got)
+            assert (n_out == n_in) if "-c" in args or "-cb" in args else (0 < n_out < n_in)
+    head = [ln for ln in lines if ln.startswith("@")]
+    body = [ln for ln in lines if not ln.startswith("@")]
+    giant = [("same\t" + ln.split("\t", 1)[1]) for ln in body[:1500]]          # one read group larger than any piece
+    both(head + giant, ["out", "-b"]); both(head + giant, ["out"])
+    for few in (body[:3], []):
+        both(head + few, ["out"]); both(head + few, ["out", "-cb"])
+    odd = []
+    for k, ln in enumerate(body[:40]):
+        f = [x for x in ln.split("\t") if not x.startswith("rs:")]
+        odd.append("\t".join(f + [["rs:Z:3", "rs:A:7", "rs:f:5", "rs:i:300", "rs:Z:junk"][k % 5]]))
+    both(head + odd, ["out"]); both(head + odd, ["out", "-b"])
