@@ -971,6 +971,30 @@ int cmd_out(int argc, char **argv, const std::string &cl)
     return (close_output() || put_failed) ? 1 : 0;   // a record that cannot be encoded for the chosen container is an error, not a silent drop
 }
 
+// BAM records `extract` has no use for: an integer rs tag without an artifact bit, or no rs tag at all (remap.d:29-33).
+// Anything unusual (damaged sizes, an rs tag of another type) is NOT skipped, so the text route below sees and judges it.
+bool no_artifact_bits(const uint8_t *p, size_t n)
+{
+    if (n < 32) return false;
+    const uint64_t l_name = p[8], n_cig = bamfast::get_u16(p + 12);
+    const int64_t l_seq = bamfast::get_i32(p + 16);
+    if (l_seq < 0 || 32 + l_name + 4 * n_cig + (uint64_t)(l_seq + 1) / 2 + (uint64_t)l_seq > n) return false;
+    const uint8_t *a = p + 32 + l_name + 4 * n_cig + (uint64_t)(l_seq + 1) / 2 + (uint64_t)l_seq, *const e = p + n;
+    while (a < e) {
+        const size_t sz = bamfast::aux_field_size(a, e);
+        if (!sz) return false;
+        if (a[0] == 'r' && a[1] == 's') {
+            switch (a[2]) {
+            case 'c': case 'C': return !(a[3] & 6);
+            case 's': case 'S': case 'i': case 'I': return !(a[3] & 6);   // little endian: the low byte comes first
+            default: return false;
+            }
+        }
+        a += sz;
+    }
+    return true;
+}
+
 int cmd_extract(int argc, char **argv, const std::string &cl)
 {
     const Options opt = parse_options(argc, argv, 2, { { 't', "threads", true }, { 'h', "help", false }, { 'b', "bam", false },
@@ -982,6 +1006,7 @@ int cmd_extract(int argc, char **argv, const std::string &cl)
     if (!output_container(opt, con)) return 1;
     open_output(con);
     Sam sam;
+    sam.in.skip_records_if(no_artifact_bits);
     if (!sam.open(path)) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
     write_header(sam, "fade-extract", cl);
     static const char comp[] = "=TGKCYSBAWRDMHVN";   // complement of "=ACMGRSVTWYHKDBN" (util.d:18-21)

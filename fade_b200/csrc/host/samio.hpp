@@ -498,6 +498,9 @@ public:
         if (f_ && f_ != stdin) fclose(f_);
     }
     bool is_bam() const { return bam_; }
+    // BAM input only: records for which skip(record bytes after block_size, length) holds are not converted to text and
+    // come out of getline() as empty lines (a caller that needs one record in ten saves nine conversions); set before open()
+    void skip_records_if(bool (*skip)(const uint8_t *, size_t)) { skip_ = skip; }
     bool failed() const { return fail_ || (bz_ && bz_->bad()); }
     // next SAM text line (header lines first); false at the end
     bool getline(std::string &line)
@@ -534,8 +537,12 @@ private:
         q_.resize((size_t)n);
         int bad = 0;
 #pragma omp parallel for schedule(static) reduction(| : bad) if (n > 256)
-        for (long k = 0; k < n; ++k)
-            if (!bam_to_sam(raw_.data() + off_[(size_t)k], off_[(size_t)k + 1] - off_[(size_t)k], hdr_, q_[(size_t)k])) bad |= 1;
+        for (long k = 0; k < n; ++k) {
+            const uint8_t *rec = raw_.data() + off_[(size_t)k];
+            const size_t len = off_[(size_t)k + 1] - off_[(size_t)k];
+            if (skip_ && skip_(rec, len)) { q_[(size_t)k].clear(); continue; }   // served as an empty line, which the callers pass over
+            if (!bam_to_sam(rec, len, hdr_, q_[(size_t)k])) bad |= 1;
+        }
         if (bad) {   // serve the records before the first damaged one, then fail
             fail_ = true;
             std::string tmp;
@@ -546,6 +553,7 @@ private:
         return !q_.empty();
     }
     static constexpr size_t kBatch = 1 << 15;
+    bool (*skip_)(const uint8_t *, size_t) = nullptr;
     std::vector<std::string> q_;
     size_t q_pos_ = 0;
     std::vector<uint8_t> raw_;

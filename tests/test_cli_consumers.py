@@ -229,7 +229,7 @@ def test_sort_refuses_damaged_input(tmp_path):
         assert p.returncode == 1 and b"malformed" in p.stderr
 
 
-def test_out_on_bam_input_equals_out_on_sam_input(tmp_path, monkeypatch):
+def test_out_and_extract_on_bam_input_equal_those_on_sam_input(tmp_path, monkeypatch):
     """BAM input takes a binary route through `out` (records copied as bytes, only clipped ones through text); SAM input
     the text route.  Both must give the same records, statistics and warnings: name-sorted and unsorted input, -c, all
     three containers, the file read in pieces of a single BGZF block (read groups then straddle the pieces), a giant
@@ -272,3 +272,7 @@ def test_out_on_bam_input_equals_out_on_sam_input(tmp_path, monkeypatch):
         f = [x for x in ln.split("\t") if not x.startswith("rs:")]
         odd.append("\t".join(f + [["rs:Z:3", "rs:A:7", "rs:f:5", "rs:i:300", "rs:Z:junk"][k % 5]]))
     both(head + odd, ["out"]); both(head + odd, ["out", "-b"])
+    # extract skips BAM records without artifact bits before they are converted to text: same output as from SAM input
+    for args in (["extract"], ["extract", "-b"]):
+        assert sum(not ln.startswith("@") for ln in both(lines, args)) > 50
+        both(head + odd, args); both(head, args)
