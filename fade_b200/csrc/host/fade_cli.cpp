@@ -770,6 +770,7 @@ int out_bam_input(FILE *f, const std::string &path, bool clip, int con, int thre
                                        : "[W::fade-out] Output doesn't look name-sorted, ejecting by only reads with an artifact\n");
         }
         size_t n = offs.size();
+        if (n == 0 && !eof) continue;    // only the front of one record so far
         if (!clip && sorted && !eof) {   // the last read group may continue in the part of the file not read yet
             const size_t tail = offs.back();
             while (n > 0 && same_name(offs[n - 1], tail)) --n;
