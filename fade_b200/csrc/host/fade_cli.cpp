@@ -1183,14 +1183,19 @@ int cmd_view(int argc, char **argv)
     const bool bulk = opt.has("bulk");      // through the parallel readers / writers of the annotate loop
     int con = 0;
     if (!output_container(opt, con)) return 1;
-    if (bulk || opt.has("count")) {
+    {   // BAM input always takes the parallel route (--bulk asks for it on SAM text as well)
         FILE *f = path == "-" ? stdin : fopen(path.c_str(), "rb");
         if (!f) { fprintf(stderr, "fade-b200: cannot read %s\n", path.c_str()); return 1; }
-        std::string pre(2, '\0');
-        pre.resize(fread(&pre[0], 1, 2, f));
-        const bool is_bam = pre.size() == 2 && (uint8_t)pre[0] == 0x1f && (uint8_t)pre[1] == 0x8b;
-        if (opt.has("count")) return bamfast::count_records(f, pre, is_bam, threads > 0 ? threads : omp_get_max_threads());
-        return bamfast::copy_records(f, pre, is_bam, con, threads > 0 ? threads : omp_get_max_threads());
+        const int c0 = fgetc(f);
+        if (c0 != EOF) ungetc(c0, f);      // a gzip member starts with 0x1f, SAM text never does
+        if (c0 == 0x1f || bulk || opt.has("count")) {
+            std::string pre(2, '\0');
+            pre.resize(fread(&pre[0], 1, 2, f));
+            const bool is_bam = pre.size() == 2 && (uint8_t)pre[0] == 0x1f && (uint8_t)pre[1] == 0x8b;
+            if (opt.has("count")) return bamfast::count_records(f, pre, is_bam, threads > 0 ? threads : omp_get_max_threads());
+            return bamfast::copy_records(f, pre, is_bam, con, threads > 0 ? threads : omp_get_max_threads());
+        }
+        if (f != stdin) fclose(f);
     }
     open_output(con);
     samio::LineSource in;
