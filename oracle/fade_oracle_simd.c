@@ -39,25 +39,27 @@ typedef struct {
     size_t cap_q, cap_t, cap_tr;
 } simd_ws;
 
+static void *alloc64(size_t bytes) { return aligned_alloc(64, (bytes + 63) & ~(size_t)63); }
+
 static void ws_reserve(simd_ws *w, int qmax, int tmax, int lanes)
 {
     if ((size_t)qmax > w->cap_q) {
         free(w->q); free(w->H); free(w->E);
         w->cap_q = (size_t)qmax + 64;
-        w->q = (int16_t *)aligned_alloc(64, w->cap_q * lanes * 2);
-        w->H = (int16_t *)aligned_alloc(64, w->cap_q * lanes * 2);
-        w->E = (int16_t *)aligned_alloc(64, w->cap_q * lanes * 2);
+        w->q = (int16_t *)alloc64(w->cap_q * lanes * 2);
+        w->H = (int16_t *)alloc64(w->cap_q * lanes * 2);
+        w->E = (int16_t *)alloc64(w->cap_q * lanes * 2);
     }
     if ((size_t)tmax > w->cap_t) {
         free(w->t);
         w->cap_t = (size_t)tmax + 256;
-        w->t = (int16_t *)aligned_alloc(64, w->cap_t * lanes * 2);
+        w->t = (int16_t *)alloc64(w->cap_t * lanes * 2);
     }
     const size_t need = (size_t)qmax * tmax * lanes;
     if (need > w->cap_tr) {
         free(w->tr);
         w->cap_tr = need + need / 4;
-        w->tr = (uint8_t *)aligned_alloc(64, (w->cap_tr + 63) & ~(size_t)63);
+        w->tr = (uint8_t *)alloc64(w->cap_tr);
     }
 }
 
