@@ -73,7 +73,7 @@ static void simd_sw16(simd_ws *w, int qmax, int tmax, const fo_params *p,
     const __m256i vmatch = _mm256_set1_epi16((short)p->match), vmis = _mm256_set1_epi16((short)p->mismatch);
     const __m256i zero = _mm256_setzero_si256();
     const __m256i neg = _mm256_set1_epi16(-20000);
-    const __m256i c1 = _mm256_set1_epi16(1), c2 = _mm256_set1_epi16(2), c3 = _mm256_set1_epi16(3);
+    const __m256i c1 = _mm256_set1_epi16(1), c3 = _mm256_set1_epi16(3);
     const __m256i c4 = _mm256_set1_epi16(4), c8 = _mm256_set1_epi16(8);
     enum { LANES = 16 };
     /* locals: the byte stores into the trace table may alias *w as far as the compiler knows */
@@ -86,6 +86,10 @@ static void simd_sw16(simd_ws *w, int qmax, int tmax, const fo_params *p,
         const __m256i tv = _mm256_load_si256((const __m256i *)(wt + (size_t)j * LANES));
         const __m256i vj = _mm256_set1_epi16((short)j);
         __m256i hdiag = zero, hup = zero, f = neg;
+        /* end cell, first column then first row, strictly greater only: inside a column only the first row that beats
+         * everything before it is tracked (cbest starts at the best of the earlier columns); the column number and the
+         * global best are updated once per column */
+        __m256i cbest = best, ci = zero, vi = zero;
         uint8_t *trj = wtr + (size_t)j * qmax * LANES;   /* column after column: the stores are sequential */
         for (int i = 0; i < qmax; ++i) {
             const __m256i qv = _mm256_load_si256((const __m256i *)(wq + (size_t)i * LANES));
@@ -100,24 +104,27 @@ static void simd_sw16(simd_ws *w, int qmax, int tmax, const fo_params *p,
             const __m256i s = _mm256_blendv_epi8(vmis, vmatch, _mm256_cmpeq_epi16(qv, tv));
             const __m256i hd = _mm256_max_epi16(_mm256_adds_epi16(hdiag, s), zero);
             const __m256i h = _mm256_max_epi16(_mm256_max_epi16(hd, ev), fv);
-            /* source priority DIAG/ZERO > F > E */
+            /* source priority DIAG/ZERO > F > E; the comparison masks are 0 / -1, so 3 + is_f is E or F and 1 + is_z
+             * is DIAG or ZERO */
             const __m256i is_d = _mm256_cmpeq_epi16(h, hd), is_f = _mm256_cmpeq_epi16(h, fv);
             const __m256i is_z = _mm256_cmpeq_epi16(h, zero);
-            __m256i src = _mm256_blendv_epi8(c3, c2, is_f);
-            src = _mm256_blendv_epi8(src, _mm256_andnot_si256(is_z, c1), is_d);
+            const __m256i src = _mm256_blendv_epi8(_mm256_add_epi16(c3, is_f), _mm256_add_epi16(c1, is_z), is_d);
             __m256i tb = _mm256_or_si256(src, _mm256_or_si256(_mm256_and_si256(eo, c4), _mm256_and_si256(fo, c8)));
             /* 16 x int16 -> 16 bytes */
             const __m256i pk = _mm256_packus_epi16(tb, tb);
             const __m128i lo = _mm256_castsi256_si128(pk), hi = _mm256_extracti128_si256(pk, 1);
             _mm_storeu_si128((__m128i *)(trj + (size_t)i * LANES), _mm_unpacklo_epi64(lo, hi));
-            /* end cell: first column, then first row (strictly greater only) */
-            const __m256i gt = _mm256_cmpgt_epi16(h, best);
-            best = _mm256_max_epi16(best, h);
-            bi = _mm256_blendv_epi8(bi, _mm256_set1_epi16((short)i), gt);
-            bj = _mm256_blendv_epi8(bj, vj, gt);
+            const __m256i gt = _mm256_cmpgt_epi16(h, cbest);
+            cbest = _mm256_max_epi16(cbest, h);
+            ci = _mm256_blendv_epi8(ci, vi, gt);
+            vi = _mm256_add_epi16(vi, c1);
             hdiag = hleft; hup = h; f = fv;
             E[i] = ev; H[i] = h;
         }
+        const __m256i upd = _mm256_cmpgt_epi16(cbest, best);
+        best = cbest;
+        bi = _mm256_blendv_epi8(bi, ci, upd);
+        bj = _mm256_blendv_epi8(bj, vj, upd);
     }
     int16_t b[LANES], xi[LANES], xj[LANES];
     _mm256_storeu_si256((__m256i *)b, best); _mm256_storeu_si256((__m256i *)xi, bi); _mm256_storeu_si256((__m256i *)xj, bj);
@@ -133,7 +140,7 @@ static void simd_sw32(simd_ws *w, int qmax, int tmax, const fo_params *p,
     const __m512i vo = _mm512_set1_epi16((short)p->gap_open), ve = _mm512_set1_epi16((short)p->gap_extend);
     const __m512i vmatch = _mm512_set1_epi16((short)p->match), vmis = _mm512_set1_epi16((short)p->mismatch);
     const __m512i zero = _mm512_setzero_si512();
-    const __m512i neg = _mm512_set1_epi16(-20000);
+    const __m512i neg = _mm512_set1_epi16(-20000), one = _mm512_set1_epi16(1);
     const __m256i b1 = _mm256_set1_epi8(1), b2 = _mm256_set1_epi8(2), b3 = _mm256_set1_epi8(3);
     const __m256i b4 = _mm256_set1_epi8(4), b8 = _mm256_set1_epi8(8);
     __m512i *const H = (__m512i *)w->H, *const E = (__m512i *)w->E;
@@ -145,6 +152,7 @@ static void simd_sw32(simd_ws *w, int qmax, int tmax, const fo_params *p,
         const __m512i tv = _mm512_load_si512((const void *)(wt + (size_t)j * LANES));
         const __m512i vj = _mm512_set1_epi16((short)j);
         __m512i hdiag = zero, hup = zero, f = neg;
+        __m512i cbest = best, ci = zero, vi = zero;      /* end cell as in simd_sw16 */
         uint8_t *trj = wtr + (size_t)j * qmax * LANES;   /* column after column: the stores are sequential */
         for (int i = 0; i < qmax; ++i) {
             const __m512i qv = _mm512_load_si512((const void *)(wq + (size_t)i * LANES));
@@ -165,14 +173,17 @@ static void simd_sw32(simd_ws *w, int qmax, int tmax, const fo_params *p,
             tb = _mm256_mask_mov_epi8(tb, is_d, _mm256_maskz_mov_epi8(is_nz, b1));
             tb = _mm256_or_si256(tb, _mm256_or_si256(_mm256_maskz_mov_epi8(eo, b4), _mm256_maskz_mov_epi8(fo, b8)));
             _mm256_storeu_si256((__m256i *)(trj + (size_t)i * LANES), tb);
-            /* end cell: first column, then first row (strictly greater only) */
-            const __mmask32 gt = _mm512_cmpgt_epi16_mask(h, best);
-            best = _mm512_max_epi16(best, h);
-            bi = _mm512_mask_mov_epi16(bi, gt, _mm512_set1_epi16((short)i));
-            bj = _mm512_mask_mov_epi16(bj, gt, vj);
+            const __mmask32 gt = _mm512_cmpgt_epi16_mask(h, cbest);
+            cbest = _mm512_max_epi16(cbest, h);
+            ci = _mm512_mask_mov_epi16(ci, gt, vi);
+            vi = _mm512_add_epi16(vi, one);
             hdiag = hleft; hup = h; f = fv;
             E[i] = ev; H[i] = h;
         }
+        const __mmask32 upd = _mm512_cmpgt_epi16_mask(cbest, best);
+        best = cbest;
+        bi = _mm512_mask_mov_epi16(bi, upd, ci);
+        bj = _mm512_mask_mov_epi16(bj, upd, vj);
     }
     int16_t b[LANES], xi[LANES], xj[LANES];
     _mm512_storeu_si512((void *)b, best); _mm512_storeu_si512((void *)xi, bi); _mm512_storeu_si512((void *)xj, bj);
