@@ -62,6 +62,15 @@ def test_reannotation_and_the_consumer_chain(preload, tmp_path):
     test_gpu_cli.test_end_to_end_chain_annotate_out_extract(tmp_path / "b")
 
 
+def test_bam_routes_of_the_driver(preload, tmp_path):
+    """BAM in / out, --text-path, re-annotation of an annotated BAM, `annotate -b | out -c -b`, and records of every
+    shape (all aux types, '*' fields, several contigs) through the binary and the text loop"""
+    import test_gpu_cli
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    test_gpu_cli.test_cli_annotate_reads_and_writes_bam(tmp_path / "a")
+    test_gpu_cli.test_binary_bam_path_equals_text_path_on_rich_records(tmp_path / "b")
+
+
 def test_ring_over_several_devices_keeps_input_order(preload, tmp_path):
     """anno.d:44-50's one writer: with 1, 2 and 3 devices and batches far smaller than the file (so that the ring wraps
     many times and ends on a partial round) the output is byte for byte the same, for SAM, uBAM and BAM output and for
